@@ -1,0 +1,232 @@
+"""Generate tests/golden/*.npz by running the REFERENCE ITSELF on seeded inputs.
+
+Run only in the build container (needs /root/reference; the GPU box has no
+reference tree):  ``python oracle/make_golden.py``
+
+What is imported from the reference, unmodified:
+  * ``src/mtmvar.py``            (matplotlib stubbed -- numerics never touch it)
+  * ``src/dataloader.py``        ``_design_eeg_filters`` / ``_apply_filters``
+  * ``src/data_structures.py``   ``MultimodalData._decimate_signals``
+  * ``src/eeg_alpha_ibi_ffdtf.py`` ``EEG_IBI_FFDTF_Pipeline._create_windows``
+Third-party modules that are absent here (mne, xarray, neurokit2, xmltodict,
+matplotlib, ...) are replaced by empty stubs: none of them is touched by the
+functions called below.  ``mne_bridge.load_eeg_signals`` needs a NetCDF file
+and xarray, so its filter block (mne_bridge.py:158-184) is reproduced with the
+same SciPy calls.  ``psd.compute_psd_multitaper`` is a one-line call into mne
+(absent) -> no golden vector from the reference; see frontend_oracle header.
+"""
+from __future__ import annotations
+
+import contextlib
+import importlib
+import io
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+class _Stub(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        sub = _Stub(self.__name__ + "." + name)
+        setattr(self, name, sub)
+        return sub
+
+    def __call__(self, *a, **k):
+        return None
+
+
+def import_reference():
+    for name in ("matplotlib", "matplotlib.pyplot", "mne", "mne.time_frequency", "xmltodict", "neurokit2",
+                 "xarray", "joblib", "plotly", "plotly.graph_objects", "plotly.subplots", "netCDF4",
+                 "autoreject", "mne_icalabel", "specparam", "seaborn"):
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except Exception:
+                sys.modules[name] = _Stub(name)
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from src import mtmvar, dataloader, data_structures
+    try:
+        from src import eeg_alpha_ibi_ffdtf
+    except Exception as exc:          # pragma: no cover
+        print("eeg_alpha_ibi_ffdtf not importable:", exc)
+        eeg_alpha_ibi_ffdtf = None
+    return mtmvar, dataloader, data_structures, eeg_alpha_ibi_ffdtf
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def main():
+    sys.path.insert(0, ROOT)
+    from hyperscanning_signal_analysis_b200 import synth
+    from scipy import signal
+    import scipy
+
+    mtmvar, dataloader, ds, ffd = import_reference()
+    os.makedirs(OUT, exist_ok=True)
+    versions = f"numpy {np.__version__} scipy {scipy.__version__}"
+
+    # ---------------------------------------------------------------- MVAR, small (the reference's real use: m=4, fs=8, p=5)
+    rng = np.random.default_rng(7)
+    m, n, p, fs = 4, 480, 5, 8.0
+    x = np.zeros((m, n))
+    e = rng.standard_normal((m, n))
+    a1 = np.array([[0.5, 0.2, 0, 0], [0, 0.4, 0.3, 0], [0, 0, -0.3, 0.2], [0.25, 0, 0, 0.35]])
+    for t in range(1, n):
+        x[:, t] = a1 @ x[:, t - 1] + e[:, t]
+    freqs = np.arange(0.1, 4.0 + 0.13, 0.13)
+    A, V = mtmvar.ar_coeff(x, p)
+    H, Af = mtmvar.mvar_transfer_function(A, freqs, fs)
+    rl, rr, r0 = mtmvar.count_corr(x[:, :, None], p, 1)
+    np.savez_compressed(
+        os.path.join(OUT, "mvar_m4.npz"), versions=versions, x=x, p=p, fs=fs, freqs=freqs,
+        r_left=rl, r_right=rr, r_zero=r0, A=A, V=V, H=H, Af=Af,
+        dtf=quiet(mtmvar.dtf_multivariate, x, freqs, fs, optimal_model_order=p),
+        ffdtf=quiet(mtmvar.full_freq_dtf, x, freqs, fs, optimal_model_order=p),
+        S=quiet(mtmvar.multivariate_spectra, x, freqs, fs, optimal_model_order=p),
+        gpdc=quiet(mtmvar.gen_partial_directed_coherence, x, freqs, fs, optimal_model_order=p),
+        crit_aic=mtmvar.mvar_criterion(x, 8, "AIC", False)[0],
+        crit_hq=mtmvar.mvar_criterion(x, 8, "HQ", False)[0],
+        crit_sc=mtmvar.mvar_criterion(x, 8, "SC", False)[0],
+        popt=np.array([mtmvar.mvar_criterion(x, 8, c, False)[2] for c in ("AIC", "HQ", "SC")]),
+    )
+
+    # ---------------------------------------------------------------- MVAR, multi-trial (3-D ar_coeff path)
+    rng = np.random.default_rng(11)
+    xt = rng.standard_normal((7, 96, 5))
+    xt[:, 1:, :] += 0.6 * xt[:, :-1, :]
+    A, V = mtmvar.ar_coeff(xt, 3)
+    rl, rr, r0 = mtmvar.count_corr(xt, 3, 1)
+    np.savez_compressed(os.path.join(OUT, "mvar_trials.npz"), versions=versions, x=xt, p=3, A=A, V=V,
+                        r_left=rl, r_right=rr, r_zero=r0)
+
+    # ---------------------------------------------------------------- filters (cfg1 generator, 4 channels x 3000 samples)
+    raw = synth.dyad_eeg(seed=synth.BASE_SEED, m=38, fs=256.0, n_samples=3000)
+    md = ds.MultimodalData()
+    md.fs = 256.0
+    names_ch = [f"c{i}" for i in range(19)]
+    names_cg = [f"c{i}_cg" for i in range(19)]
+    md.eeg_channel_names_ch = names_ch
+    md.eeg_channel_names_cg = names_cg
+    md.eeg_channel_mapping = {nm: i for i, nm in enumerate(names_ch + names_cg)}
+    filters = dataloader._design_eeg_filters(md, lowcut=1.0, highcut=40.0, filter_type="iir")
+    filt = raw.copy()
+    quiet(dataloader._apply_filters, md, filters, filt)
+    sel = [0, 7, 19, 37]
+    (bn, an), (bl, al), (bh, ah), _ = filters
+    np.savez_compressed(os.path.join(OUT, "filters_iir.npz"), versions=versions, fs=256.0, raw=raw[sel], out=filt[sel],
+                        b_notch=bn, a_notch=an, b_low=bl, a_low=al, b_high=bh, a_high=ah,
+                        applied=np.array([md.eeg_filtration.notch["applied"], md.eeg_filtration.low_pass["applied"],
+                                          md.eeg_filtration.high_pass["applied"]]))
+    # the reference's own unit-test input (tests/test_dataloader.py:181-197): 10 Hz + 60 Hz, fs 256, n 1000
+    tt = np.arange(1000) / 256.0
+    sig = np.sin(2 * np.pi * 10 * tt) + 0.5 * np.sin(2 * np.pi * 60 * tt) + 3.0
+    md2 = ds.MultimodalData()
+    md2.fs = 256.0
+    md2.eeg_channel_names_ch = ["Fz"]
+    md2.eeg_channel_names_cg = []
+    md2.eeg_channel_mapping = {"Fz": 0}
+    f2 = dataloader._design_eeg_filters(md2, lowcut=1.0, highcut=40.0, filter_type="iir")
+    buf = sig[None, :].copy()
+    quiet(dataloader._apply_filters, md2, f2, buf)
+    np.savez_compressed(os.path.join(OUT, "filters_unit.npz"), versions=versions, fs=256.0, raw=sig[None, :], out=buf)
+
+    # mne_bridge filter block (order-4 Butterworth + notch Q=15), (time, channel) layout, same SciPy calls as mne_bridge.py:158-184
+    tc = raw[[1, 20, 30]].T.copy()
+    d = tc.copy()
+    b, a = signal.butter(4, 1.0 / 128.0, btype="highpass"); d = signal.filtfilt(b, a, d, axis=0)
+    b, a = signal.butter(4, 45.0 / 128.0, btype="lowpass"); d = signal.filtfilt(b, a, d, axis=0)
+    b, a = signal.iirnotch(50.0, Q=15, fs=256.0); d = signal.filtfilt(b, a, d, axis=0)
+    np.savez_compressed(os.path.join(OUT, "filters_bridge.npz"), versions=versions, fs=256.0, low=1.0, high=45.0, raw=tc, out=d)
+
+    # ---------------------------------------------------------------- decimation through the real MultimodalData._decimate_signals
+    import pandas as pd
+    raw4 = synth.dyad_eeg(seed=synth.BASE_SEED + 4, m=4, fs=1024.0, n_samples=4099, drift=True)
+    md3 = ds.MultimodalData()
+    md3.fs = 1024.0
+    md3.id = "W_000"
+    md3.eeg_channel_names_ch = ["Fz", "Cz"]
+    md3.eeg_channel_names_cg = ["Fz_cg"]
+    md3.eeg_channel_mapping = {"Fz": 0, "Cz": 1, "Fz_cg": 2}
+    withnan = raw4[3].copy()
+    withnan[:5] = np.nan
+    withnan[1000:1040] = np.nan
+    md3.data = pd.DataFrame({
+        "time": np.arange(4099) / 1024.0, "time_idx": np.arange(4099),
+        "EEG_ch_Fz": raw4[0], "EEG_ch_Cz": raw4[1], "EEG_cg_Fz": raw4[2], "IBI_ch": withnan,
+        "events": np.array([None] * 4099, dtype=object), "diode": (np.arange(4099) % 7).astype(float),
+    })
+    dec = quiet(md3._decimate_signals, q=8)
+    np.savez_compressed(os.path.join(OUT, "decimate_q8.npz"), versions=versions, q=8, fs_in=1024.0, fs_out=dec.fs,
+                        raw=np.stack([raw4[0], raw4[1], raw4[2], withnan]),
+                        out=np.stack([dec.data[c].values for c in ("EEG_ch_Fz", "EEG_ch_Cz", "EEG_cg_Fz", "IBI_ch")]),
+                        time=dec.data["time"].values, diode=dec.data["diode"].values)
+    # the reference unit-test shape (tests/test_data_structures.py:305-339): n=1000, q=4
+    md4 = ds.MultimodalData()
+    md4.fs = 256.0
+    xs = np.sin(2 * np.pi * 5 * np.arange(1000) / 256.0)
+    md4.data = pd.DataFrame({"time": np.arange(1000) / 256.0, "time_idx": np.arange(1000), "EEG_ch_Fz": xs})
+    dec4 = quiet(md4._decimate_signals, q=4)
+    np.savez_compressed(os.path.join(OUT, "decimate_q4.npz"), versions=versions, q=4, raw=xs[None], out=dec4.data["EEG_ch_Fz"].values[None],
+                        fs_out=dec4.fs)
+
+    # ---------------------------------------------------------------- MVAR at the BASELINE shape: cfg1 pipeline, two 2-s windows, F=32 grid
+    x1 = synth.cfg1_raw()
+    md5 = ds.MultimodalData()
+    md5.fs = 256.0
+    md5.eeg_channel_names_ch = names_ch
+    md5.eeg_channel_names_cg = names_cg
+    md5.eeg_channel_mapping = {nm: i for i, nm in enumerate(names_ch + names_cg)}
+    f5 = dataloader._design_eeg_filters(md5, lowcut=1.0, highcut=40.0, filter_type="iir")
+    y1 = x1.copy()
+    quiet(dataloader._apply_filters, md5, f5, y1)
+    fgrid = np.linspace(0, 128, 32, endpoint=False)
+    starts = np.array([1024, 9000])
+    wins = np.stack([y1[:, s:s + 512] for s in starts])
+    As, Vs, ffs, conds = [], [], [], []
+    for w in wins:
+        A, V = mtmvar.ar_coeff(w, 8)
+        As.append(A); Vs.append(V)
+        ffs.append(quiet(mtmvar.full_freq_dtf, w, fgrid, 256.0, optimal_model_order=8))
+        conds.append(np.linalg.cond(mtmvar.count_corr(w[:, :, None], 8, 1)[0]))
+    np.savez_compressed(os.path.join(OUT, "mvar_cfg2_windows.npz"), versions=versions, windows=wins, starts=starts, p=8, fs=256.0,
+                        freqs=fgrid, A=np.stack(As), V=np.stack(Vs), ffdtf=np.stack(ffs).astype(np.float64), cond=np.array(conds))
+    # whole 60-s segment (cfg1), F=16 grid -> small file; input regenerated from synth in the test (checked by checksum)
+    f16 = np.linspace(0, 128, 16, endpoint=False)
+    A, V = mtmvar.ar_coeff(y1, 8)
+    np.savez_compressed(os.path.join(OUT, "mvar_cfg1.npz"), versions=versions, p=8, fs=256.0, freqs=f16, A=A, V=V,
+                        filtered_rows=y1[[0, 18, 19, 37]], filtered_sum=float(np.sum(y1)), raw_sum=float(np.sum(x1)),
+                        ffdtf=quiet(mtmvar.full_freq_dtf, y1, f16, 256.0, optimal_model_order=8),
+                        S=quiet(mtmvar.multivariate_spectra, y1, f16, 256.0, optimal_model_order=8),
+                        cond=np.linalg.cond(mtmvar.count_corr(y1[:, :, None], 8, 1)[0]))
+
+    # ---------------------------------------------------------------- window starts from the real _create_windows
+    if ffd is not None:
+        pipe = ffd.EEG_IBI_FFDTF_Pipeline.__new__(ffd.EEG_IBI_FFDTF_Pipeline)
+        cases = [(153600, 599, 512), (15360, 59, 512), (999, 3, None), (999, 3, 400), (777, 10, 100), (512, 1, 512)]
+        rec = {}
+        for (T, nw, ws) in cases:
+            sig = np.arange(T, dtype=float)[None, :]
+            wl = pipe._create_windows(sig, n_windows=nw, window_size=ws)
+            rec[f"T{T}_n{nw}_w{ws}"] = np.array([int(w[0, 0]) for w in wl] + [wl[0].shape[1]])
+        np.savez_compressed(os.path.join(OUT, "window_starts.npz"), versions=versions, **rec)
+
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

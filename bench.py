@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""MVAR+DTF windows/sec (2x19 ch, p=8, 256 bins) -- BASELINE.json's metric.
+
+One "step" = one pass of the hot path (lag covariances -> LWR Yule-Walker -> A(f)^-1 ->
+|H|^2 -> ffDTF) over one 10-minute synthetic TALK task: 599 windows of 2 s at 50 % overlap,
+38 channels, p = 8, 256 bins (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+N > 1: launched by torchrun, one rank per GPU; every rank owns its own dyad (weak scaling,
+no data-path collective -- windows of different dyads are independent).  The final result
+all-gather over NCCL that north_star describes is timed separately and reported under
+"allgather" (it is not part of `value`; see DESIGN.md "Multi-GPU").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M, WIN, HOP, P, F, FS = 38, 512, 256, 8, 256, 256.0
+TASK_SECONDS = 600
+METRIC = "MVAR+DTF windows/sec (2x19ch, p=8, 256 bins)"
+UNIT = "windows/s"
+
+
+# ------------------------------------------------------------------ workload
+def make_task(seed):
+    """Filtered synthetic task (m, T) + window starts + frequency grid."""
+    from scipy import signal
+    from hyperscanning_signal_analysis_b200 import synth
+    x = synth.cfg2_raw(seed=seed, seconds=TASK_SECONDS)
+    # notch 50 Hz (Q=30) + band 1-64 Hz, the reference's production values
+    # (scripts/export_dyade_to_ncdf_by_task_batch.py:27-31); setup only, outside every timed region
+    y = x - x.mean(axis=1, keepdims=True)
+    for b, a in (signal.iirnotch(50.0, 30.0, fs=FS), signal.butter(2, 64.0, "low", fs=FS), signal.butter(2, 1.0, "high", fs=FS)):
+        y = signal.filtfilt(b, a, y, axis=1)
+    T = y.shape[1]
+    n_win = (T - WIN) // HOP + 1
+    starts = np.linspace(0, T - WIN, n_win, dtype=int).astype(np.int64)      # _create_windows, eeg_alpha_ibi_ffdtf.py:513
+    freqs = np.linspace(0.0, FS / 2, F, endpoint=False)
+    return np.ascontiguousarray(y), starts, freqs
+
+
+def flops_per_window():
+    """Algorithmic FLOPs per window, SURVEY.md 8(d) (reference's algorithm counts)."""
+    m, n, p, f = M, WIN, P, F
+    k3 = 2 * m * m * sum(n - L for L in range(p + 1))
+    mp = m * p
+    k4 = (2 / 3) * mp ** 3 + 2 * mp ** 2 * m + 2 * m * m * mp
+    k5_asm = 4 * p * m * m * f
+    k5_inv = 8 * m ** 3 * f
+    k5_red = 5 * m * m * f
+    return {"lagcov": k3, "yule_walker": k4, "transfer": k5_asm + k5_inv, "normalise": k5_red,
+            "total": k3 + k4 + k5_asm + k5_inv + k5_red}
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for s in self.samples:
+            for nm, v in zip(names, s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        pw = [float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].replace(".", "").isdigit() else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(self.samples), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------ CPU baseline (oracle port)
+def _cpu_worker(args):
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    seg, freqs = args
+    from oracle import mvar_oracle as mo
+    return float(mo.full_freq_dtf(seg, freqs, FS, optimal_model_order=P).sum())
+
+
+def cpu_baseline(y, starts, freqs, budget_s=20.0, max_windows=None):
+    """Oracle port of full_freq_dtf (same per-bin np.linalg.inv loop as the reference) on every host core,
+    one window per task, BLAS pinned to one thread per process.  Bounded sample of the same windows."""
+    import multiprocessing as mp
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:
+        threadpool_limits = None
+    cores = os.cpu_count() or 1
+    from oracle import mvar_oracle as mo
+    # calibrate on one window, single process
+    t0 = time.perf_counter()
+    if threadpool_limits:
+        with threadpool_limits(limits=1):
+            mo.full_freq_dtf(y[:, :WIN], freqs, FS, optimal_model_order=P)
+    else:
+        mo.full_freq_dtf(y[:, :WIN], freqs, FS, optimal_model_order=P)
+    t_one = time.perf_counter() - t0
+    n = int(max(cores, min(len(starts), budget_s * cores / max(t_one, 1e-3))))
+    if max_windows:
+        n = min(n, max_windows)
+    n = min(n, len(starts))
+    segs = [(np.ascontiguousarray(y[:, s:s + WIN]), freqs) for s in starts[:n]]
+    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    os.environ["MKL_NUM_THREADS"] = "1"
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, segs[:cores])             # warm the workers
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, segs, chunksize=max(1, n // (cores * 4)))
+        dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} of {len(starts)} windows of the same task, oracle/mvar_oracle.full_freq_dtf (NumPy port of src/mtmvar.py), "
+                      f"{cores} processes x 1 BLAS thread; single-process {1.0 / t_one:.2f} windows/s",
+            "seconds": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    y, starts, freqs = make_task(20260101)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_baseline(y, starts, freqs, budget_s=8.0)
+        if i >= args.warmup:
+            vals.append(r)
+    v = float(np.mean([r["value"] for r in vals]))
+    n = int(vals[-1]["sample"].split()[0])
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * float(np.mean([r["seconds"] for r in vals])), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg2: 599 windows x (38 ch x 512), p=8, F=256; each step = bounded sample of these windows on the host CPU",
+                       "windows_per_step": n},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": vals[-1]["cores"], "kind": "port", "sample": vals[-1]["sample"]},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from hyperscanning_signal_analysis_b200 import _lib, mtmvar
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+
+    y, starts, freqs = make_task(20260101 + 3 * rank)       # one dyad per rank (cfg3 seeds)
+    n_win = len(starts)
+    T = y.shape[1]
+    x_d = torch.from_numpy(y).cuda()
+    st_d = torch.from_numpy(starts).cuda()
+    fr_d = torch.from_numpy(freqs).cuda()
+    out_d = torch.empty((n_win, M, M, F), dtype=torch.float64, device="cuda")
+    status = torch.zeros(n_win, dtype=torch.int32, device="cuda")
+    ws = torch.empty(lib.hs_mvar_ffdtf_ws_bytes(n_win, M, P, F), dtype=torch.uint8, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def step():
+        flush.zero_()                                        # L2 flush (256 MiB > 126 MB L2), inside the timed region
+        _lib.check(lib.hs_mvar_ffdtf_f64(x_d.data_ptr(), st_d.data_ptr(), T, n_win, M, WIN, P, fr_d.data_ptr(), F, FS,
+                                         out_d.data_ptr(), None, None, status.data_ptr(), ws.data_ptr(), stream.cuda_stream),
+                   "hs_mvar_ffdtf_f64")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    launches = _lib.launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    assert int(status.max().item()) == 0, "singular window in the synthetic workload"
+    value = world * n_win * args.steps / (total_ms * 1e-3)
+
+    # ---------------- per-stage device times (same stream, CUDA events), K5 = dominant kernel
+    fl = flops_per_window()
+    R = torch.empty((n_win, P + 1, M, M), dtype=torch.float64, device="cuda")
+    A = torch.empty((n_win, M, M, P), dtype=torch.float64, device="cuda")
+    V = torch.empty((n_win, M, M), dtype=torch.float64, device="cuda")
+    yw_ws = torch.empty(lib.hs_yw_ws_bytes(n_win, M, P), dtype=torch.uint8, device="cuda")
+    tr_ws = torch.empty(lib.hs_transfer_ws_bytes(n_win, M, P, F), dtype=torch.uint8, device="cuda")
+    sp = stream.cuda_stream
+    stages = {
+        "lagcov": lambda: lib.hs_lagcov_f64(x_d.data_ptr(), st_d.data_ptr(), T, n_win, 1, M, WIN, P, R.data_ptr(), sp),
+        "yule_walker": lambda: lib.hs_yw_solve_f64(R.data_ptr(), n_win, M, P, A.data_ptr(), V.data_ptr(), None, status.data_ptr(), yw_ws.data_ptr(), sp),
+        "transfer": lambda: lib.hs_transfer_dtf_f64(A.data_ptr(), fr_d.data_ptr(), F, FS, n_win, M, P, None, None, out_d.data_ptr(), None,
+                                                    status.data_ptr(), tr_ws.data_ptr(), sp),
+        "transfer+normalise": lambda: lib.hs_transfer_dtf_f64(A.data_ptr(), fr_d.data_ptr(), F, FS, n_win, M, P, None, None, None, out_d.data_ptr(),
+                                                              status.data_ptr(), tr_ws.data_ptr(), sp),
+    }
+    stage_ms = {}
+    for name, fn in stages.items():
+        ts = []
+        for i in range(3 + max(3, args.steps)):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _lib.check(fn(), name)
+            b.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(a.elapsed_time(b))
+        stage_ms[name] = float(np.mean(ts))
+    import ctypes as C
+    tf = C.c_double(0.0)
+    _lib.check(lib.hs_measure_dfma_tflops(C.byref(tf), flush.data_ptr(), 5), "hs_measure_dfma_tflops")
+    dfma_peak = tf.value
+    k5_tflops = fl["transfer"] * n_win / (stage_ms["transfer"] * 1e-3) * 1e-12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    roofline = {"kernel": "transfer_dtf_kernel (A(f) assembly + complex 38x38 inverse + |H|^2, 599*256 matrices per launch)",
+                "bound": "fp64", "achieved": k5_tflops, "peak": dfma_peak, "unit": "TFLOP/s", "frac": k5_tflops / dfma_peak if dfma_peak else None,
+                "peak_source": "hs_measure_dfma_tflops: register-only DFMA loop on all SMs, measured in this run "
+                               "(MEASURED_PEAKS.json has no FP64 figure; its hbm_gbs is %s)" % peaks.get("hbm_gbs"),
+                "flops_per_launch": fl["transfer"] * n_win, "ms_per_launch": stage_ms["transfer"], "traffic": None,
+                "hbm_write_gbs": n_win * M * M * F * 8 / (stage_ms["transfer"] * 1e-3) * 1e-9,
+                "stages_ms": stage_ms,
+                "stages_tflops": {k: fl[k] * n_win / (stage_ms[k] * 1e-3) * 1e-12 for k in ("lagcov", "yule_walker", "transfer")},
+                "step_tflops": fl["total"] * n_win * args.steps * world / (total_ms * 1e-3) * 1e-12}
+
+    # ---------------- e2e through the host-buffer API (pinned NumPy in, pinned NumPy out)
+    x_pin = torch.from_numpy(y).pin_memory()
+    out_pin = torch.empty((n_win, M, M, F), dtype=torch.float64).pin_memory()
+    plan = mtmvar.FfdtfPlan(n_win, M, WIN, P, F, T)
+    x_np, out_np = x_pin.numpy(), out_pin.numpy()
+    plan.run(x_np, starts, freqs, FS, out=out_np)
+    e2e_steps = max(2, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        plan.run(x_np, starts, freqs, FS, out=out_np)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e = {"value": world * n_win * e2e_steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(y.nbytes + starts.nbytes + freqs.nbytes),
+           "d2h_bytes_per_step": int(out_np.nbytes + 4 * n_win), "steps": e2e_steps,
+           "api": "mtmvar.FfdtfPlan.run -> hs_plan_mvar_ffdtf_host (chunked H2D/compute/D2H on 3 streams), host wall clock incl. final sync"}
+    assert abs(float(out_np[0].sum()) - M) < 1e-6
+    plan.close()
+
+    # ---------------- optional: final result all-gather over NCCL (reported separately)
+    allgather = None
+    if world > 1:
+        gathered = torch.empty((world,) + tuple(out_d.shape), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(gathered, out_d)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step()
+        dist.all_gather_into_tensor(gathered, out_d)
+        b.record()
+        barrier()
+        g_ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(g_ms, op=dist.ReduceOp.MAX)
+        allgather = {"windows_per_s_incl_allgather": world * n_win / (float(g_ms.item()) * 1e-3), "ms_step_plus_allgather": float(g_ms.item()),
+                     "bytes_received_per_rank": int((world - 1) * out_d.numel() * 8)}
+        del gathered
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(y, starts, freqs, budget_s=20.0)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "cfg2: sliding-window ffDTF, 599 windows x (38 ch x 512 samples) of one 600 s task per GPU, p=8, F=256, hop 256",
+                           "windows_per_step_per_gpu": n_win, "parallelism": f"one dyad per GPU x{world}, no data-path collective",
+                           "l2": "explicit 256 MiB memset before every step, inside the timed region; each step also writes 1.77 GB (> 126 MB L2)"},
+                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
+        if cpu:
+            line["cpu_baseline"] = cpu
+        if allgather:
+            line["allgather"] = allgather
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,383 @@
+// C-ABI entry points (include/hs_b200.h) for the MVAR/DTF path + error plumbing.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "hs_internal.h"
+#include "mvar_launch.h"
+
+namespace hs {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_launch(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
+    return HS_OK;
+}
+
+int device_sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+static int k5_groups() {
+    static int ng = 0;
+    if (ng == 0) {
+        const char* e = getenv("HS_K5_GROUPS");
+        ng = e ? atoi(e) : 6;
+        if (ng != 4 && ng != 6 && ng != 8) ng = 6;
+    }
+    return ng;
+}
+
+static void k5_segments(int F, int ng, int* n_seg, int* seg_len) {
+    int target = 8 * ng;
+    const char* e = getenv("HS_K5_SEG");
+    if (e && atoi(e) > 0) target = atoi(e);
+    int ns = (F + target / 2) / target;
+    if (ns < 1) ns = 1;
+    int sl = (F + ns - 1) / ns;
+    sl = (sl + ng - 1) / ng * ng;
+    ns = (F + sl - 1) / sl;
+    *n_seg = ns;
+    *seg_len = sl;
+}
+
+// DFMA throughput probe: 16 independent FMA chains per thread, 8 warps x 4 CTAs per SM.
+__global__ void dfma_probe_kernel(double* out, double a, double b, int iters) {
+    double x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = a + i + threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = fma(x[i], b, a);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += x[i];
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace hs
+
+using namespace hs;
+
+extern "C" {
+
+const char* hs_last_error(void) { return g_err; }
+int hs_version(void) { return 100; }
+long long hs_launch_count(void) { return g_launches.load(); }
+
+int hs_measure_dfma_tflops(double* tflops, double* d_scratch, int reps) {
+    if (!tflops || !d_scratch) return set_error(HS_ERR_INVALID, "hs_measure_dfma_tflops: null pointer");
+    const int sms = device_sm_count();
+    const int grid = sms * 4, block = 256, iters = 4096;
+    cudaEvent_t e0, e1;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return set_error(HS_ERR_CUDA, "event create");
+    dfma_probe_kernel<<<grid, block>>>(d_scratch, 1.0000001, 0.9999999, iters);
+    int rc = check_launch("dfma_probe_kernel");
+    if (rc) return rc;
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    if (reps < 1) reps = 1;
+    for (int r = 0; r < reps; ++r) {
+        cudaEventRecord(e0);
+        dfma_probe_kernel<<<grid, block>>>(d_scratch, 1.0000001, 0.9999999, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = (double)grid * block * 16.0 * iters * 2.0 / (best * 1e-3) * 1e-12;
+    return HS_OK;
+}
+
+int hs_lagcov_f64(const double* d_x, const int64_t* d_offsets, int64_t ch_stride, int n_win, int trials, int m, int n,
+                  int p, double* d_R, void* stream) {
+    if (!d_x || !d_offsets || !d_R) return set_error(HS_ERR_INVALID, "hs_lagcov_f64: null pointer");
+    if (n_win < 0 || trials < 1 || m < 1 || n < 1 || p < 0) return set_error(HS_ERR_INVALID, "hs_lagcov_f64: bad sizes");
+    if (p >= n) return set_error(HS_ERR_INVALID, "hs_lagcov_f64: model order %d must be < window length %d", p, n);
+    if (n_win == 0) return HS_OK;
+    K3Params P;
+    P.x = d_x;
+    P.offsets = reinterpret_cast<const long long*>(d_offsets);
+    P.ch_stride = ch_stride;
+    P.R = d_R;
+    P.n_win = n_win;
+    P.trials = trials;
+    P.m = m;
+    P.n = n;
+    P.p = p;
+    return launch_lagcov(P, (cudaStream_t)stream);
+}
+
+int hs_yw_assemble_f64(const double* d_R, int n_win, int m, int p, double* d_G, double* d_rhs, void* stream) {
+    if (!d_R || !d_G || !d_rhs) return set_error(HS_ERR_INVALID, "hs_yw_assemble_f64: null pointer");
+    if (n_win <= 0) return HS_OK;
+    return launch_toeplitz(d_R, n_win, m, p, d_G, d_rhs, (cudaStream_t)stream);
+}
+
+size_t hs_yw_ws_bytes(int n_win, int m, int p) { return align_up(lwr_ws_doubles(lwr_grid(n_win), m, p) * sizeof(double)); }
+
+int hs_yw_solve_f64(const double* d_R, int n_win, int m, int p, double* d_A, double* d_V, double* d_Vall,
+                    int32_t* d_status, void* d_ws, void* stream) {
+    if (!d_R || !d_A || !d_V || !d_status || !d_ws) return set_error(HS_ERR_INVALID, "hs_yw_solve_f64: null pointer");
+    if (m < 1 || p < 1) return set_error(HS_ERR_INVALID, "hs_yw_solve_f64: bad sizes m=%d p=%d", m, p);
+    if (n_win <= 0) return HS_OK;
+    K4Params P;
+    P.R = d_R;
+    P.A = d_A;
+    P.V = d_V;
+    P.Vall = d_Vall;
+    P.status = d_status;
+    P.ws = reinterpret_cast<double*>(d_ws);
+    P.n_win = n_win;
+    P.m = m;
+    P.p = p;
+    return launch_lwr(P, lwr_grid(n_win), (cudaStream_t)stream);
+}
+
+int hs_ztable_f64(const double* d_freqs, int F, int p, double fs, void* d_z, void* stream) {
+    if (!d_freqs || !d_z) return set_error(HS_ERR_INVALID, "hs_ztable_f64: null pointer");
+    if (F <= 0 || p <= 0) return HS_OK;
+    return launch_ztable(d_freqs, F, p, fs, d_z, (cudaStream_t)stream);
+}
+
+size_t hs_transfer_ws_bytes(int n_win, int m, int p, int F) {
+    int ns, sl;
+    k5_segments(F, k5_groups(), &ns, &sl);
+    return align_up((size_t)p * F * 16) + align_up((size_t)n_win * ns * m * sizeof(double)) + 256;
+}
+
+int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double fs, int n_win, int m, int p, void* d_H,
+                        void* d_Af, double* d_dtf, double* d_ffdtf, int32_t* d_status, void* d_ws, void* stream) {
+    if (!d_A || !d_freqs || !d_status || !d_ws) return set_error(HS_ERR_INVALID, "hs_transfer_dtf_f64: null pointer");
+    if (m < 1 || p < 1 || F < 1) return set_error(HS_ERR_INVALID, "hs_transfer_dtf_f64: bad sizes");
+    if (n_win <= 0) return HS_OK;
+    if (m > kPadMaxHost) return set_error(HS_ERR_UNSUPPORTED, "hs_transfer_dtf_f64: m=%d > %d not supported yet", m, kPadMaxHost);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ng = k5_groups();
+    int ns, sl;
+    k5_segments(F, ng, &ns, &sl);
+    unsigned char* ws = reinterpret_cast<unsigned char*>(d_ws);
+    double2* z = reinterpret_cast<double2*>(ws);
+    double* rowpart = reinterpret_cast<double*>(ws + align_up((size_t)p * F * 16));
+    int rc = launch_ztable(d_freqs, F, p, fs, z, st);
+    if (rc) return rc;
+    K5Params P;
+    P.A = d_A;
+    P.z = z;
+    P.dtf = d_dtf ? d_dtf : d_ffdtf;
+    P.rowpart = d_ffdtf ? rowpart : nullptr;
+    P.H = reinterpret_cast<double2*>(d_H);
+    P.Af = reinterpret_cast<double2*>(d_Af);
+    P.status = d_status;
+    P.n_win = n_win;
+    P.m = m;
+    P.p = p;
+    P.F = F;
+    P.n_seg = ns;
+    P.seg_len = sl;
+    rc = launch_transfer_dtf(P, ng, st);
+    if (rc) return rc;
+    if (d_ffdtf) rc = launch_ffdtf_normalize(P.dtf, rowpart, n_win, m, F, ns, d_ffdtf, st);
+    return rc;
+}
+
+size_t hs_mvar_ffdtf_ws_bytes(int n_win, int m, int p, int F) {
+    size_t b = 0;
+    b += align_up((size_t)n_win * (p + 1) * m * m * sizeof(double));   // R
+    b += align_up((size_t)n_win * m * m * p * sizeof(double));         // A
+    b += align_up((size_t)n_win * m * m * sizeof(double));             // V
+    b += hs_yw_ws_bytes(n_win, m, p);
+    b += hs_transfer_ws_bytes(n_win, m, p, F);
+    return b + 256;
+}
+
+int hs_mvar_ffdtf_f64(const double* d_x, const int64_t* d_offsets, int64_t ch_stride, int n_win, int m, int n, int p,
+                      const double* d_freqs, int F, double fs, double* d_ffdtf, double* d_A, double* d_V,
+                      int32_t* d_status, void* d_ws, void* stream) {
+    if (!d_x || !d_offsets || !d_freqs || !d_ffdtf || !d_status || !d_ws)
+        return set_error(HS_ERR_INVALID, "hs_mvar_ffdtf_f64: null pointer");
+    if (n_win <= 0) return HS_OK;
+    unsigned char* ws = reinterpret_cast<unsigned char*>(d_ws);
+    double* R = reinterpret_cast<double*>(ws);
+    ws += align_up((size_t)n_win * (p + 1) * m * m * sizeof(double));
+    double* A = reinterpret_cast<double*>(ws);
+    ws += align_up((size_t)n_win * m * m * p * sizeof(double));
+    double* V = reinterpret_cast<double*>(ws);
+    ws += align_up((size_t)n_win * m * m * sizeof(double));
+    void* yw_ws = ws;
+    ws += hs_yw_ws_bytes(n_win, m, p);
+    void* tr_ws = ws;
+    if (d_A) A = d_A;
+    if (d_V) V = d_V;
+    int rc = hs_lagcov_f64(d_x, d_offsets, ch_stride, n_win, 1, m, n, p, R, stream);
+    if (rc) return rc;
+    rc = hs_yw_solve_f64(R, n_win, m, p, A, V, nullptr, d_status, yw_ws, stream);
+    if (rc) return rc;
+    return hs_transfer_dtf_f64(A, d_freqs, F, fs, n_win, m, p, nullptr, nullptr, nullptr, d_ffdtf, d_status, tr_ws, stream);
+}
+
+int hs_spectra_f64(const void* d_H, const double* d_V, int n_win, int m, int F, void* d_S, void* stream) {
+    if (!d_H || !d_V || !d_S) return set_error(HS_ERR_INVALID, "hs_spectra_f64: null pointer");
+    if (n_win <= 0) return HS_OK;
+    return launch_spectra(d_H, d_V, n_win, m, F, d_S, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// Host-buffer plan: chunked H2D -> K3/K4/K5 -> D2H pipeline on two streams.
+// ------------------------------------------------------------------------------------------
+struct hs_plan {
+    int max_windows, m, n, p, F;
+    int64_t max_samples;
+    int chunk;                 // windows per chunk
+    double* d_x = nullptr;
+    int64_t* d_offsets = nullptr;
+    double* d_freqs = nullptr;
+    double* d_out[2] = {nullptr, nullptr};
+    void* d_ws[2] = {nullptr, nullptr};
+    int32_t* d_status = nullptr;
+    int64_t* h_offsets = nullptr;     // pinned
+    cudaStream_t s_compute[2] = {nullptr, nullptr};
+    cudaStream_t s_copy = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    size_t ws_bytes = 0;
+};
+
+#define PLAN_CUDA(call)                                                                          \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            int rc__ = set_error(e__ == cudaErrorMemoryAllocation ? HS_ERR_NOMEM : HS_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+            return rc__;                                                                         \
+        }                                                                                        \
+    } while (0)
+
+int hs_plan_create(hs_plan** plan, int max_windows, int m, int n, int p, int F, int64_t max_samples) {
+    if (!plan || max_windows < 1 || m < 1 || n < 1 || p < 1 || F < 1 || max_samples < n)
+        return set_error(HS_ERR_INVALID, "hs_plan_create: bad arguments");
+    hs_plan* pl = new hs_plan();
+    pl->max_windows = max_windows;
+    pl->m = m;
+    pl->n = n;
+    pl->p = p;
+    pl->F = F;
+    pl->max_samples = max_samples;
+    int chunk = 96;
+    const char* e = getenv("HS_PLAN_CHUNK");
+    if (e && atoi(e) > 0) chunk = atoi(e);
+    if (chunk > max_windows) chunk = max_windows;
+    pl->chunk = chunk;
+    *plan = pl;
+    PLAN_CUDA(cudaMalloc(&pl->d_x, (size_t)m * max_samples * sizeof(double)));
+    PLAN_CUDA(cudaMalloc(&pl->d_offsets, (size_t)max_windows * sizeof(int64_t)));
+    PLAN_CUDA(cudaMalloc(&pl->d_freqs, (size_t)F * sizeof(double)));
+    PLAN_CUDA(cudaMalloc(&pl->d_status, (size_t)max_windows * sizeof(int32_t)));
+    PLAN_CUDA(cudaMallocHost(&pl->h_offsets, (size_t)max_windows * sizeof(int64_t)));
+    pl->ws_bytes = hs_mvar_ffdtf_ws_bytes(chunk, m, p, F);
+    for (int i = 0; i < 2; ++i) {
+        PLAN_CUDA(cudaMalloc(&pl->d_out[i], (size_t)chunk * m * m * F * sizeof(double)));
+        PLAN_CUDA(cudaMalloc(&pl->d_ws[i], pl->ws_bytes));
+        PLAN_CUDA(cudaStreamCreateWithFlags(&pl->s_compute[i], cudaStreamNonBlocking));
+        PLAN_CUDA(cudaEventCreateWithFlags(&pl->ev_done[i], cudaEventDisableTiming));
+        PLAN_CUDA(cudaEventCreateWithFlags(&pl->ev_free[i], cudaEventDisableTiming));
+    }
+    PLAN_CUDA(cudaStreamCreateWithFlags(&pl->s_copy, cudaStreamNonBlocking));
+    PLAN_CUDA(cudaEventCreateWithFlags(&pl->ev_in, cudaEventDisableTiming));
+    return HS_OK;
+}
+
+void hs_plan_destroy(hs_plan* pl) {
+    if (!pl) return;
+    cudaDeviceSynchronize();
+    cudaFree(pl->d_x);
+    cudaFree(pl->d_offsets);
+    cudaFree(pl->d_freqs);
+    cudaFree(pl->d_status);
+    cudaFreeHost(pl->h_offsets);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(pl->d_out[i]);
+        cudaFree(pl->d_ws[i]);
+        if (pl->s_compute[i]) cudaStreamDestroy(pl->s_compute[i]);
+        if (pl->ev_done[i]) cudaEventDestroy(pl->ev_done[i]);
+        if (pl->ev_free[i]) cudaEventDestroy(pl->ev_free[i]);
+    }
+    if (pl->s_copy) cudaStreamDestroy(pl->s_copy);
+    if (pl->ev_in) cudaEventDestroy(pl->ev_in);
+    delete pl;
+}
+
+int hs_plan_mvar_ffdtf_host(hs_plan* pl, const double* h_x, int64_t t_total, const int64_t* h_starts, int n_win,
+                            const double* h_freqs, double fs, double* h_ffdtf, int32_t* h_status) {
+    if (!pl || !h_x || !h_starts || !h_freqs || !h_ffdtf || !h_status)
+        return set_error(HS_ERR_INVALID, "hs_plan_mvar_ffdtf_host: null pointer");
+    if (n_win > pl->max_windows || t_total > pl->max_samples || n_win < 0)
+        return set_error(HS_ERR_INVALID, "hs_plan_mvar_ffdtf_host: plan too small (n_win=%d, T=%lld)", n_win, (long long)t_total);
+    for (int w = 0; w < n_win; ++w) {
+        if (h_starts[w] < 0 || h_starts[w] + pl->n > t_total)
+            return set_error(HS_ERR_INVALID, "hs_plan_mvar_ffdtf_host: window %d [%lld, +%d) outside the signal", w, (long long)h_starts[w], pl->n);
+        pl->h_offsets[w] = h_starts[w];
+    }
+    if (n_win == 0) return HS_OK;
+    const int m = pl->m, F = pl->F;
+    // inputs
+    PLAN_CUDA(cudaMemcpyAsync(pl->d_x, h_x, (size_t)m * t_total * sizeof(double), cudaMemcpyHostToDevice, pl->s_copy));
+    PLAN_CUDA(cudaMemcpyAsync(pl->d_offsets, pl->h_offsets, (size_t)n_win * sizeof(int64_t), cudaMemcpyHostToDevice, pl->s_copy));
+    PLAN_CUDA(cudaMemcpyAsync(pl->d_freqs, h_freqs, (size_t)F * sizeof(double), cudaMemcpyHostToDevice, pl->s_copy));
+    PLAN_CUDA(cudaMemsetAsync(pl->d_status, 0, (size_t)n_win * sizeof(int32_t), pl->s_copy));
+    PLAN_CUDA(cudaEventRecord(pl->ev_in, pl->s_copy));
+    const size_t per_win = (size_t)m * m * F;
+    int slot = 0;
+    bool used[2] = {false, false};
+    for (int w0 = 0; w0 < n_win; w0 += pl->chunk, slot ^= 1) {
+        const int nw = (n_win - w0 < pl->chunk) ? (n_win - w0) : pl->chunk;
+        cudaStream_t sc = pl->s_compute[slot];
+        PLAN_CUDA(cudaStreamWaitEvent(sc, pl->ev_in, 0));
+        if (used[slot]) PLAN_CUDA(cudaStreamWaitEvent(sc, pl->ev_free[slot], 0));    // previous D2H of this slot finished
+        int rc = hs_mvar_ffdtf_f64(pl->d_x, pl->d_offsets + w0, t_total, nw, m, pl->n, pl->p, pl->d_freqs, F, fs, pl->d_out[slot],
+                                   nullptr, nullptr, pl->d_status + w0, pl->d_ws[slot], sc);
+        if (rc) return rc;
+        PLAN_CUDA(cudaEventRecord(pl->ev_done[slot], sc));
+        PLAN_CUDA(cudaStreamWaitEvent(pl->s_copy, pl->ev_done[slot], 0));
+        PLAN_CUDA(cudaMemcpyAsync(h_ffdtf + (size_t)w0 * per_win, pl->d_out[slot], (size_t)nw * per_win * sizeof(double),
+                                  cudaMemcpyDeviceToHost, pl->s_copy));
+        PLAN_CUDA(cudaEventRecord(pl->ev_free[slot], pl->s_copy));
+        used[slot] = true;
+    }
+    PLAN_CUDA(cudaMemcpyAsync(h_status, pl->d_status, (size_t)n_win * sizeof(int32_t), cudaMemcpyDeviceToHost, pl->s_copy));
+    PLAN_CUDA(cudaStreamSynchronize(pl->s_copy));
+    PLAN_CUDA(cudaStreamSynchronize(pl->s_compute[0]));
+    PLAN_CUDA(cudaStreamSynchronize(pl->s_compute[1]));
+    return HS_OK;
+}
+
+}  // extern "C"

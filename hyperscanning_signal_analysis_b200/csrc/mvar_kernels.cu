@@ -1,0 +1,623 @@
+// MVAR hot path on sm_100a, FP64:  lag covariances (K3) -> LWR Yule-Walker (K4) ->
+// A(f)^-1 / DTF / ffDTF (K5).  See DESIGN.md for the data layout and roofline of each.
+//
+// Replaces, for batches of windows:
+//   count_corr              /root/reference  src/mtmvar.py:35-87
+//   ar_coeff                src/mtmvar.py:90-123
+//   mvar_transfer_function  src/mtmvar.py:126-162
+//   dtf_multivariate        src/mtmvar.py:204-234   (|H|^2, un-normalised)
+//   full_freq_dtf           src/mtmvar.py:237-284
+//   multivariate_spectra    src/mtmvar.py:165-201   (H V H^T, plain transpose)
+#include "hs_tile.cuh"
+#include "hs_internal.h"
+#include "mvar_launch.h"
+
+namespace hs {
+
+// =====================================================================================
+// z table:  z[k][f] = exp(-(k+1) * 2*pi*i * f / fs), same expression order as
+// mtmvar.py:153 (argument rounded exactly as NumPy rounds it, then sincos).
+// =====================================================================================
+__global__ void ztable_kernel(const double* __restrict__ freqs, int F, int p, double fs, double2* __restrict__ z) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p * F) return;
+    const int k = idx / F + 1, f = idx % F;
+    // numpy: (((-k * 2) * pi) * 1j) * freqs / fs   ->  imaginary part ((-2k*pi) * f) / fs
+    const double t = (((double)(-k * 2) * 3.141592653589793) * freqs[f]) / fs;
+    double s, c;
+    sincos(t, &s, &c);
+    z[idx] = make_double2(c, s);
+}
+
+// =====================================================================================
+// K5  transfer_dtf :  per (window, frequency)  A(f) = I - sum_k A_k z_k(f),  H = A(f)^-1,
+//                     dtf = |H|^2, plus per-row partial sums for the ffDTF denominator.
+//
+// One CTA = NG tile groups (64 threads each) that share one window's AR coefficients in
+// shared memory and work on NG consecutive frequency bins at a time; |H|^2 of the NG
+// bins is staged in shared memory so the (m, m, F) output (F fastest, as the reference
+// lays it out) is written in NG*8-byte contiguous runs.
+// Work unit = (window, segment of seg_len bins); units are dealt round-robin to a
+// persistent grid of one CTA per SM.
+// =====================================================================================
+template <int T>
+struct K5Smem {
+    // dynamic shared memory carve-up (all offsets in bytes, 16 B aligned)
+    // doubles per coefficient row, chosen = 2 (mod 16) so that 8 consecutive rows hit 8 distinct 16 B bank groups
+    static __host__ __device__ size_t coef_stride(int m, int p) { const int mp = m * p; return (size_t)(mp + ((2 - (mp & 15) + 16) & 15)); }
+    static __host__ __device__ size_t coef_bytes(int m, int p) { return coef_stride(m, p) * m * sizeof(double); }
+    static __host__ __device__ size_t stage_bytes(int m, int ng) { return (size_t)m * m * ng * sizeof(double); }
+    static __host__ __device__ size_t total(int m, int p, int ng) {
+        return coef_bytes(m, p) + stage_bytes(m, ng) + (size_t)ng * sizeof(GJScratch) + (size_t)m * ng * sizeof(double) + 64;
+    }
+};
+
+
+template <int T, int NG>
+__global__ void __launch_bounds__(NG * 64, 1) transfer_dtf_kernel(const K5Params P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int m = P.m, p = P.p, F = P.F;
+    const size_t cstride = K5Smem<T>::coef_stride(m, p);
+    double* coef = reinterpret_cast<double*>(smem_raw);
+    double* stage = reinterpret_cast<double*>(smem_raw + K5Smem<T>::coef_bytes(m, p));
+    GJScratch* gjs = reinterpret_cast<GJScratch*>(smem_raw + K5Smem<T>::coef_bytes(m, p) + K5Smem<T>::stage_bytes(m, NG));
+    double* rsg = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(gjs) + NG * sizeof(GJScratch));   // [m][NG]
+
+    const Group g = make_group();
+    GJScratch* sh = gjs + g.gid;
+    const int nthreads = NG * 64;
+    const int n_units = P.n_win * P.n_seg;
+    int loaded_w = -1;
+
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int w = unit / P.n_seg, seg = unit % P.n_seg;
+        const int f_begin = seg * P.seg_len, f_end = min(F, f_begin + P.seg_len);
+        if (w != loaded_w) {
+            __syncthreads();
+            // AR coefficients of window w -> shared (row i padded to cstride doubles)
+            const double* Aw = P.A + (size_t)w * m * m * p;
+            const int row_len = m * p;
+            for (int e = threadIdx.x; e < m * row_len; e += nthreads) {
+                const int i = e / row_len, c = e - i * row_len;
+                coef[i * cstride + c] = Aw[e];
+            }
+            loaded_w = w;
+        }
+        __syncthreads();
+        double rs_acc = 0.0;    // thread t < m*NG accumulates row (t / NG), slot (t % NG)
+
+        for (int f0 = f_begin; f0 < f_end; f0 += NG) {
+            const int f = f0 + g.gid;
+            const bool active = f < f_end;
+            if (active) {
+                double ar[T][T], ai[T][T];
+                // ---- build A(f) tile
+#pragma unroll
+                for (int a = 0; a < T; ++a)
+#pragma unroll
+                    for (int b = 0; b < T; ++b) {
+                        ar[a][b] = ((g.tr + 8 * a) == (g.tc + 8 * b)) ? 1.0 : 0.0;
+                        ai[a][b] = 0.0;
+                    }
+                for (int k = 0; k < p; ++k) {
+                    const double2 zz = __ldg(&P.z[(size_t)k * F + f]);
+#pragma unroll
+                    for (int a = 0; a < T; ++a) {
+                        const int i = g.tr + 8 * a;
+#pragma unroll
+                        for (int b = 0; b < T; ++b) {
+                            const int j = g.tc + 8 * b;
+                            if (i < m && j < m) {
+                                const double c = coef[i * cstride + j * p + k];
+                                ar[a][b] = fma(-c, zz.x, ar[a][b]);
+                                ai[a][b] = fma(-c, zz.y, ai[a][b]);
+                            }
+                        }
+                    }
+                }
+                if (P.Af) {
+#pragma unroll
+                    for (int a = 0; a < T; ++a)
+#pragma unroll
+                        for (int b = 0; b < T; ++b) {
+                            const int i = g.tr + 8 * a, j = g.tc + 8 * b;
+                            if (i < m && j < m) P.Af[((size_t)w * m * m + (size_t)i * m + j) * F + f] = make_double2(ar[a][b], ai[a][b]);
+                        }
+                }
+                // ---- invert
+                gj_inverse<T, true>(ar, ai, m, g, sh);
+                if (g.l64 == 0 && sh->singular) atomicOr(&P.status[w], 1);
+                // ---- un-permute into the staging buffer / H
+#pragma unroll
+                for (int a = 0; a < T; ++a) {
+                    const int i = g.tr + 8 * a;
+                    if (i < m) {
+                        const int ri = sh->rowmap[i];
+#pragma unroll
+                        for (int b = 0; b < T; ++b) {
+                            const int j = g.tc + 8 * b;
+                            if (j < m) {
+                                const int cj = sh->colmap[j];
+                                stage[(ri * m + cj) * NG + g.gid] = fma(ar[a][b], ar[a][b], ai[a][b] * ai[a][b]);
+                                if (P.H) P.H[((size_t)w * m * m + (size_t)ri * m + cj) * F + f] = make_double2(ar[a][b], ai[a][b]);
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- cooperative write-out of the NG bins, NG doubles contiguous per (i, j)
+            const int nvalid = min(NG, f_end - f0);
+            if (P.dtf) {
+                double* out = P.dtf + (size_t)w * m * m * F + f0;
+                for (int e = threadIdx.x; e < m * m * NG; e += nthreads) {
+                    const int pair = e / NG, s = e - pair * NG;
+                    if (s < nvalid) out[(size_t)pair * F + s] = stage[e];
+                }
+            }
+            if (threadIdx.x < m * NG) {
+                const int i = threadIdx.x / NG, s = threadIdx.x - i * NG;
+                if (s < nvalid) {
+                    const double* sp = stage + (size_t)i * m * NG + s;
+                    double acc = 0.0;
+                    for (int j = 0; j < m; ++j) acc += sp[j * NG];
+                    rs_acc += acc;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- per-unit row sums (fixed summation order -> deterministic)
+        if (P.rowpart) {
+            if (threadIdx.x < m * NG) rsg[threadIdx.x] = rs_acc;
+            __syncthreads();
+            if (threadIdx.x < m) {
+                double acc = 0.0;
+                for (int s = 0; s < NG; ++s) acc += rsg[threadIdx.x * NG + s];
+                P.rowpart[((size_t)w * P.n_seg + seg) * m + threadIdx.x] = acc;
+            }
+        }
+    }
+}
+
+// ffdtf[w][i][j][f] = dtf[w][i][j][f] / sum_seg rowpart[w][seg][i]     (mtmvar.py:281-283)
+__global__ void ffdtf_normalize_kernel(double* __restrict__ dtf, const double* __restrict__ rowpart, int m, int F, int n_seg,
+                                       double* __restrict__ out) {
+    const int w = blockIdx.y;
+    const int i = blockIdx.x;
+    __shared__ double inv_s;
+    if (threadIdx.x == 0) {
+        double acc = 0.0;
+        for (int s = 0; s < n_seg; ++s) acc += rowpart[((size_t)w * n_seg + s) * m + i];
+        inv_s = acc;
+    }
+    __syncthreads();
+    const double denom = inv_s;
+    const size_t base = ((size_t)w * m + i) * (size_t)m * F;
+    const size_t n = (size_t)m * F;
+    if ((n & 1) == 0 && ((reinterpret_cast<uintptr_t>(dtf + base) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out + base) & 15) == 0)) {
+        const double2* src = reinterpret_cast<const double2*>(dtf + base);
+        double2* dst = reinterpret_cast<double2*>(out + base);
+        for (size_t e = threadIdx.x; e < n / 2; e += blockDim.x) {
+            double2 v = src[e];
+            v.x = v.x / denom;
+            v.y = v.y / denom;
+            dst[e] = v;
+        }
+    } else {
+        for (size_t e = threadIdx.x; e < n; e += blockDim.x) out[base + e] = dtf[base + e] / denom;
+    }
+}
+
+template <int T, int NG>
+static int launch_k5_t(const K5Params& P, int sm_count, cudaStream_t stream) {
+    const size_t smem = K5Smem<T>::total(P.m, P.p, NG);
+    cudaError_t e = cudaFuncSetAttribute(transfer_dtf_kernel<T, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "transfer_dtf: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
+    const int n_units = P.n_win * P.n_seg;
+    const int grid = n_units < sm_count ? n_units : sm_count;
+    transfer_dtf_kernel<T, NG><<<grid, NG * 64, smem, stream>>>(P);
+    return check_launch("transfer_dtf_kernel");
+}
+
+int launch_transfer_dtf(const K5Params& P, int ng, cudaStream_t stream) {
+    const int T = (P.m + 7) / 8;
+    const int sm = device_sm_count();
+    if (ng == 8) {
+        switch (T) {
+            case 1: return launch_k5_t<1, 8>(P, sm, stream);
+            case 2: return launch_k5_t<2, 8>(P, sm, stream);
+            case 3: return launch_k5_t<3, 8>(P, sm, stream);
+            case 4: return launch_k5_t<4, 8>(P, sm, stream);
+            case 5: return launch_k5_t<5, 8>(P, sm, stream);
+        }
+    } else if (ng == 6) {
+        switch (T) {
+            case 1: return launch_k5_t<1, 6>(P, sm, stream);
+            case 2: return launch_k5_t<2, 6>(P, sm, stream);
+            case 3: return launch_k5_t<3, 6>(P, sm, stream);
+            case 4: return launch_k5_t<4, 6>(P, sm, stream);
+            case 5: return launch_k5_t<5, 6>(P, sm, stream);
+        }
+    } else if (ng == 4) {
+        switch (T) {
+            case 1: return launch_k5_t<1, 4>(P, sm, stream);
+            case 2: return launch_k5_t<2, 4>(P, sm, stream);
+            case 3: return launch_k5_t<3, 4>(P, sm, stream);
+            case 4: return launch_k5_t<4, 4>(P, sm, stream);
+            case 5: return launch_k5_t<5, 4>(P, sm, stream);
+        }
+    }
+    return set_error(HS_ERR_UNSUPPORTED, "transfer_dtf: no kernel for m=%d ng=%d", P.m, ng);
+}
+
+
+// =====================================================================================
+// K3  lag_cov :  R(L)[i][j] = 1/(n*trials) * sum_trials sum_{t=0}^{n-1-L} x_i(t) x_j(t+L),
+//                L = 0..p   (count_corr, mtmvar.py:54-59, 72-73, 78-85; biased, no mean removal).
+//
+// One CTA per window.  Group g of the CTA owns lag (round*NG + g); all groups consume the
+// same time-major panel  xs[t][ch]  staged once per chunk of TC samples (+ halo of the
+// largest lag in the round), so the window is read from L2/HBM once per lag-round.
+// m > 40 is handled by looping over 40 x 40 output blocks.
+// =====================================================================================
+static_assert(kPadMaxHost == kPadMax, "pad mismatch");
+constexpr int kK3Chunk = 64;
+constexpr int kK3Ld = 41;       // odd stride: transposed staging stores are conflict-light
+
+
+template <int T>
+__global__ void __launch_bounds__(576, 1) lagcov_kernel(const K3Params P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int NG = blockDim.x >> 6;
+    const Group g = make_group();
+    const int m = P.m, n = P.n, p = P.p;
+    const int w = blockIdx.x;
+    const int nblk = (m + kPadMax - 1) / kPadMax;
+    double* panelB = reinterpret_cast<double*>(smem_raw);                       // [(TC + NG-1 .. ) x 41]
+    const int halo_max = p;                                                     // rows of halo reserved
+    double* panelA = panelB + (size_t)(kK3Chunk + halo_max) * kK3Ld;            // [TC x 41], only when bi != bj
+    const double scale = 1.0 / ((double)n * (double)P.trials);
+
+    for (int bi = 0; bi < nblk; ++bi)
+        for (int bj = 0; bj < nblk; ++bj) {
+            const int mi = min(kPadMax, m - bi * kPadMax), mj = min(kPadMax, m - bj * kPadMax);
+            for (int l0 = 0; l0 <= p; l0 += NG) {
+                const int lag = l0 + g.gid;
+                const bool has_lag = lag <= p;
+                const int halo = min(NG - 1, p - l0);
+                double acc[T][T];
+#pragma unroll
+                for (int a = 0; a < T; ++a)
+#pragma unroll
+                    for (int b = 0; b < T; ++b) acc[a][b] = 0.0;
+                for (int tr = 0; tr < P.trials; ++tr) {
+                    const double* xu = P.x + P.offsets[(size_t)w * P.trials + tr];
+                    for (int t0 = 0; t0 < n; t0 += kK3Chunk) {
+                        __syncthreads();
+                        // stage rows [t0, t0+TC+halo) of block bj (and TC rows of block bi if different)
+                        const int rowsB = kK3Chunk + halo;
+                        for (int e = threadIdx.x; e < kPadMax * rowsB; e += blockDim.x) {
+                            const int c = e / rowsB, t = e - c * rowsB;
+                            double v = 0.0;
+                            if (c < mj && t0 + t < n) v = xu[(size_t)(bj * kPadMax + c) * P.ch_stride + t0 + t];
+                            panelB[t * kK3Ld + c] = v;
+                        }
+                        if (bi != bj) {
+                            for (int e = threadIdx.x; e < kPadMax * kK3Chunk; e += blockDim.x) {
+                                const int c = e / kK3Chunk, t = e - c * kK3Chunk;
+                                double v = 0.0;
+                                if (c < mi && t0 + t < n) v = xu[(size_t)(bi * kPadMax + c) * P.ch_stride + t0 + t];
+                                panelA[t * kK3Ld + c] = v;
+                            }
+                        }
+                        __syncthreads();
+                        if (has_lag) {
+                            const double* pa = (bi != bj) ? panelA : panelB;
+                            tile_mac<T, false>(acc, pa, kK3Ld, panelB + (size_t)(lag - l0) * kK3Ld, kK3Ld, kK3Chunk, g);
+                        }
+                    }
+                }
+                if (has_lag) {
+                    double* Rw = P.R + (((size_t)w * (p + 1) + lag) * m + (size_t)bi * kPadMax) * m + (size_t)bj * kPadMax;
+#pragma unroll
+                    for (int a = 0; a < T; ++a) {
+                        const int i = g.tr + 8 * a;
+#pragma unroll
+                        for (int b = 0; b < T; ++b) {
+                            const int j = g.tc + 8 * b;
+                            if (i < mi && j < mj) Rw[(size_t)i * m + j] = acc[a][b] * scale;
+                        }
+                    }
+                }
+            }
+        }
+}
+
+int launch_lagcov(const K3Params& P, cudaStream_t stream) {
+    int ng = P.p + 1;
+    if (ng > 9) ng = 9;
+    const size_t smem = ((size_t)(kK3Chunk + P.p) + kK3Chunk) * kK3Ld * sizeof(double);
+    if (smem > 200 * 1024) return set_error(HS_ERR_UNSUPPORTED, "lagcov: model order %d too large for the staged panel", P.p);
+    cudaError_t e = cudaFuncSetAttribute(lagcov_kernel<kTileMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "lagcov: %s", cudaGetErrorString(e));
+    lagcov_kernel<kTileMax><<<P.n_win, ng * 64, smem, stream>>>(P);
+    return check_launch("lagcov_kernel");
+}
+
+// Block-Toeplitz Yule-Walker system exactly as count_corr returns it (mtmvar.py:65-76):
+// G[a][b] = R(a-b) (a>b), R(b-a)^T (a<b), R(0) (a=b);  rhs = [R(1); ...; R(p)].
+__global__ void toeplitz_assemble_kernel(const double* __restrict__ R, int m, int p, double* __restrict__ G, double* __restrict__ rhs) {
+    const int w = blockIdx.y;
+    const size_t mp = (size_t)m * p;
+    const double* Rw = R + (size_t)w * (p + 1) * m * m;
+    const size_t total = mp * mp + mp * m;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        if (e < mp * mp) {
+            const size_t row = e / mp, col = e - row * mp;
+            const int a = (int)(row / m), i = (int)(row % m), b = (int)(col / m), j = (int)(col % m);
+            double v;
+            if (a >= b) v = Rw[((size_t)(a - b) * m + i) * m + j];
+            else v = Rw[((size_t)(b - a) * m + j) * m + i];
+            G[(size_t)w * mp * mp + e] = v;
+        } else {
+            const size_t q = e - mp * mp;
+            const size_t row = q / m, j = q - row * m;
+            const int a = (int)(row / m), i = (int)(row % m);
+            rhs[(size_t)w * mp * m + q] = Rw[((size_t)(a + 1) * m + i) * m + j];
+        }
+    }
+}
+
+int launch_toeplitz(const double* R, int n_win, int m, int p, double* G, double* rhs, cudaStream_t stream) {
+    dim3 grid(64, n_win);
+    toeplitz_assemble_kernel<<<grid, 256, 0, stream>>>(R, m, p, G, rhs);
+    return check_launch("toeplitz_assemble_kernel");
+}
+
+// =====================================================================================
+// K4  lwr_solve :  Levinson-Wiggins-Robinson (Whittle) recursion for the block-Toeplitz
+//     Yule-Walker system that ar_coeff solves with a dense LU (mtmvar.py:116-122).
+//     With Gamma(l) = R(l)^T:
+//        D    = Gamma(k+1) - sum_{j=1..k} A_j Gamma(k+1-j)
+//        A_{k+1} = D Vb^-1          B_{k+1} = D^T Vf^-1
+//        A_j <- A_j - A_{k+1} B_{k+1-j}      B_j <- B_j - B_{k+1} A_{k+1-j}
+//        Vf  <- Vf - A_{k+1} D^T    Vb  <- Vb - B_{k+1} D
+//     A[i][j][k] = A_{k+1}[i][j],  V = Vf(p)  (= R0 - X rhs of mtmvar.py:119).
+//     One CTA (4 tile groups) per window, persistent over windows; A_j/B_j live in an
+//     L2-resident global scratch (double buffered per order), operands are staged as
+//     k-major 40 x 40 panels in shared memory.
+// =====================================================================================
+
+constexpr int kK4Groups = 4;
+constexpr int kPanel = kPadMax * kPadMax;
+
+template <int T>
+__global__ void __launch_bounds__(kK4Groups * 64, 1) lwr_kernel(const K4Params P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* panels = reinterpret_cast<double*>(smem_raw);              // [NG][2][kPanel]
+    double* D = panels + (size_t)kK4Groups * 2 * kPanel;                // D[q][c]  = Delta[q][c]
+    double* DT = D + kPanel;                                            // DT[q][c] = Delta[c][q]
+    double* KFT = DT + kPanel;                                          // KFT[q][i] = Kf[i][q]
+    double* KBT = KFT + kPanel;
+    GJScratch* gjs = reinterpret_cast<GJScratch*>(KBT + kPanel);
+    const Group g = make_group();
+    double* pA = panels + (size_t)g.gid * 2 * kPanel;
+    double* pB = pA + kPanel;
+    GJScratch* sh = gjs + g.gid;
+    const int m = P.m, p = P.p;
+    const size_t mm = (size_t)m * m;
+    double* ws = P.ws + (size_t)blockIdx.x * 4 * p * mm;               // [par][A|B][p][mm]
+    auto stA = [&](int par, int j) { return ws + ((size_t)(par * 2 + 0) * p + j) * mm; };   // j = 0-based index of A_{j+1}
+    auto stB = [&](int par, int j) { return ws + ((size_t)(par * 2 + 1) * p + j) * mm; };
+
+    // zero the shared panels once (padding stays zero / finite)
+    for (int e = threadIdx.x; e < (kK4Groups * 2 + 4) * kPanel; e += blockDim.x) panels[e] = 0.0;
+
+    for (int w = blockIdx.x; w < P.n_win; w += gridDim.x) {
+        const double* Rw = P.R + (size_t)w * (p + 1) * mm;
+        __syncthreads();
+        double Vt[T][T];          // group 0: Vf, group 1: Vb   (both start as Gamma(0) = R(0)^T)
+        double dummy[T][T];
+        if (g.gid < 2) {
+#pragma unroll
+            for (int a = 0; a < T; ++a)
+#pragma unroll
+                for (int b = 0; b < T; ++b) {
+                    const int i = g.tr + 8 * a, j = g.tc + 8 * b;
+                    Vt[a][b] = (i < m && j < m) ? Rw[(size_t)j * m + i] : 0.0;
+                }
+        }
+        for (int kk = 0; kk < p; ++kk) {
+            const int cur = kk & 1, nxt = cur ^ 1;
+            const bool last = (kk == p - 1);
+            // ---- phase 1: partial Delta_g = - sum_{j in group} A_j Gamma(kk+1-j)
+            {
+                double acc[T][T];
+#pragma unroll
+                for (int a = 0; a < T; ++a)
+#pragma unroll
+                    for (int b = 0; b < T; ++b) acc[a][b] = 0.0;
+                for (int j = g.gid; j < kk; j += kK4Groups) {        // A_{j+1} with Gamma(kk - j)
+                    group_sync(g);
+                    load_panel<true>(pA, stA(cur, j), m, m, g);                       // pA[q][i] = A[i][q]
+                    load_panel<true>(pB, Rw + (size_t)(kk - j) * mm, m, m, g);        // pB[q][c] = R(l)[c][q] = Gamma(l)[q][c]
+                    group_sync(g);
+                    tile_mac<T, true>(acc, pA, kPadMax, pB, kPadMax, m, g);
+                }
+                group_sync(g);
+                store_tile<T>(pA, kPadMax, acc, kPadMax, g);           // partial, row-major (full padded tile)
+            }
+            __syncthreads();
+            // ---- phase 2: Delta, inverses
+            if (g.gid < 2) {
+                double dl[T][T];
+#pragma unroll
+                for (int a = 0; a < T; ++a)
+#pragma unroll
+                    for (int b = 0; b < T; ++b) {
+                        const int i = g.tr + 8 * a, j = g.tc + 8 * b;
+                        double v = (i < m && j < m) ? Rw[((size_t)(kk + 1) * m + j) * m + i] : 0.0;   // Gamma(kk+1)[i][j]
+                        for (int q = 0; q < kK4Groups; ++q) v += panels[(size_t)q * 2 * kPanel + i * kPadMax + j];
+                        dl[a][b] = v;
+                    }
+                if (g.gid == 0) {
+                    store_tile<T>(D, kPadMax, dl, m, g);
+                    store_tile_t<T>(DT, kPadMax, dl, m, g);
+                }
+                // invert own V (copy; padding -> identity) and publish it in own pB (row-major = k-major right operand)
+                if (!(last && g.gid == 0)) {
+                    double iv[T][T];
+#pragma unroll
+                    for (int a = 0; a < T; ++a)
+#pragma unroll
+                        for (int b = 0; b < T; ++b) {
+                            const int i = g.tr + 8 * a, j = g.tc + 8 * b;
+                            iv[a][b] = (i < m && j < m) ? Vt[a][b] : ((i == j) ? 1.0 : 0.0);
+                        }
+                    gj_inverse<T, false>(iv, dummy, m, g, sh);
+                    if (g.l64 == 0 && sh->singular) atomicOr(&P.status[w], 2);
+#pragma unroll
+                    for (int a = 0; a < T; ++a) {
+                        const int i = g.tr + 8 * a;
+#pragma unroll
+                        for (int b = 0; b < T; ++b) {
+                            const int j = g.tc + 8 * b;
+                            if (i < m && j < m) pB[sh->rowmap[i] * kPadMax + sh->colmap[j]] = iv[a][b];
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- phase 3: reflection coefficients and residual covariances
+            if (g.gid == 0) {
+                // Kf = Delta * Vb^-1   (Vb^-1 is in group 1's pB)
+                double kf[T][T];
+#pragma unroll
+                for (int a = 0; a < T; ++a)
+#pragma unroll
+                    for (int b = 0; b < T; ++b) kf[a][b] = 0.0;
+                tile_mac<T, false>(kf, DT, kPadMax, panels + (size_t)(1 * 2 + 1) * kPanel, kPadMax, m, g);
+                store_tile_t<T>(KFT, kPadMax, kf, m, g);
+                store_tile<T>(stA(nxt, kk), m, kf, m, g);
+                group_sync(g);
+                tile_mac<T, true>(Vt, KFT, kPadMax, DT, kPadMax, m, g);      // Vf -= Kf * Delta^T
+                if (P.Vall) store_tile<T>(P.Vall + ((size_t)w * p + kk) * mm, m, Vt, m, g);
+            } else if (g.gid == 1 && !last) {
+                // Kb = Delta^T * Vf^-1  (Vf^-1 is in group 0's pB)
+                double kb[T][T];
+#pragma unroll
+                for (int a = 0; a < T; ++a)
+#pragma unroll
+                    for (int b = 0; b < T; ++b) kb[a][b] = 0.0;
+                tile_mac<T, false>(kb, D, kPadMax, panels + (size_t)(0 * 2 + 1) * kPanel, kPadMax, m, g);
+                store_tile_t<T>(KBT, kPadMax, kb, m, g);
+                store_tile<T>(stB(nxt, kk), m, kb, m, g);
+                group_sync(g);
+                tile_mac<T, true>(Vt, KBT, kPadMax, D, kPadMax, m, g);       // Vb -= Kb * Delta
+            }
+            __syncthreads();
+            // ---- phase 4: order update of A_j (and B_j unless this is the last order)
+            const int n_items = last ? kk : 2 * kk;
+            for (int it = g.gid; it < n_items; it += kK4Groups) {
+                const bool isA = it < kk;
+                const int j = isA ? it : it - kk;             // 0-based: A_{j+1} pairs with B_{kk-j}
+                double acc[T][T];
+                const double* own = isA ? stA(cur, j) : stB(cur, j);
+                const double* other = isA ? stB(cur, kk - 1 - j) : stA(cur, kk - 1 - j);
+                group_sync(g);
+                load_panel<false>(pB, other, m, m, g);
+                load_tile<T>(acc, own, m, m, g);
+                group_sync(g);
+                tile_mac<T, true>(acc, isA ? KFT : KBT, kPadMax, pB, kPadMax, m, g);
+                store_tile<T>(isA ? stA(nxt, j) : stB(nxt, j), m, acc, m, g);
+            }
+            __syncthreads();
+        }
+        // ---- outputs: A[w][i][j][k] = A_{k+1}[i][j]
+        {
+            const int fin = p & 1;
+            double* Aw = P.A + (size_t)w * mm * p;
+            for (size_t e = threadIdx.x; e < mm * p; e += blockDim.x) {
+                const size_t ij = e / p;
+                const int k = (int)(e - ij * p);
+                Aw[e] = stA(fin, k)[ij];
+            }
+            if (g.gid == 0) store_tile<T>(P.V + (size_t)w * mm, m, Vt, m, g);
+        }
+    }
+}
+
+size_t lwr_ws_doubles(int grid, int m, int p) { return (size_t)grid * 4 * p * m * m; }
+int lwr_grid(int n_win) { const int sm = device_sm_count(); return n_win < sm ? n_win : sm; }
+
+int launch_lwr(const K4Params& P, int grid, cudaStream_t stream) {
+    if (P.m > kPadMax) return set_error(HS_ERR_UNSUPPORTED, "lwr: m=%d > %d not supported by the register-tile path", P.m, kPadMax);
+    const size_t smem = (size_t)(kK4Groups * 2 + 4) * kPanel * sizeof(double) + kK4Groups * sizeof(GJScratch);
+    cudaError_t e = cudaFuncSetAttribute(lwr_kernel<kTileMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "lwr: %s", cudaGetErrorString(e));
+    lwr_kernel<kTileMax><<<grid, kK4Groups * 64, smem, stream>>>(P);
+    return check_launch("lwr_kernel");
+}
+
+
+int launch_ztable(const double* freqs, int F, int p, double fs, void* z, cudaStream_t stream) {
+    const int n = p * F;
+    ztable_kernel<<<(n + 255) / 256, 256, 0, stream>>>(freqs, F, p, fs, reinterpret_cast<double2*>(z));
+    return check_launch("ztable_kernel");
+}
+
+int launch_ffdtf_normalize(double* dtf, const double* rowpart, int n_win, int m, int F, int n_seg, double* out, cudaStream_t stream) {
+    dim3 grid(m, n_win);
+    ffdtf_normalize_kernel<<<grid, 256, 0, stream>>>(dtf, rowpart, m, F, n_seg, out);
+    return check_launch("ffdtf_normalize_kernel");
+}
+
+// =====================================================================================
+// S(f) = H(f) * (V * H(f)^T), plain transpose (quirk of mtmvar.py:199).  One CTA per
+// (window, bin); generic in m (shared-memory resident, m <= 64) -- not on the metric path.
+// =====================================================================================
+__global__ void spectra_kernel(const double2* __restrict__ H, const double* __restrict__ V, int m, int F, double2* __restrict__ S) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* h = reinterpret_cast<double2*>(smem_raw);          // [m][m]
+    double2* t = h + (size_t)m * m;                             // T = V * H^T
+    const int w = blockIdx.y, f = blockIdx.x;
+    const size_t base = (size_t)w * m * m;
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) h[e] = H[(base + e) * F + f];
+    __syncthreads();
+    const double* Vw = V + base;
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+        const int i = e / m, j = e - i * m;      // T[i][j] = sum_k V[i][k] H[j][k]
+        double sr = 0.0, si = 0.0;
+        for (int k = 0; k < m; ++k) {
+            const double v = Vw[i * m + k];
+            const double2 x = h[j * m + k];
+            sr = fma(v, x.x, sr);
+            si = fma(v, x.y, si);
+        }
+        t[e] = make_double2(sr, si);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+        const int i = e / m, j = e - i * m;      // S[i][j] = sum_k H[i][k] T[k][j]
+        double sr = 0.0, si = 0.0;
+        for (int k = 0; k < m; ++k) {
+            const double2 a = h[i * m + k], b = t[k * m + j];
+            sr = fma(a.x, b.x, fma(-a.y, b.y, sr));
+            si = fma(a.x, b.y, fma(a.y, b.x, si));
+        }
+        S[(base + e) * F + f] = make_double2(sr, si);
+    }
+}
+
+int launch_spectra(const void* H, const double* V, int n_win, int m, int F, void* S, cudaStream_t stream) {
+    const size_t smem = (size_t)2 * m * m * sizeof(double2);
+    if (smem > 200 * 1024) return set_error(HS_ERR_UNSUPPORTED, "spectra: m=%d too large", m);
+    cudaError_t e = cudaFuncSetAttribute(spectra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "spectra: %s", cudaGetErrorString(e));
+    dim3 grid(F, n_win);
+    spectra_kernel<<<grid, 256, smem, stream>>>(reinterpret_cast<const double2*>(H), V, m, F, reinterpret_cast<double2*>(S));
+    return check_launch("spectra_kernel");
+}
+
+
+}  // namespace hs

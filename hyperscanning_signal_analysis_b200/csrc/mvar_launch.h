@@ -1,0 +1,49 @@
+// Parameter blocks and host-side launchers of the MVAR kernels (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace hs {
+
+constexpr int kPadMaxHost = 40;
+
+struct K3Params {
+    const double* x;             // base pointer
+    const long long* offsets;    // (n_win * trials) element offset of (channel 0, sample 0) of each unit
+    long long ch_stride;         // elements between channels
+    double* R;                   // (n_win, p+1, m, m)
+    int n_win, trials, m, n, p;
+};
+
+struct K4Params {
+    const double* R;     // (n_win, p+1, m, m)
+    double* A;           // (n_win, m, m, p)
+    double* V;           // (n_win, m, m)
+    double* Vall;        // (n_win, p, m, m) residual covariance after each order, or null
+    int* status;         // (n_win)
+    double* ws;          // grid * 4 * p * m * m doubles
+    int n_win, m, p;
+};
+
+struct K5Params {
+    const double* A;        // (n_win, m, m, p)
+    const double2* z;       // (p, F)
+    double* dtf;            // (n_win, m, m, F) or null
+    double* rowpart;        // (n_win, n_seg, m) partial row sums, or null
+    double2* H;             // (n_win, m, m, F) complex or null
+    double2* Af;            // (n_win, m, m, F) complex or null
+    int* status;            // (n_win) sticky singular flags
+    int n_win, m, p, F, n_seg, seg_len;
+};
+
+int launch_lagcov(const K3Params& P, cudaStream_t stream);
+int launch_toeplitz(const double* R, int n_win, int m, int p, double* G, double* rhs, cudaStream_t stream);
+size_t lwr_ws_doubles(int grid, int m, int p);
+int lwr_grid(int n_win);
+int launch_lwr(const K4Params& P, int grid, cudaStream_t stream);
+int launch_ztable(const double* freqs, int F, int p, double fs, void* z, cudaStream_t stream);
+int launch_transfer_dtf(const K5Params& P, int ng, cudaStream_t stream);
+int launch_ffdtf_normalize(double* dtf, const double* rowpart, int n_win, int m, int F, int n_seg, double* out, cudaStream_t stream);
+int launch_spectra(const void* H, const double* V, int n_win, int m, int F, void* S, cudaStream_t stream);
+
+}  // namespace hs

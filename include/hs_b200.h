@@ -1,0 +1,146 @@
+/* hs_b200.h -- C ABI of the B200-native connectivity hot path.
+ *
+ * The reference (SYNCC-IN/hyperscanning-signal-analysis) is pure Python and has no
+ * FFI; its "operator interface" for this path is a set of module-level Python
+ * functions.  Each entry point below names the reference function (file:line under
+ * /root/reference) whose arithmetic it replaces; the Python modules in
+ * hyperscanning_signal_analysis_b200/ keep the reference signatures and call these
+ * through ctypes (see INTEGRATION.md for the binding a maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every array is float64 / complex128 / int32 /
+ *     int64, C-contiguous unless a stride argument says otherwise;
+ *   - "d_" pointers are DEVICE pointers, "h_" pointers are HOST pointers;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *   - device entry points never allocate and never synchronise: scratch is
+ *     caller-provided (sizes from the *_ws_bytes queries);
+ *   - return 0 on success, a negative HS_ERR_* code otherwise; hs_last_error()
+ *     returns a thread-local message.  Numerically singular windows do not fail the
+ *     batch: they set bits in the per-window int32 `status` array
+ *     (1 = A(f) singular at some bin, 2 = singular residual covariance in the
+ *     Yule-Walker recursion), which the Python layer turns into
+ *     numpy.linalg.LinAlgError like np.linalg.solve / inv would raise.
+ */
+#ifndef HS_B200_H
+#define HS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HS_OK 0
+#define HS_ERR_INVALID (-1)
+#define HS_ERR_UNSUPPORTED (-2)
+#define HS_ERR_CUDA (-3)
+#define HS_ERR_NOMEM (-4)
+
+#define HS_STATUS_SINGULAR_TRANSFER 1
+#define HS_STATUS_SINGULAR_YW 2
+
+const char* hs_last_error(void);
+int hs_version(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+long long hs_launch_count(void);
+
+/* Roofline probe: achieved FP64 FMA throughput (TFLOP/s, best of `reps` runs of a register-only
+ * DFMA loop on every SM) -- the denominator bench.py reports K3-K5 against, because the
+ * driver-written MEASURED_PEAKS.json holds no FP64 figure.  d_scratch: >= 8 MiB device memory.
+ * Synchronises; not part of the data path.                                                  */
+int hs_measure_dfma_tflops(double* tflops, double* d_scratch, int reps);
+
+/* ---------------------------------------------------------------- MVAR / DTF (K3-K5) */
+
+/* Lag covariances R(0..p), biased 1/n, no mean removal, averaged over trials.
+ * Replaces count_corr, src/mtmvar.py:35-87 (lags :54-59, lag 0 :72-73, trial mean :78-85).
+ *   d_x          base pointer of the signals
+ *   d_offsets    (n_win*trials) int64 element offsets of (channel 0, sample 0) of each window/trial
+ *   ch_stride    elements between consecutive channels (time stride is 1)
+ *   d_R          out (n_win, p+1, m, m)                                                     */
+int hs_lagcov_f64(const double* d_x, const int64_t* d_offsets, int64_t ch_stride, int n_win, int trials, int m,
+                  int n, int p, double* d_R, void* stream);
+
+/* Block-Toeplitz system as count_corr returns it (src/mtmvar.py:65-76):
+ * d_G (n_win, m*p, m*p), d_rhs (n_win, m*p, m); R(0) is d_R[:, 0].                          */
+int hs_yw_assemble_f64(const double* d_R, int n_win, int m, int p, double* d_G, double* d_rhs, void* stream);
+
+/* Yule-Walker solve by the Levinson-Wiggins-Robinson recursion.
+ * Replaces np.linalg.solve + residual + reshape of ar_coeff, src/mtmvar.py:116-122.
+ *   d_A (n_win, m, m, p)   d_V (n_win, m, m)   d_Vall optional (n_win, p, m, m): residual
+ *   covariance after every order (what mvar_criterion, mtmvar.py:577-590, refits p times for)
+ *   d_ws scratch of hs_yw_ws_bytes(n_win, m, p) bytes.                                       */
+size_t hs_yw_ws_bytes(int n_win, int m, int p);
+int hs_yw_solve_f64(const double* d_R, int n_win, int m, int p, double* d_A, double* d_V, double* d_Vall,
+                    int32_t* d_status, void* d_ws, void* stream);
+
+/* z[k][f] = exp(-(k+1) 2 pi i f / fs), src/mtmvar.py:151-153.  d_z (p, F) complex128.        */
+int hs_ztable_f64(const double* d_freqs, int F, int p, double fs, void* d_z, void* stream);
+
+/* A(f) = I - sum_k A_k z_k(f), H(f) = A(f)^-1, dtf = |H|^2 and ffDTF.
+ * Replaces mvar_transfer_function (src/mtmvar.py:126-162), dtf_multivariate (:232) and the
+ * normalisation loop of full_freq_dtf (:278-284).  All outputs optional (NULL to skip):
+ *   d_H, d_Af   (n_win, m, m, F) complex128       d_dtf, d_ffdtf (n_win, m, m, F) float64
+ * d_ffdtf may alias d_dtf.  d_ws: hs_transfer_ws_bytes(n_win, m, p, F) bytes.                */
+size_t hs_transfer_ws_bytes(int n_win, int m, int p, int F);
+int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double fs, int n_win, int m, int p,
+                        void* d_H, void* d_Af, double* d_dtf, double* d_ffdtf, int32_t* d_status, void* d_ws,
+                        void* stream);
+
+/* S(f) = H(f) V H(f)^T with a plain transpose, src/mtmvar.py:197-199.  d_S (n_win, m, m, F) complex128. */
+int hs_spectra_f64(const void* d_H, const double* d_V, int n_win, int m, int F, void* d_S, void* stream);
+
+/* Fused windows -> ffDTF (the metric path): K3 -> K4 -> K5 on one stream.
+ * Equivalent to calling full_freq_dtf(window, freqs, fs, optimal_model_order=p)
+ * (src/mtmvar.py:237) for every window of EEG_IBI_FFDTF_Pipeline.run_pipeline's loop
+ * (src/eeg_alpha_ibi_ffdtf.py:741-755) and stacking as at :651.
+ *   d_A / d_V optional outputs (may be NULL: taken from the workspace).                     */
+size_t hs_mvar_ffdtf_ws_bytes(int n_win, int m, int p, int F);
+int hs_mvar_ffdtf_f64(const double* d_x, const int64_t* d_offsets, int64_t ch_stride, int n_win, int m, int n, int p,
+                      const double* d_freqs, int F, double fs, double* d_ffdtf, double* d_A, double* d_V,
+                      int32_t* d_status, void* d_ws, void* stream);
+
+/* Host-buffer variant (what a Python caller holding NumPy arrays uses; e2e in bench.py):
+ * h_x (m, T_total) float64 host, h_starts (n_win) int64 window start samples,
+ * h_ffdtf (n_win, m, m, F) host output, h_status (n_win).  Copies, computes and copies back
+ * in window chunks on two streams so PCIe transfers overlap the kernels; synchronises before
+ * returning.  The plan owns its device buffers and pinned staging.                           */
+typedef struct hs_plan hs_plan;
+int hs_plan_create(hs_plan** plan, int max_windows, int m, int n, int p, int F, int64_t max_samples);
+void hs_plan_destroy(hs_plan* plan);
+int hs_plan_mvar_ffdtf_host(hs_plan* plan, const double* h_x, int64_t t_total, const int64_t* h_starts, int n_win,
+                            const double* h_freqs, double fs, double* h_ffdtf, int32_t* h_status);
+
+/* ---------------------------------------------------------------- front end (K1, K2, K6) */
+
+/* Zero-phase IIR: scipy.signal.filtfilt(b, a, x) with SciPy defaults (odd extension,
+ * padlen = 3*ntaps, lfilter_zi initial state), applied for each of n_filt filters in series,
+ * after optional DC removal.  Replaces the channel loop of _apply_filters,
+ * src/dataloader.py:786-803 (IIR branch :789-792) and the filter block of
+ * mne_bridge.load_eeg_signals, src/mne_bridge.py:161-184.
+ *   d_x (n_sig rows): element (s, t) at d_x[s*sig_stride + t*t_stride]; filtered in place
+ *   h_b, h_a  (n_filt, ntaps) HOST coefficient arrays, zero padded to ntaps, a[0] == 1
+ *   d_ws: hs_filtfilt_ws_bytes(n_sig, n) bytes.                                              */
+size_t hs_filtfilt_ws_bytes(int n_sig, int64_t n);
+int hs_iir_filtfilt_f64(double* d_x, int n_sig, int64_t n, int64_t sig_stride, int64_t t_stride, const double* h_b,
+                        const double* h_a, int n_filt, int ntaps, int remove_dc, void* d_ws, void* stream);
+
+/* scipy.signal.decimate(x, q, ftype='fir', zero_phase=True), src/data_structures.py:792:
+ * y[k] = sum_j b[j] x[q k + half - j], half = (ntaps-1)/2, zero outside.  d_y (n_sig, ceil(n/q)). */
+int hs_fir_decimate_f64(const double* d_x, int n_sig, int64_t n, int64_t sig_stride, int q, const double* d_b,
+                        int ntaps, double* d_y, int64_t y_stride, void* stream);
+
+/* Multitaper PSD (mne.time_frequency.psd_array_multitaper defaults reached through
+ * compute_psd_multitaper, src/psd.py:30-32): remove mean, taper, FFT, eigenvalue-weighted power.
+ *   d_x (n_sig, n)   d_tapers (K, n)   d_weights (K) = sqrt(eigvals)
+ *   bins k_lo..k_hi-1 of the rfft grid are returned in d_psd (n_sig, k_hi-k_lo).
+ * Hand-written FFT (no cuFFT): any n (power-of-two direct, otherwise Bluestein).             */
+size_t hs_mt_psd_ws_bytes(int n_sig, int64_t n, int K);
+int hs_mt_psd_f64(const double* d_x, int n_sig, int64_t n, const double* d_tapers, const double* d_weights, int K,
+                  int k_lo, int k_hi, double* d_psd, void* d_ws, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HS_B200_H */

@@ -6,7 +6,7 @@
   and the IIR branch of ``_apply_filters`` (dataloader.py:788-792).
 * ``filtfilt_df2t``: explicit restatement of what ``scipy.signal.filtfilt``
   does with its defaults -- pinned against SciPy
-  itself in tests (0.0 max abs diff).
+  itself in tests (agrees to ~1e-15 relative; SciPy's C loop contracts FMAs).
 * ``decimate_fir``: closed form of ``scipy.signal.decimate(x, q, ftype='fir',
   zero_phase=True)`` (data_structures.py:792; Appendix A.2), pinned against SciPy.
 * ``psd_multitaper``: restatement of MNE 1.11 ``psd_array_multitaper`` defaults

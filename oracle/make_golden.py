@@ -184,34 +184,40 @@ def main():
                         fs_out=dec4.fs)
 
     # ---------------------------------------------------------------- MVAR at the BASELINE shape: cfg1 pipeline, two 2-s windows, F=32 grid
+    # Band 1-64 Hz = the reference's production values (scripts/export_dyade_to_ncdf_by_task_batch.py:27-31): cond(G) ~ 3e7.
+    # A second fixture with the 40 Hz low-pass is kept as an ill-conditioned stress case (cond ~ 1.5e9, where two runs
+    # of the SAME LU solver on inputs differing by 1 ulp already differ by ~1e-8).
     x1 = synth.cfg1_raw()
-    md5 = ds.MultimodalData()
-    md5.fs = 256.0
-    md5.eeg_channel_names_ch = names_ch
-    md5.eeg_channel_names_cg = names_cg
-    md5.eeg_channel_mapping = {nm: i for i, nm in enumerate(names_ch + names_cg)}
-    f5 = dataloader._design_eeg_filters(md5, lowcut=1.0, highcut=40.0, filter_type="iir")
-    y1 = x1.copy()
-    quiet(dataloader._apply_filters, md5, f5, y1)
     fgrid = np.linspace(0, 128, 32, endpoint=False)
-    starts = np.array([1024, 9000])
-    wins = np.stack([y1[:, s:s + 512] for s in starts])
-    As, Vs, ffs, conds = [], [], [], []
-    for w in wins:
-        A, V = mtmvar.ar_coeff(w, 8)
-        As.append(A); Vs.append(V)
-        ffs.append(quiet(mtmvar.full_freq_dtf, w, fgrid, 256.0, optimal_model_order=8))
-        conds.append(np.linalg.cond(mtmvar.count_corr(w[:, :, None], 8, 1)[0]))
-    np.savez_compressed(os.path.join(OUT, "mvar_cfg2_windows.npz"), versions=versions, windows=wins, starts=starts, p=8, fs=256.0,
-                        freqs=fgrid, A=np.stack(As), V=np.stack(Vs), ffdtf=np.stack(ffs).astype(np.float64), cond=np.array(conds))
-    # whole 60-s segment (cfg1), F=16 grid -> small file; input regenerated from synth in the test (checked by checksum)
     f16 = np.linspace(0, 128, 16, endpoint=False)
-    A, V = mtmvar.ar_coeff(y1, 8)
-    np.savez_compressed(os.path.join(OUT, "mvar_cfg1.npz"), versions=versions, p=8, fs=256.0, freqs=f16, A=A, V=V,
-                        filtered_rows=y1[[0, 18, 19, 37]], filtered_sum=float(np.sum(y1)), raw_sum=float(np.sum(x1)),
-                        ffdtf=quiet(mtmvar.full_freq_dtf, y1, f16, 256.0, optimal_model_order=8),
-                        S=quiet(mtmvar.multivariate_spectra, y1, f16, 256.0, optimal_model_order=8),
-                        cond=np.linalg.cond(mtmvar.count_corr(y1[:, :, None], 8, 1)[0]))
+    starts = np.array([1024, 9000])
+    for tag, highcut in (("", 64.0), ("_lp40", 40.0)):
+        md5 = ds.MultimodalData()
+        md5.fs = 256.0
+        md5.eeg_channel_names_ch = names_ch
+        md5.eeg_channel_names_cg = names_cg
+        md5.eeg_channel_mapping = {nm: i for i, nm in enumerate(names_ch + names_cg)}
+        f5 = dataloader._design_eeg_filters(md5, lowcut=1.0, highcut=highcut, filter_type="iir")
+        y1 = x1.copy()
+        quiet(dataloader._apply_filters, md5, f5, y1)
+        wins = np.stack([y1[:, s:s + 512] for s in starts])
+        As, Vs, ffs, conds = [], [], [], []
+        for w in wins:
+            A, V = mtmvar.ar_coeff(w, 8)
+            As.append(A); Vs.append(V)
+            ffs.append(quiet(mtmvar.full_freq_dtf, w, fgrid, 256.0, optimal_model_order=8))
+            conds.append(np.linalg.cond(mtmvar.count_corr(w[:, :, None], 8, 1)[0]))
+        np.savez_compressed(os.path.join(OUT, f"mvar_cfg2_windows{tag}.npz"), versions=versions, windows=wins, starts=starts, p=8,
+                            fs=256.0, highcut=highcut, freqs=fgrid, A=np.stack(As), V=np.stack(Vs), ffdtf=np.stack(ffs),
+                            cond=np.array(conds))
+        if tag == "":
+            # whole 60-s segment (cfg1), F=16 grid -> small file; the input is regenerated from synth + filters in the test
+            A, V = mtmvar.ar_coeff(y1, 8)
+            np.savez_compressed(os.path.join(OUT, "mvar_cfg1.npz"), versions=versions, p=8, fs=256.0, highcut=highcut, freqs=f16, A=A, V=V,
+                                filtered_rows=y1[[0, 18, 19, 37]], filtered_sum=float(np.sum(y1)), raw_sum=float(np.sum(x1)),
+                                ffdtf=quiet(mtmvar.full_freq_dtf, y1, f16, 256.0, optimal_model_order=8),
+                                S=quiet(mtmvar.multivariate_spectra, y1, f16, 256.0, optimal_model_order=8),
+                                cond=np.linalg.cond(mtmvar.count_corr(y1[:, :, None], 8, 1)[0]))
 
     # ---------------------------------------------------------------- window starts from the real _create_windows
     if ffd is not None:

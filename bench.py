@@ -110,45 +110,35 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ CPU baseline (oracle port)
-def _cpu_worker(args):
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
-    seg, freqs = args
-    from oracle import mvar_oracle as mo
-    return float(mo.full_freq_dtf(seg, freqs, FS, optimal_model_order=P).sum())
-
-
-def cpu_baseline(y, starts, freqs, budget_s=20.0, max_windows=None):
-    """Oracle port of full_freq_dtf (same per-bin np.linalg.inv loop as the reference) on every host core,
-    one window per task, BLAS pinned to one thread per process.  Bounded sample of the same windows."""
-    import multiprocessing as mp
-    try:
-        from threadpoolctl import threadpool_limits
-    except Exception:
-        threadpool_limits = None
+def cpu_baseline(y, starts, freqs, budget_s=20.0):
+    """Oracle port of full_freq_dtf (same per-bin np.linalg.inv loop as the reference) on every host core:
+    one worker process per core (1 BLAS thread each), windows dealt evenly.  Bounded sample of the same task."""
+    import tempfile
     cores = os.cpu_count() or 1
     from oracle import mvar_oracle as mo
-    # calibrate on one window, single process
     t0 = time.perf_counter()
-    if threadpool_limits:
-        with threadpool_limits(limits=1):
-            mo.full_freq_dtf(y[:, :WIN], freqs, FS, optimal_model_order=P)
-    else:
-        mo.full_freq_dtf(y[:, :WIN], freqs, FS, optimal_model_order=P)
+    mo.full_freq_dtf(y[:, :WIN], freqs, FS, optimal_model_order=P)
     t_one = time.perf_counter() - t0
-    n = int(max(cores, min(len(starts), budget_s * cores / max(t_one, 1e-3))))
-    if max_windows:
-        n = min(n, max_windows)
-    n = min(n, len(starts))
-    segs = [(np.ascontiguousarray(y[:, s:s + WIN]), freqs) for s in starts[:n]]
-    os.environ["OMP_NUM_THREADS"] = "1"
-    os.environ["OPENBLAS_NUM_THREADS"] = "1"
-    os.environ["MKL_NUM_THREADS"] = "1"
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, segs[:cores])             # warm the workers
+    n = int(min(len(starts), max(cores, budget_s * cores / max(t_one, 1e-3))))
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "windows.npz")
+        np.savez(path, windows=np.stack([y[:, s:s + WIN] for s in starts[:n]]), freqs=freqs)
+        env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
+        bounds = np.linspace(0, n, cores + 1).astype(int)
+        procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "oracle", "cpu_worker.py"), path, str(bounds[i]), str(bounds[i + 1]),
+                                   str(FS), str(P)], stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, env=env)
+                 for i in range(cores)]
+        for pr in procs:
+            assert pr.stdout.readline().strip() == "ready"
         t0 = time.perf_counter()
-        pool.map(_cpu_worker, segs, chunksize=max(1, n // (cores * 4)))
+        for pr in procs:
+            pr.stdin.write("go\n")
+            pr.stdin.flush()
+        for pr in procs:
+            assert pr.stdout.readline().startswith("done")
         dt = time.perf_counter() - t0
+        for pr in procs:
+            pr.wait()
     return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n} of {len(starts)} windows of the same task, oracle/mvar_oracle.full_freq_dtf (NumPy port of src/mtmvar.py), "
                       f"{cores} processes x 1 BLAS thread; single-process {1.0 / t_one:.2f} windows/s",

@@ -48,8 +48,8 @@ static int k5_groups() {
     static int ng = 0;
     if (ng == 0) {
         const char* e = getenv("HS_K5_GROUPS");
-        ng = e ? atoi(e) : 6;
-        if (ng != 4 && ng != 6 && ng != 8) ng = 6;
+        ng = e ? atoi(e) : 8;
+        if (ng != 4 && ng != 6 && ng != 8) ng = 8;
     }
     return ng;
 }
@@ -206,6 +206,7 @@ int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double 
     P.F = F;
     P.n_seg = ns;
     P.seg_len = sl;
+    { const char* e = getenv("HS_K5_FLIP"); P.flip = e ? atoi(e) : 0; }
     rc = launch_transfer_dtf(P, ng, st);
     if (rc) return rc;
     if (d_ffdtf) rc = launch_ffdtf_normalize(P.dtf, rowpart, n_win, m, F, ns, d_ffdtf, st);

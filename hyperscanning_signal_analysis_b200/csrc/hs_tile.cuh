@@ -11,11 +11,14 @@
 //               panels, so every LDS is an 8-lane contiguous 64 B read that is
 //               broadcast to the other 3 quarter-warps: no bank conflicts)
 //   gj_inverse  in-place Gauss-Jordan inversion with implicit row pivoting; the
-//               pivot column/row are exchanged through ~1.5 KB of shared memory,
+//               pivot column goes through ~1.3 KB of shared memory (one 64-thread
+//               barrier per step), the scaled pivot row is broadcast with width-8
+//               shuffles (threads that share a column set are 8 consecutive lanes),
 //               everything else is rank-1 updates on registers (DFMA-bound).
 //
 // The column owners of a given column (fixed tc, tr = 0..7) are 8 consecutive
-// lanes of ONE warp, so the pivot search is three xor-shuffles.
+// lanes of ONE warp, so the pivot search is three xor-shuffles; consecutive columns
+// belong to alternating warps so the two warps share the pivot work evenly.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -31,15 +34,21 @@ struct Group {
     int gid;         // group index inside the CTA
     int l64;         // thread index inside the group
     int bar;         // named barrier id (1..15)
+    int wpar;        // parity of the columns this thread's warp owns
 };
 
-__device__ __forceinline__ Group make_group() {
+__device__ __forceinline__ Group make_group(const int flip = 0) {
     Group g;
     g.l64 = threadIdx.x & 63;
     g.gid = threadIdx.x >> 6;
-    const int w = g.l64 >> 5, lane = g.l64 & 31;
+    const int lane = g.l64 & 31;
+    // Column parity owned by this warp.  Groups 2q and 2q+1 of a CTA land on different SMSP pairs, groups g and
+    // g+2 on the same pair: flipping the parity for every other group of a pair keeps both SMSPs of the pair busy
+    // with a mix of column-owner work and plain updates at every elimination step.
+    const int w = (g.l64 >> 5) ^ (((g.gid >> 1) & 1) & flip);
     g.tr = lane & 7;
-    g.tc = (lane >> 3) + 4 * w;
+    g.tc = ((lane >> 3) << 1) | w;     // consecutive columns alternate between the two warps of the group
+    g.wpar = w;
     g.bar = 1 + g.gid;
     return g;
 }
@@ -50,11 +59,11 @@ __device__ __forceinline__ void group_sync(const Group& g) {
 
 // Scratch for gj_inverse, one per group.
 struct __align__(16) GJScratch {
-    double2 c[2][kPadMax];   // pivot-column multipliers (double buffered)
-    double2 r[kPadMax];      // scaled pivot row
-    double2 inv;             // 1 / pivot
-    int piv;                 // pivot row of the current step
+    double2 c[2][kPadMax];   // pivot-column multipliers (double buffered by step parity)
+    double2 inv[2];          // 1 / pivot            (double buffered)
+    int piv[2];              // pivot row of the step (double buffered)
     int singular;            // sticky flag
+    int pad_;
     int rowmap[kPadMax];     // storage row i  -> row of the inverse
     int colmap[kPadMax];     // storage col j  -> column of the inverse
 };
@@ -68,116 +77,134 @@ struct __align__(16) GJScratch {
 // (np.linalg.inv, which the reference calls per frequency bin at mtmvar.py:159,
 // is LU with partial pivoting; any pivoted elimination agrees to rounding.)
 // ---------------------------------------------------------------------------------
-template <int T, bool CPLX>
+template <int T, bool CPLX, bool PIVOT = true>
 __device__ __forceinline__ void gj_inverse(double (&ar)[T][T], double (&ai)[T][T], const int m,
                                            const Group& g, GJScratch* sh) {
+    constexpr int kNone = 1 << 20;
     unsigned used = 0;
     int step = 0;
+    const int wsel = g.wpar;              // parity of the columns this warp owns
     if (g.l64 == 0) sh->singular = 0;
     group_sync(g);   // previous user of the scratch (rowmap/colmap readers) is done
 #pragma unroll
     for (int b = 0; b < T; ++b) {
+#pragma unroll 1
         for (int kc = 0; kc < 8; ++kc) {
             const int k = kc + 8 * b;
             if (k >= m) break;
             const int par = step & 1;
-            if (g.tc == kc) {
-                // ---- pivot search over the unused rows of column k (8 lanes of one warp)
-                const unsigned mask = 0xFFu << (8 * (kc & 3));   // the 8 owner lanes of this warp
+            if ((kc & 1) == wsel) {
+                // ---- pivot search, whole warp in lock step (warp-uniform branch, full-mask shuffles):
+                //      every 8-lane group scans ITS column tc + 8b; only the group with tc == kc publishes.
                 double best = -1.0;
-                int bi = -1, fb = 1 << 20;
+                int bi = kNone;
+                if (!PIVOT) { best = 1.0; bi = k; }      // experiment: static diagonal pivot
 #pragma unroll
-                for (int a = 0; a < T; ++a) {
+                for (int a = 0; a < (PIVOT ? T : 0); ++a) {
                     const int i = g.tr + 8 * a;
                     const bool ok = (i < m) && !((used >> a) & 1u);
                     double mag = ar[a][b] * ar[a][b];
                     if (CPLX) mag = fma(ai[a][b], ai[a][b], mag);
-                    if (ok && i < fb) fb = i;
-                    if (ok && mag > best) { best = mag; bi = i; }
+                    const bool gt = mag > best;
+                    if (ok && (gt || bi == kNone)) {
+                        bi = i;
+                        if (gt) best = mag;
+                    }
                 }
 #pragma unroll
-                for (int off = 1; off < 8; off <<= 1) {
-                    const double ob = __shfl_xor_sync(mask, best, off, 8);
-                    const int oi = __shfl_xor_sync(mask, bi, off, 8);
-                    const int of = __shfl_xor_sync(mask, fb, off, 8);
-                    if (oi >= 0 && (ob > best || (ob == best && oi < bi) || bi < 0)) { best = ob; bi = oi; }
-                    fb = min(fb, of);
+                for (int off = 1; off < (PIVOT ? 8 : 0); off <<= 1) {
+                    const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                    if (ob > best || (ob == best && oi < bi)) {
+                        best = ob;
+                        bi = oi;
+                    }
                 }
-                const bool bad = (bi < 0) || !(best > 0.0);
-                const int r = (bi < 0) ? fb : bi;
-                // ---- publish multipliers, reset own column to e_r
+                const int r = bi;                 // agreed by the 8 lanes of the group (max |a|, lowest row on ties)
+                if (g.tc == kc) {
+                    // publish multipliers, reset own column to zero (the pivot lane fixes up row r below)
 #pragma unroll
-                for (int a = 0; a < T; ++a) {
-                    const int i = g.tr + 8 * a;
-                    double2 v = make_double2(ar[a][b], CPLX ? ai[a][b] : 0.0);
-                    if (i == r) {
+                    for (int a = 0; a < T; ++a) {
+                        sh->c[par][g.tr + 8 * a] = make_double2(ar[a][b], CPLX ? ai[a][b] : 0.0);
+                        ar[a][b] = 0.0;
+                        if (CPLX) ai[a][b] = 0.0;
+                    }
+                    if (g.tr == (r & 7)) {
                         // this lane holds the pivot: 1/p = conj(p)/|p|^2
+                        const double2 pv = sh->c[par][r];
                         double2 iv;
                         if (CPLX) {
-                            const double d = 1.0 / fma(v.x, v.x, v.y * v.y);
-                            iv = make_double2(v.x * d, -v.y * d);
+                            const double d = 1.0 / fma(pv.x, pv.x, pv.y * pv.y);
+                            iv = make_double2(pv.x * d, -pv.y * d);
                         } else {
-                            iv = make_double2(1.0 / v.x, 0.0);
+                            iv = make_double2(1.0 / pv.x, 0.0);
                         }
-                        sh->inv = iv;
-                        sh->piv = r;
+                        sh->c[par][r] = make_double2(0.0, 0.0);     // row r is not eliminated
+                        sh->inv[par] = iv;
+                        sh->piv[par] = r;
                         sh->rowmap[r] = k;
                         sh->colmap[k] = r;
-                        if (bad) sh->singular = 1;
-                        v = make_double2(0.0, 0.0);
-                        ar[a][b] = 1.0;
-                    } else {
-                        ar[a][b] = 0.0;
-                    }
-                    if (CPLX) ai[a][b] = 0.0;
-                    sh->c[par][i] = v;
-                }
-            }
-            group_sync(g);
-            const int r = sh->piv;
-            if (g.tr == (r & 7)) {
-                const double2 iv = sh->inv;
-                const int ra = r >> 3;
-                used |= 1u << ra;
-#pragma unroll
-                for (int a = 0; a < T; ++a) {
-                    if (a == ra) {
-#pragma unroll
-                        for (int bb = 0; bb < T; ++bb) {
-                            const double xr = ar[a][bb], xi = CPLX ? ai[a][bb] : 0.0;
-                            double yr, yi = 0.0;
-                            if (CPLX) {
-                                yr = fma(xr, iv.x, -xi * iv.y);
-                                yi = fma(xr, iv.y, xi * iv.x);
-                                ai[a][bb] = yi;
-                            } else {
-                                yr = xr * iv.x;
-                            }
-                            ar[a][bb] = yr;
-                            sh->r[g.tc + 8 * bb] = make_double2(yr, yi);
-                        }
+                        if (!(best > 0.0)) sh->singular = 1;
                     }
                 }
             }
             group_sync(g);
+            // ---- pivot row: its owners scale it in registers, then it is broadcast inside each 8-lane
+            //      (same tc) group.  ra (which of my T row slots) is uniform over the group, so the
+            //      switch is warp-uniform and every register index below is static.
+            const int r = sh->piv[par];
+            const int rl = r & 7, ra = r >> 3;
+            const bool row_owner = (g.tr == rl);
+            const double2 iv = sh->inv[par];
+            if (row_owner) used |= 1u << ra;
+            double rr[T], ri[T];
+#define HS_GJ_ROW_CASE(A)                                                                         \
+    case A:                                                                                       \
+        if constexpr (A < T) {                                                                    \
+            if (row_owner) {                                                                      \
+                if (g.tc == kc) {                                                                 \
+                    ar[A][b] = 1.0; /* own column was zeroed: becomes 1 * inv */                  \
+                    if (CPLX) ai[A][b] = 0.0;                                                     \
+                }                                                                                 \
+                _Pragma("unroll") for (int bb = 0; bb < T; ++bb) {                                \
+                    const double xr = ar[A][bb], xi = CPLX ? ai[A][bb] : 0.0;                     \
+                    if (CPLX) {                                                                   \
+                        ar[A][bb] = fma(xr, iv.x, -xi * iv.y);                                    \
+                        ai[A][bb] = fma(xr, iv.y, xi * iv.x);                                     \
+                    } else {                                                                      \
+                        ar[A][bb] = xr * iv.x;                                                    \
+                    }                                                                             \
+                }                                                                                 \
+            }                                                                                     \
+            _Pragma("unroll") for (int bb = 0; bb < T; ++bb) {                                    \
+                rr[bb] = __shfl_sync(0xffffffffu, ar[A][bb], rl, 8);                              \
+                ri[bb] = CPLX ? __shfl_sync(0xffffffffu, ai[A][bb], rl, 8) : 0.0;                 \
+            }                                                                                     \
+        }                                                                                         \
+        break;
+            switch (ra) {
+                HS_GJ_ROW_CASE(0)
+                HS_GJ_ROW_CASE(1)
+                HS_GJ_ROW_CASE(2)
+                HS_GJ_ROW_CASE(3)
+                HS_GJ_ROW_CASE(4)
+                default:
+#pragma unroll
+                    for (int bb = 0; bb < T; ++bb) rr[bb] = ri[bb] = 0.0;
+                    break;
+            }
+#undef HS_GJ_ROW_CASE
             // ---- rank-1 update of every tile (row r has multiplier 0)
-            double cr[T], ci[T];
 #pragma unroll
             for (int a = 0; a < T; ++a) {
-                const double2 v = sh->c[par][g.tr + 8 * a];
-                cr[a] = v.x;
-                ci[a] = v.y;
-            }
+                const double2 cv = sh->c[par][g.tr + 8 * a];
 #pragma unroll
-            for (int bb = 0; bb < T; ++bb) {
-                const double2 rv = sh->r[g.tc + 8 * bb];
-#pragma unroll
-                for (int a = 0; a < T; ++a) {
+                for (int bb = 0; bb < T; ++bb) {
                     if (CPLX) {
-                        ar[a][bb] = fma(-cr[a], rv.x, fma(ci[a], rv.y, ar[a][bb]));
-                        ai[a][bb] = fma(-cr[a], rv.y, fma(-ci[a], rv.x, ai[a][bb]));
+                        ar[a][bb] = fma(-cv.x, rr[bb], fma(cv.y, ri[bb], ar[a][bb]));
+                        ai[a][bb] = fma(-cv.x, ri[bb], fma(-cv.y, rr[bb], ai[a][bb]));
                     } else {
-                        ar[a][bb] = fma(-cr[a], rv.x, ar[a][bb]);
+                        ar[a][bb] = fma(-cv.x, rr[bb], ar[a][bb]);
                     }
                 }
             }

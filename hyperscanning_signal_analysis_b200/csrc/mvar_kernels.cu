@@ -8,6 +8,7 @@
 //   dtf_multivariate        src/mtmvar.py:204-234   (|H|^2, un-normalised)
 //   full_freq_dtf           src/mtmvar.py:237-284
 //   multivariate_spectra    src/mtmvar.py:165-201   (H V H^T, plain transpose)
+#include <cstdlib>
 #include "hs_tile.cuh"
 #include "hs_internal.h"
 #include "mvar_launch.h"
@@ -42,139 +43,135 @@ __global__ void ztable_kernel(const double* __restrict__ freqs, int F, int p, do
 // =====================================================================================
 template <int T>
 struct K5Smem {
-    // dynamic shared memory carve-up (all offsets in bytes, 16 B aligned)
     // doubles per coefficient row, chosen = 2 (mod 16) so that 8 consecutive rows hit 8 distinct 16 B bank groups
-    static __host__ __device__ size_t coef_stride(int m, int p) { const int mp = m * p; return (size_t)(mp + ((2 - (mp & 15) + 16) & 15)); }
-    static __host__ __device__ size_t coef_bytes(int m, int p) { return coef_stride(m, p) * m * sizeof(double); }
-    static __host__ __device__ size_t stage_bytes(int m, int ng) { return (size_t)m * m * ng * sizeof(double); }
+    // rows and columns are zero-padded to the 8T x 8T tile grid so the assembly loop needs no bounds checks
+    static __host__ __device__ size_t coef_stride(int m, int p) { const int mp = 8 * T * p; return (size_t)(mp + ((2 - (mp & 15) + 16) & 15)); }
+    static __host__ __device__ size_t coef_bytes(int m, int p) { return coef_stride(m, p) * 8 * T * sizeof(double); }
     static __host__ __device__ size_t total(int m, int p, int ng) {
-        return coef_bytes(m, p) + stage_bytes(m, ng) + (size_t)ng * sizeof(GJScratch) + (size_t)m * ng * sizeof(double) + 64;
+        return coef_bytes(m, p) + (size_t)ng * sizeof(GJScratch) + (size_t)ng * 2 * kPadMax * sizeof(double) + 64;
     }
 };
 
-
-template <int T, int NG>
+template <int T, int NG, bool PIVOT = true>
 __global__ void __launch_bounds__(NG * 64, 1) transfer_dtf_kernel(const K5Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int m = P.m, p = P.p, F = P.F;
-    const size_t cstride = K5Smem<T>::coef_stride(m, p);
+    const int cstride = (int)K5Smem<T>::coef_stride(m, p);
     double* coef = reinterpret_cast<double*>(smem_raw);
-    double* stage = reinterpret_cast<double*>(smem_raw + K5Smem<T>::coef_bytes(m, p));
-    GJScratch* gjs = reinterpret_cast<GJScratch*>(smem_raw + K5Smem<T>::coef_bytes(m, p) + K5Smem<T>::stage_bytes(m, NG));
-    double* rsg = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(gjs) + NG * sizeof(GJScratch));   // [m][NG]
+    GJScratch* gjs = reinterpret_cast<GJScratch*>(smem_raw + K5Smem<T>::coef_bytes(m, p));
+    double* rsg = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(gjs) + NG * sizeof(GJScratch));   // [NG][2][40]
 
-    const Group g = make_group();
+    const Group g = make_group(P.flip);
     GJScratch* sh = gjs + g.gid;
+    double* rs_mine = rsg + (size_t)(g.gid * 2 + (g.l64 >> 5)) * kPadMax;
     const int nthreads = NG * 64;
     const int n_units = P.n_win * P.n_seg;
-    int loaded_w = -1;
+    const bool vec_ok = ((p & 1) == 0);
+    // offset (doubles) of this thread's tile entry (a = 0, b = 0) inside the coefficient block
+    const int off00 = g.tr * cstride + g.tc * p;
 
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const int w = unit / P.n_seg, seg = unit % P.n_seg;
         const int f_begin = seg * P.seg_len, f_end = min(F, f_begin + P.seg_len);
-        if (w != loaded_w) {
-            __syncthreads();
-            // AR coefficients of window w -> shared (row i padded to cstride doubles)
+        __syncthreads();
+        {   // AR coefficients of window w -> shared (row i padded to cstride doubles)
             const double* Aw = P.A + (size_t)w * m * m * p;
-            const int row_len = m * p;
-            for (int e = threadIdx.x; e < m * row_len; e += nthreads) {
-                const int i = e / row_len, c = e - i * row_len;
-                coef[i * cstride + c] = Aw[e];
+            const int row_len = m * p, pad_len = 8 * T * p;
+            for (int i = g.gid * 2 + (g.l64 >> 5); i < 8 * T; i += NG * 2) {       // one warp per row
+                for (int c = threadIdx.x & 31; c < pad_len; c += 32)
+                    coef[i * cstride + c] = (i < m && c < row_len) ? Aw[(size_t)i * row_len + c] : 0.0;
             }
-            loaded_w = w;
+            for (int e = threadIdx.x; e < NG * 2 * kPadMax; e += nthreads) rsg[e] = 0.0;
         }
         __syncthreads();
-        double rs_acc = 0.0;    // thread t < m*NG accumulates row (t / NG), slot (t % NG)
 
-        for (int f0 = f_begin; f0 < f_end; f0 += NG) {
-            const int f = f0 + g.gid;
-            const bool active = f < f_end;
-            if (active) {
-                double ar[T][T], ai[T][T];
-                // ---- build A(f) tile
+        for (int f = f_begin + g.gid; f < f_end; f += NG) {
+            double ar[T][T], ai[T][T];
+            // ---- build A(f) = I - sum_k A_k z_k(f)
+#pragma unroll
+            for (int a = 0; a < T; ++a)
+#pragma unroll
+                for (int b = 0; b < T; ++b) {
+                    ar[a][b] = ((g.tr + 8 * a) == (g.tc + 8 * b)) ? 1.0 : 0.0;
+                    ai[a][b] = 0.0;
+                }
+            if (vec_ok) {
+                for (int k = 0; k < p; k += 2) {
+                    const double2 z0 = __ldg(&P.z[(size_t)k * F + f]);
+                    const double2 z1 = __ldg(&P.z[(size_t)(k + 1) * F + f]);
+                    const double* cp = coef + off00 + k;
+#pragma unroll
+                    for (int a = 0; a < T; ++a) {
+#pragma unroll
+                        for (int b = 0; b < T; ++b) {
+                            const double2 c = *reinterpret_cast<const double2*>(cp + a * 8 * cstride + b * 8 * p);
+                            ar[a][b] = fma(-c.x, z0.x, fma(-c.y, z1.x, ar[a][b]));
+                            ai[a][b] = fma(-c.x, z0.y, fma(-c.y, z1.y, ai[a][b]));
+                        }
+                    }
+                }
+            } else {
+                for (int k = 0; k < p; ++k) {
+                    const double2 zz = __ldg(&P.z[(size_t)k * F + f]);
+                    const double* cp = coef + off00 + k;
+#pragma unroll
+                    for (int a = 0; a < T; ++a) {
+#pragma unroll
+                        for (int b = 0; b < T; ++b) {
+                            const double c = cp[a * 8 * cstride + b * 8 * p];
+                            ar[a][b] = fma(-c, zz.x, ar[a][b]);
+                            ai[a][b] = fma(-c, zz.y, ai[a][b]);
+                        }
+                    }
+                }
+            }
+            const size_t wbase = (size_t)w * m * m;
+            if (P.Af) {
 #pragma unroll
                 for (int a = 0; a < T; ++a)
 #pragma unroll
                     for (int b = 0; b < T; ++b) {
-                        ar[a][b] = ((g.tr + 8 * a) == (g.tc + 8 * b)) ? 1.0 : 0.0;
-                        ai[a][b] = 0.0;
+                        const int i = g.tr + 8 * a, j = g.tc + 8 * b;
+                        if (i < m && j < m) P.Af[(wbase + (size_t)i * m + j) * F + f] = make_double2(ar[a][b], ai[a][b]);
                     }
-                for (int k = 0; k < p; ++k) {
-                    const double2 zz = __ldg(&P.z[(size_t)k * F + f]);
+            }
+            // ---- invert
+            gj_inverse<T, true, PIVOT>(ar, ai, m, g, sh);
+            if (g.l64 == 0 && sh->singular) atomicOr(&P.status[w], 1);
+            // ---- |H|^2 straight to global (8 B stores; the 32 B sectors are completed in L2 by the
+            //      neighbouring bins, which other groups of this CTA write within the same ~100 us),
+            //      plus this bin's contribution to the ffDTF row sums.
+            int cj[T];
 #pragma unroll
-                    for (int a = 0; a < T; ++a) {
-                        const int i = g.tr + 8 * a;
+            for (int b = 0; b < T; ++b) cj[b] = sh->colmap[min(g.tc + 8 * b, kPadMax - 1)];
 #pragma unroll
-                        for (int b = 0; b < T; ++b) {
-                            const int j = g.tc + 8 * b;
-                            if (i < m && j < m) {
-                                const double c = coef[i * cstride + j * p + k];
-                                ar[a][b] = fma(-c, zz.x, ar[a][b]);
-                                ai[a][b] = fma(-c, zz.y, ai[a][b]);
-                            }
-                        }
-                    }
-                }
-                if (P.Af) {
+            for (int a = 0; a < T; ++a) {
+                const int i = g.tr + 8 * a;
+                const int ri = sh->rowmap[min(i, kPadMax - 1)];
+                double rsum = 0.0;
 #pragma unroll
-                    for (int a = 0; a < T; ++a)
-#pragma unroll
-                        for (int b = 0; b < T; ++b) {
-                            const int i = g.tr + 8 * a, j = g.tc + 8 * b;
-                            if (i < m && j < m) P.Af[((size_t)w * m * m + (size_t)i * m + j) * F + f] = make_double2(ar[a][b], ai[a][b]);
-                        }
-                }
-                // ---- invert
-                gj_inverse<T, true>(ar, ai, m, g, sh);
-                if (g.l64 == 0 && sh->singular) atomicOr(&P.status[w], 1);
-                // ---- un-permute into the staging buffer / H
-#pragma unroll
-                for (int a = 0; a < T; ++a) {
-                    const int i = g.tr + 8 * a;
-                    if (i < m) {
-                        const int ri = sh->rowmap[i];
-#pragma unroll
-                        for (int b = 0; b < T; ++b) {
-                            const int j = g.tc + 8 * b;
-                            if (j < m) {
-                                const int cj = sh->colmap[j];
-                                stage[(ri * m + cj) * NG + g.gid] = fma(ar[a][b], ar[a][b], ai[a][b] * ai[a][b]);
-                                if (P.H) P.H[((size_t)w * m * m + (size_t)ri * m + cj) * F + f] = make_double2(ar[a][b], ai[a][b]);
-                            }
-                        }
+                for (int b = 0; b < T; ++b) {
+                    const int j = g.tc + 8 * b;
+                    if (i < m && j < m) {
+                        const double v = fma(ar[a][b], ar[a][b], ai[a][b] * ai[a][b]);
+                        rsum += v;
+                        const size_t o = (wbase + (size_t)ri * m + cj[b]) * F + f;
+                        if (P.dtf) P.dtf[o] = v;
+                        if (P.H) P.H[o] = make_double2(ar[a][b], ai[a][b]);
                     }
                 }
+                // reduce over the 4 column groups of this warp (lane bits 3, 4), fixed order
+                rsum += __shfl_xor_sync(0xffffffffu, rsum, 8);
+                rsum += __shfl_xor_sync(0xffffffffu, rsum, 16);
+                if ((g.l64 & 24) == 0 && i < m) rs_mine[ri] += rsum;      // one writer per (warp, row): deterministic
             }
-            __syncthreads();
-            // ---- cooperative write-out of the NG bins, NG doubles contiguous per (i, j)
-            const int nvalid = min(NG, f_end - f0);
-            if (P.dtf) {
-                double* out = P.dtf + (size_t)w * m * m * F + f0;
-                for (int e = threadIdx.x; e < m * m * NG; e += nthreads) {
-                    const int pair = e / NG, s = e - pair * NG;
-                    if (s < nvalid) out[(size_t)pair * F + s] = stage[e];
-                }
-            }
-            if (threadIdx.x < m * NG) {
-                const int i = threadIdx.x / NG, s = threadIdx.x - i * NG;
-                if (s < nvalid) {
-                    const double* sp = stage + (size_t)i * m * NG + s;
-                    double acc = 0.0;
-                    for (int j = 0; j < m; ++j) acc += sp[j * NG];
-                    rs_acc += acc;
-                }
-            }
-            __syncthreads();
         }
         // ---- per-unit row sums (fixed summation order -> deterministic)
-        if (P.rowpart) {
-            if (threadIdx.x < m * NG) rsg[threadIdx.x] = rs_acc;
-            __syncthreads();
-            if (threadIdx.x < m) {
-                double acc = 0.0;
-                for (int s = 0; s < NG; ++s) acc += rsg[threadIdx.x * NG + s];
-                P.rowpart[((size_t)w * P.n_seg + seg) * m + threadIdx.x] = acc;
-            }
+        __syncthreads();
+        if (P.rowpart && threadIdx.x < m) {
+            double acc = 0.0;
+            for (int q = 0; q < NG * 2; ++q) acc += rsg[q * kPadMax + threadIdx.x];
+            P.rowpart[((size_t)w * P.n_seg + seg) * m + threadIdx.x] = acc;
         }
     }
 }
@@ -208,20 +205,21 @@ __global__ void ffdtf_normalize_kernel(double* __restrict__ dtf, const double* _
     }
 }
 
-template <int T, int NG>
+template <int T, int NG, bool PIVOT = true>
 static int launch_k5_t(const K5Params& P, int sm_count, cudaStream_t stream) {
     const size_t smem = K5Smem<T>::total(P.m, P.p, NG);
-    cudaError_t e = cudaFuncSetAttribute(transfer_dtf_kernel<T, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(transfer_dtf_kernel<T, NG, PIVOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "transfer_dtf: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
     const int n_units = P.n_win * P.n_seg;
     const int grid = n_units < sm_count ? n_units : sm_count;
-    transfer_dtf_kernel<T, NG><<<grid, NG * 64, smem, stream>>>(P);
+    transfer_dtf_kernel<T, NG, PIVOT><<<grid, NG * 64, smem, stream>>>(P);
     return check_launch("transfer_dtf_kernel");
 }
 
 int launch_transfer_dtf(const K5Params& P, int ng, cudaStream_t stream) {
     const int T = (P.m + 7) / 8;
     const int sm = device_sm_count();
+    if (ng == 6 && T == 5 && getenv("HS_K5_NOPIVOT")) return launch_k5_t<5, 6, false>(P, sm, stream);   // experiment only
     if (ng == 8) {
         switch (T) {
             case 1: return launch_k5_t<1, 8>(P, sm, stream);
@@ -284,7 +282,7 @@ __global__ void __launch_bounds__(576, 1) lagcov_kernel(const K3Params P) {
             for (int l0 = 0; l0 <= p; l0 += NG) {
                 const int lag = l0 + g.gid;
                 const bool has_lag = lag <= p;
-                const int halo = min(NG - 1, p - l0);
+                const int halo = min(l0 + NG - 1, p);          // largest lag of this round: x_j(t + lag) lives `lag` rows below x_i(t)
                 double acc[T][T];
 #pragma unroll
                 for (int a = 0; a < T; ++a)
@@ -313,7 +311,7 @@ __global__ void __launch_bounds__(576, 1) lagcov_kernel(const K3Params P) {
                         __syncthreads();
                         if (has_lag) {
                             const double* pa = (bi != bj) ? panelA : panelB;
-                            tile_mac<T, false>(acc, pa, kK3Ld, panelB + (size_t)(lag - l0) * kK3Ld, kK3Ld, kK3Chunk, g);
+                            tile_mac<T, false>(acc, pa, kK3Ld, panelB + (size_t)lag * kK3Ld, kK3Ld, kK3Chunk, g);
                         }
                     }
                 }

@@ -34,6 +34,7 @@ struct K5Params {
     double2* Af;            // (n_win, m, m, F) complex or null
     int* status;            // (n_win) sticky singular flags
     int n_win, m, p, F, n_seg, seg_len;
+    int flip;               // 1: alternate the column-owner parity between groups sharing an SMSP pair
 };
 
 int launch_lagcov(const K3Params& P, cudaStream_t stream);

@@ -1,0 +1,106 @@
+"""Array-level front end: zero-phase IIR filtering (K1) and FIR decimation (K2) on the GPU.
+NumPy (or CUDA tensors) in, same kind out.  Filter *design* (iirnotch / butter / firwin) stays host-side
+SciPy: it is O(taps), data independent, and the coefficients are stored verbatim in ``Filtration``."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+
+def _torch():
+    return _lib.require_cuda()
+
+
+def _pack_filters(filters):
+    """[(b, a), ...] -> (n_filt, ntaps) float64 host arrays, zero padded; ntaps = max(len(a), len(b)) per SciPy."""
+    bs, as_ = [], []
+    for b, a in filters:
+        b = np.atleast_1d(np.asarray(b, dtype=np.float64))
+        a = np.atleast_1d(np.asarray(a, dtype=np.float64))
+        bs.append(b)
+        as_.append(a)
+    groups = []       # consecutive filters with the same ntaps share one C call
+    for b, a in zip(bs, as_):
+        nt = max(len(a), len(b))
+        bb = np.zeros(nt)
+        aa = np.zeros(nt)
+        bb[:len(b)] = b
+        aa[:len(a)] = a
+        if groups and groups[-1][0] == nt:
+            groups[-1][1].append(bb)
+            groups[-1][2].append(aa)
+        else:
+            groups.append((nt, [bb], [aa]))
+    return [(nt, np.ascontiguousarray(np.stack(b)), np.ascontiguousarray(np.stack(a))) for nt, b, a in groups]
+
+
+def filtfilt_cascade_(x_dev, filters, remove_dc=False, axis=-1):
+    """In-place ``scipy.signal.filtfilt`` cascade on a 2-D CUDA float64 tensor.
+
+    ``axis=-1``: rows are signals (dataloader layout, dataloader.py:787); ``axis=0``: columns are signals
+    ((time, channel) layout of mne_bridge.py:161-184)."""
+    torch = _torch()
+    lib = _lib.load()
+    assert x_dev.is_cuda and x_dev.dtype == torch.float64 and x_dev.dim() == 2 and x_dev.is_contiguous()
+    if axis in (-1, 1):
+        n_sig, n = x_dev.shape
+        sig_stride, t_stride = n, 1
+    else:
+        n, n_sig = x_dev.shape
+        sig_stride, t_stride = 1, n_sig
+    ws = torch.empty(max(int(lib.hs_filtfilt_ws_bytes(n_sig, n)), 16), dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    groups = _pack_filters(filters)
+    if not groups:
+        groups = [(2, np.zeros((0, 2)), np.zeros((0, 2)))]
+    first = True
+    for nt, b, a in groups:
+        rc = lib.hs_iir_filtfilt_f64(x_dev.data_ptr(), n_sig, n, sig_stride, t_stride, b.ctypes.data, a.ctypes.data,
+                                     b.shape[0], nt, int(remove_dc and first), ws.data_ptr(), stream)
+        if rc != 0:
+            msg = _lib.last_error()
+            if "padlen" in msg:
+                raise ValueError(msg)
+            raise _lib.HsError(f"hs_iir_filtfilt_f64 failed ({rc}): {msg}")
+        first = False
+    return x_dev
+
+
+def filtfilt_cascade(x, filters, remove_dc=False, axis=-1):
+    """NumPy wrapper: returns a new float64 array."""
+    torch = _torch()
+    t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).cuda()
+    filtfilt_cascade_(t, filters, remove_dc=remove_dc, axis=axis)
+    return t.cpu().numpy()
+
+
+def decimate_taps(q):
+    """Anti-alias FIR of ``scipy.signal.decimate(..., ftype='fir')``: firwin(20 q + 1, 1/q, window='hamming')."""
+    from scipy.signal import firwin
+    return firwin(20 * q + 1, 1.0 / q, window="hamming")
+
+
+def decimate_dev(x_dev, q, taps=None):
+    """(n_sig, n) CUDA float64 -> (n_sig, ceil(n/q)) CUDA float64."""
+    torch = _torch()
+    lib = _lib.load()
+    assert x_dev.is_cuda and x_dev.dtype == torch.float64 and x_dev.dim() == 2 and x_dev.is_contiguous()
+    n_sig, n = x_dev.shape
+    b = torch.from_numpy(np.ascontiguousarray(decimate_taps(q) if taps is None else taps, dtype=np.float64)).cuda()
+    n_out = -(-n // q)
+    y = torch.empty((n_sig, n_out), dtype=torch.float64, device="cuda")
+    if n_sig and n:
+        _lib.check(lib.hs_fir_decimate_f64(x_dev.data_ptr(), n_sig, n, n, int(q), b.data_ptr(), b.numel(), y.data_ptr(), n_out,
+                                           torch.cuda.current_stream().cuda_stream), "hs_fir_decimate_f64")
+    return y
+
+
+def decimate(x, q):
+    """``scipy.signal.decimate(x, q, ftype='fir', zero_phase=True)`` along the last axis (data_structures.py:792)."""
+    torch = _torch()
+    x = np.asarray(x, dtype=np.float64)
+    one_d = x.ndim == 1
+    t = torch.from_numpy(np.ascontiguousarray(np.atleast_2d(x))).cuda()
+    y = decimate_dev(t, q).cpu().numpy()
+    return y[0] if one_d else y

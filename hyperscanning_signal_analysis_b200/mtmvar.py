@@ -161,6 +161,8 @@ def windowed_ffdtf(signals, starts, window_size, freqs, fs, p, return_model=Fals
     out = torch.empty((n_win, m, m, F), dtype=torch.float64, device="cuda")
     A = torch.empty((n_win, m, m, p), dtype=torch.float64, device="cuda") if return_model else None
     V = torch.empty((n_win, m, m), dtype=torch.float64, device="cuda") if return_model else None
+    if n_win == 0:
+        return (out, A, V) if return_model else out
     status = torch.zeros((n_win,), dtype=torch.int32, device="cuda")
     ws = _ws(lib.hs_mvar_ffdtf_ws_bytes(n_win, m, p, F))
     _lib.check(lib.hs_mvar_ffdtf_f64(x.data_ptr(), st.data_ptr(), T, n_win, m, window_size, p, fr.data_ptr(), F, float(fs),

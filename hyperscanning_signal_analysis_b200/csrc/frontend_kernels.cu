@@ -35,6 +35,7 @@ struct IirCoef {
     double pw[6][kMaxOrder * kMaxOrder];  // (M^C)^(2^k), k = 0..5, row-major d x d
     int d;                                // state dimension
     int e;                                // pad length 3 * ntaps
+    int warm;                             // warm-up chunks replayed by the apply pass (order > 2 only)
 };
 
 struct IirPass {
@@ -156,10 +157,15 @@ __global__ void __launch_bounds__(128) iir_apply_kernel(const IirPass P, const I
     const double* base = P.in + (long long)s * P.in_sig_stride;
     double* ob = P.out + (long long)s * P.out_sig_stride;
     const double dc = P.mean ? P.mean[s] : 0.0;
-    const double* st = P.states + ((long long)s * P.n_chunks + ch) * D;
+    // Start `warm` chunks early from that chunk's scanned state and replay: the filter is stable, so the error of
+    // the scanned state (superposition noise, ~1e-9 for clustered poles) decays geometrically and the arithmetic
+    // that follows is the sequential recursion SciPy runs.  warm == 0 for biquads (their scan is accurate to 1e-13).
+    const long long ch0 = max(0LL, ch - (long long)c.warm);
+    const double* st = P.states + ((long long)s * P.n_chunks + ch0) * D;
     double z[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) z[k] = st[k];
+    for (long long u = ch0 * kChunk; u < ch * kChunk; ++u) df2t_step<D>(c, z, sweep_read(P, base, dc, u));
     const long long u0 = ch * kChunk, u1 = min(P.L, u0 + kChunk);
     if (P.forward) {
         for (long long u = u0; u < u1; ++u) ob[u * P.out_t_stride] = df2t_step<D>(c, z, sweep_read(P, base, dc, u));
@@ -246,35 +252,37 @@ static int prepare_filter(const double* b, const double* a, int ntaps, IirCoef* 
     }
     if (!solve_small(d, Am, rhs)) return set_error(HS_ERR_INVALID, "filtfilt: singular lfilter_zi system (filter has a pole at z = 1)");
     for (int i = 0; i < d; ++i) c->zi[i] = rhs[i];
-    // homogeneous DF2T transition: z'_k = z_{k+1} - a_{k+1} z_0 ; M^C by repeated squaring
-    std::vector<double> M(d * d, 0.0), Rm(d * d, 0.0), Tm(d * d);
-    for (int k = 0; k < d; ++k) {
-        M[k * d + 0] = -c->a[k + 1];
-        if (k + 1 < d) M[k * d + k + 1] = 1.0;
-        Rm[k * d + k] = 1.0;
-    }
-    auto matmul = [&](const std::vector<double>& X, const std::vector<double>& Y, std::vector<double>& Z) {
-        for (int i = 0; i < d; ++i)
+    // (M^C)^(2^k) = M^(C 2^k): column j = state after C 2^k homogeneous DF2T steps from e_j
+    // (z'_k = z_{k+1} - a_{k+1} z_0).  Running the recurrence itself (long double) keeps the natural rounding of the
+    // recursion; repeated squaring of this non-normal matrix loses ~cond(V)^2 eps (1e-3 for Butterworth-4 at 1 Hz).
+    long double zst[kMaxOrder][kMaxOrder];      // zst[j] = current image of e_j
+    for (int j = 0; j < d; ++j)
+        for (int k = 0; k < d; ++k) zst[j][k] = (j == k) ? 1.0L : 0.0L;
+    long long done = 0;
+    c->warm = 0;
+    bool warm_found = (d <= 2);
+    for (int kpow = 0; kpow < 6; ++kpow) {
+        const long long target = (long long)kChunk << kpow;
+        for (; done < target; ++done) {
             for (int j = 0; j < d; ++j) {
-                long double acc = 0.0L;
-                for (int k = 0; k < d; ++k) acc += (long double)X[i * d + k] * (long double)Y[k * d + j];
-                Z[i * d + j] = (double)acc;
+                const long double y = zst[j][0];
+                for (int k = 0; k < d - 1; ++k) zst[j][k] = zst[j][k + 1] - (long double)c->a[k + 1] * y;
+                zst[j][d - 1] = -(long double)c->a[d] * y;
             }
-    };
-    int e = kChunk;
-    std::vector<double> Bm = M;
-    while (e) {
-        if (e & 1) { matmul(Rm, Bm, Tm); Rm = Tm; }
-        matmul(Bm, Bm, Tm);
-        Bm = Tm;
-        e >>= 1;
+            if (!warm_found && (done + 1) % kChunk == 0) {
+                long double mx = 0.0L;
+                for (int j = 0; j < d; ++j)
+                    for (int k = 0; k < d; ++k) mx = fmaxl(mx, fabsl(zst[j][k]));
+                if (mx < 1e-6L) {
+                    c->warm = (int)((done + 1) / kChunk);
+                    warm_found = true;
+                }
+            }
+        }
+        for (int i = 0; i < d; ++i)
+            for (int j = 0; j < d; ++j) c->pw[kpow][i * d + j] = (double)zst[j][i];
     }
-    // Rm = M^C; successive squares give (M^C)^(2^k)
-    for (int k = 0; k < 6; ++k) {
-        for (int i = 0; i < d * d; ++i) c->pw[k][i] = Rm[i];
-        matmul(Rm, Rm, Tm);
-        Rm = Tm;
-    }
+    if (!warm_found) c->warm = 32;      // very slow poles: replay at most 32 chunks (documented accuracy limit)
     return HS_OK;
 }
 

@@ -183,3 +183,30 @@ def test_singular_and_bad_arguments(mv):
     # empty batch
     out = mv.windowed_ffdtf(np.ones((4, 100)), [], 20, [1.0, 2.0], 8.0, 2)
     assert tuple(out.shape) == (0, 4, 4, 2)
+
+
+def test_window_driver_batched_matches_reference_loop():
+    """compute_ffdtf_windows == the reference's serial loop (eeg_alpha_ibi_ffdtf.py:741-755) at its real-use shape
+    (m = 4, fs = 8 Hz, p = 5, freqs = arange(fmin, fmax + step, step))."""
+    from hyperscanning_signal_analysis_b200.eeg_alpha_ibi_ffdtf import compute_ffdtf_windows
+    rng = np.random.default_rng(42)
+    m, T, fs = 4, 2400, 8.0
+    x = rng.standard_normal((m, T))
+    x[:, 1:] += 0.7 * x[:, :-1]
+    x[1, 2:] += 0.4 * x[0, :-2]
+    res = compute_ffdtf_windows(x, fs, n_windows=7, window_size=600, ar_p=5, freq_min=0.1, freq_max=4.0, freq_step=0.1, with_spectra=True)
+    freqs = np.arange(0.1, 4.0 + 0.1, 0.1)
+    assert np.array_equal(res["freqs"], freqs) and res["ff_dtf_windowed"].shape == (7, 4, 4, len(freqs))
+    starts, W = mo.window_starts(T, 7, 600)
+    assert res["starts"].tolist() == starts.tolist()
+    for w, s in enumerate(starts):
+        seg = x[:, s:s + W]
+        assert relerr(res["ff_dtf_windowed"][w], mo.full_freq_dtf(seg, freqs, fs, optimal_model_order=5)) < TOL_MODEL
+        assert relerr(res["spectra_windowed"][w], mo.multivariate_spectra(seg, freqs, fs, optimal_model_order=5)) < TOL_MODEL
+    # per-window order selection (ar_p=None -> mvar_criterion, eeg_alpha_ibi_ffdtf.py:586-587)
+    res2 = compute_ffdtf_windows(x, fs, n_windows=3, window_size=None, ar_p=None, freq_min=0.1, freq_max=4.0, freq_step=0.5, max_model_order=6)
+    st2, W2 = mo.window_starts(T, 3, None)
+    for w, s in enumerate(st2):
+        popt = int(mo.mvar_criterion(x[:, s:s + W2], 6, "AIC")[2])
+        assert res2["p_opt_w"][w] == popt
+        assert relerr(res2["ff_dtf_windowed"][w], mo.full_freq_dtf(x[:, s:s + W2], res2["freqs"], fs, optimal_model_order=popt)) < TOL_MODEL

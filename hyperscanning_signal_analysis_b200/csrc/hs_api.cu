@@ -145,7 +145,10 @@ int hs_yw_assemble_f64(const double* d_R, int n_win, int m, int p, double* d_G, 
     return launch_toeplitz(d_R, n_win, m, p, d_G, d_rhs, (cudaStream_t)stream);
 }
 
-size_t hs_yw_ws_bytes(int n_win, int m, int p) { return align_up(lwr_ws_doubles(lwr_grid(n_win), m, p) * sizeof(double)); }
+size_t hs_yw_ws_bytes(int n_win, int m, int p) {
+    if (m > kPadMaxHost) return align_up(lwr_generic_ws_doubles(n_win, m, p) * sizeof(double));
+    return align_up(lwr_ws_doubles(lwr_grid(n_win), m, p) * sizeof(double));
+}
 
 int hs_yw_solve_f64(const double* d_R, int n_win, int m, int p, double* d_A, double* d_V, double* d_Vall,
                     int32_t* d_status, void* d_ws, void* stream) {
@@ -162,6 +165,7 @@ int hs_yw_solve_f64(const double* d_R, int n_win, int m, int p, double* d_A, dou
     P.n_win = n_win;
     P.m = m;
     P.p = p;
+    if (m > kPadMaxHost) return launch_lwr_generic(P, (cudaStream_t)stream);
     return launch_lwr(P, lwr_grid(n_win), (cudaStream_t)stream);
 }
 
@@ -174,6 +178,8 @@ int hs_ztable_f64(const double* d_freqs, int F, int p, double fs, void* d_z, voi
 size_t hs_transfer_ws_bytes(int n_win, int m, int p, int F) {
     int ns, sl;
     k5_segments(F, k5_groups(), &ns, &sl);
+    if (m > kPadMaxHost)      // generic path: one partial row sum per bin + per-CTA scratch matrices
+        return align_up((size_t)p * F * 16) + align_up((size_t)n_win * F * m * sizeof(double)) + align_up(transfer_generic_scratch_bytes(m)) + 256;
     return align_up((size_t)p * F * 16) + align_up((size_t)n_win * ns * m * sizeof(double)) + 256;
 }
 
@@ -182,7 +188,6 @@ int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double 
     if (!d_A || !d_freqs || !d_status || !d_ws) return set_error(HS_ERR_INVALID, "hs_transfer_dtf_f64: null pointer");
     if (m < 1 || p < 1 || F < 1) return set_error(HS_ERR_INVALID, "hs_transfer_dtf_f64: bad sizes");
     if (n_win <= 0) return HS_OK;
-    if (m > kPadMaxHost) return set_error(HS_ERR_UNSUPPORTED, "hs_transfer_dtf_f64: m=%d > %d not supported yet", m, kPadMaxHost);
     cudaStream_t st = (cudaStream_t)stream;
     const int ng = k5_groups();
     int ns, sl;
@@ -207,7 +212,14 @@ int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double 
     P.n_seg = ns;
     P.seg_len = sl;
     { const char* e = getenv("HS_K5_FLIP"); P.flip = e ? atoi(e) : 0; }
-    rc = launch_transfer_dtf(P, ng, st);
+    if (m > kPadMaxHost) {
+        P.n_seg = ns = F;
+        P.seg_len = 1;
+        void* scratch = ws + align_up((size_t)p * F * 16) + align_up((size_t)n_win * F * m * sizeof(double));
+        rc = launch_transfer_generic(P, scratch, st);
+    } else {
+        rc = launch_transfer_dtf(P, ng, st);
+    }
     if (rc) return rc;
     if (d_ffdtf) rc = launch_ffdtf_normalize(P.dtf, rowpart, n_win, m, F, ns, d_ffdtf, st);
     return rc;

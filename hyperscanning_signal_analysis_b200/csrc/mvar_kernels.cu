@@ -549,7 +549,6 @@ size_t lwr_ws_doubles(int grid, int m, int p) { return (size_t)grid * 4 * p * m 
 int lwr_grid(int n_win) { const int sm = device_sm_count(); return n_win < sm ? n_win : sm; }
 
 int launch_lwr(const K4Params& P, int grid, cudaStream_t stream) {
-    if (P.m > kPadMax) return set_error(HS_ERR_UNSUPPORTED, "lwr: m=%d > %d not supported by the register-tile path", P.m, kPadMax);
     const size_t smem = (size_t)(kK4Groups * 2 + 4) * kPanel * sizeof(double) + kK4Groups * sizeof(GJScratch);
     cudaError_t e = cudaFuncSetAttribute(lwr_kernel<kTileMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "lwr: %s", cudaGetErrorString(e));

@@ -45,6 +45,10 @@ int launch_lwr(const K4Params& P, int grid, cudaStream_t stream);
 int launch_ztable(const double* freqs, int F, int p, double fs, void* z, cudaStream_t stream);
 int launch_transfer_dtf(const K5Params& P, int ng, cudaStream_t stream);
 int launch_ffdtf_normalize(double* dtf, const double* rowpart, int n_win, int m, int F, int n_seg, double* out, cudaStream_t stream);
+size_t lwr_generic_ws_doubles(int n_win, int m, int p);
+int launch_lwr_generic(const K4Params& P, cudaStream_t stream);
+size_t transfer_generic_scratch_bytes(int m);
+int launch_transfer_generic(const K5Params& P, void* scratch, cudaStream_t stream);
 int launch_spectra(const void* H, const double* V, int n_win, int m, int F, void* S, cudaStream_t stream);
 
 }  // namespace hs

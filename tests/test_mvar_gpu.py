@@ -210,3 +210,40 @@ def test_window_driver_batched_matches_reference_loop():
         popt = int(mo.mvar_criterion(x[:, s:s + W2], 6, "AIC")[2])
         assert res2["p_opt_w"][w] == popt
         assert relerr(res2["ff_dtf_windowed"][w], mo.full_freq_dtf(x[:, s:s + W2], res2["freqs"], fs, optimal_model_order=popt)) < TOL_MODEL
+
+
+@pytest.mark.parametrize("m,n,p,F,trials", [(41, 300, 2, 9, 1), (48, 400, 3, 17, 1), (64, 512, 4, 12, 3), (90, 700, 2, 5, 1)])
+def test_generic_path_large_m(mv, m, n, p, F, trials):
+    """m > 40 goes through the block-GEMM LWR and the scratch-matrix Gauss-Jordan (generic_kernels.cu)."""
+    rng = np.random.default_rng(m * 7 + p)
+    shape = (m, n) if trials == 1 else (m, n, trials)
+    x = rng.standard_normal(shape)
+    x[:, 1:] += 0.5 * x[:, :-1]
+    freqs = np.sort(rng.uniform(0, 64, F))
+    A, V = mv.ar_coeff(x, p)
+    Ar, Vr = mo.ar_coeff(x, p)
+    assert relerr(A, Ar) < TOL_MODEL and relerr(V, Vr) < TOL_MODEL
+    H, Af = mv.mvar_transfer_function(Ar, freqs, 128.0)
+    Hr, Afr = mo.mvar_transfer_function(Ar, freqs, 128.0)
+    assert relerr(H, Hr) < TOL_MODEL and relerr(Af, Afr) < 1e-12
+    if trials == 1:
+        ff = quiet(mv.full_freq_dtf, x, freqs, 128.0, optimal_model_order=p)
+        assert relerr(ff, mo.full_freq_dtf(x, freqs, 128.0, optimal_model_order=p)) < TOL_MODEL
+        np.testing.assert_allclose(ff.sum(axis=(1, 2)), 1.0, rtol=1e-12)
+        crit, _, popt = mv.mvar_criterion(x, p, "SC")
+        cr, _, pr = mo.mvar_criterion(x, p, "SC")
+        assert relerr(crit, cr) < TOL_MODEL and int(popt) == int(pr)
+
+
+def test_cfg5_shape_high_channel_multi_trial(mv):
+    """BASELINE configs[4]: 2 x 64 channels, p = 15, 512 bins, covariances averaged over 100 epochs per window."""
+    from hyperscanning_signal_analysis_b200 import synth
+    ep = synth.cfg5_epochs(n_windows=1)[0]                       # (128, 512, 100)
+    A, V = mv.ar_coeff(ep, 15)
+    Ar, Vr = mo.ar_coeff(ep, 15)
+    assert A.shape == (128, 128, 15) and relerr(A, Ar) < TOL_MODEL and relerr(V, Vr) < TOL_MODEL
+    freqs = np.linspace(0, 128, 512, endpoint=False)
+    H, _ = mv.mvar_transfer_function(Ar, freqs, 256.0)
+    sel = [0, 100, 511]
+    Hr, _ = mo.mvar_transfer_function(Ar, freqs[sel], 256.0)
+    assert relerr(H[:, :, sel], Hr) < TOL_MODEL

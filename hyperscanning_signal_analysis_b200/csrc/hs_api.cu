@@ -48,8 +48,8 @@ static int k5_groups() {
     static int ng = 0;
     if (ng == 0) {
         const char* e = getenv("HS_K5_GROUPS");
-        ng = e ? atoi(e) : 8;
-        if (ng != 4 && ng != 6 && ng != 8) ng = 8;
+        ng = e ? atoi(e) : 6;
+        if (ng != 6 && ng != 7 && ng != 8) ng = 6;
     }
     return ng;
 }
@@ -145,8 +145,14 @@ int hs_yw_assemble_f64(const double* d_R, int n_win, int m, int p, double* d_G, 
     return launch_toeplitz(d_R, n_win, m, p, d_G, d_rhs, (cudaStream_t)stream);
 }
 
+static bool yw_use_batched(int m) {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("HS_YW_BATCHED"); mode = e ? atoi(e) : 0; }
+    return m > kPadMaxHost || mode == 1;
+}
+
 size_t hs_yw_ws_bytes(int n_win, int m, int p) {
-    if (m > kPadMaxHost) return align_up(lwr_generic_ws_doubles(n_win, m, p) * sizeof(double));
+    if (yw_use_batched(m)) return align_up(lwr_generic_ws_doubles(n_win, m, p) * sizeof(double));
     return align_up(lwr_ws_doubles(lwr_grid(n_win), m, p) * sizeof(double));
 }
 
@@ -165,7 +171,7 @@ int hs_yw_solve_f64(const double* d_R, int n_win, int m, int p, double* d_A, dou
     P.n_win = n_win;
     P.m = m;
     P.p = p;
-    if (m > kPadMaxHost) return launch_lwr_generic(P, (cudaStream_t)stream);
+    if (yw_use_batched(m)) return launch_lwr_generic(P, (cudaStream_t)stream);
     return launch_lwr(P, lwr_grid(n_win), (cudaStream_t)stream);
 }
 
@@ -180,7 +186,8 @@ size_t hs_transfer_ws_bytes(int n_win, int m, int p, int F) {
     k5_segments(F, k5_groups(), &ns, &sl);
     if (m > kPadMaxHost)      // generic path: one partial row sum per bin + per-CTA scratch matrices
         return align_up((size_t)p * F * 16) + align_up((size_t)n_win * F * m * sizeof(double)) + align_up(transfer_generic_scratch_bytes(m)) + 256;
-    return align_up((size_t)p * F * 16) + align_up((size_t)n_win * ns * m * sizeof(double)) + 256;
+    // z table, row sums (optimistic pass + pivoted redo), per-matrix flags, flag counter
+    return align_up((size_t)p * F * 16) + 2 * align_up((size_t)n_win * ns * m * sizeof(double)) + align_up((size_t)n_win * F * sizeof(int)) + 512;
 }
 
 int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double fs, int n_win, int m, int p, void* d_H,
@@ -195,6 +202,17 @@ int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double 
     unsigned char* ws = reinterpret_cast<unsigned char*>(d_ws);
     double2* z = reinterpret_cast<double2*>(ws);
     double* rowpart = reinterpret_cast<double*>(ws + align_up((size_t)p * F * 16));
+    double* rowpart2 = nullptr;
+    int* bad = nullptr;
+    int* bad_count = nullptr;
+    static int k5_mode = -1;       // 1 (default): optimistic elimination + check + pivoted redo; 0: pivoted only
+    if (k5_mode < 0) { const char* e = getenv("HS_K5_PIVOT_ONLY"); k5_mode = (e && atoi(e)) ? 0 : 1; }
+    if (m <= kPadMaxHost) {
+        const size_t rp = align_up((size_t)n_win * ns * m * sizeof(double));
+        rowpart2 = reinterpret_cast<double*>(ws + align_up((size_t)p * F * 16) + rp);
+        bad = reinterpret_cast<int*>(ws + align_up((size_t)p * F * 16) + 2 * rp);
+        bad_count = reinterpret_cast<int*>(ws + align_up((size_t)p * F * 16) + 2 * rp + align_up((size_t)n_win * F * sizeof(int)));
+    }
     int rc = launch_ztable(d_freqs, F, p, fs, z, st);
     if (rc) return rc;
     K5Params P;
@@ -212,16 +230,30 @@ int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double 
     P.n_seg = ns;
     P.seg_len = sl;
     { const char* e = getenv("HS_K5_FLIP"); P.flip = e ? atoi(e) : 0; }
+    P.rowpart2 = nullptr;
+    P.bad = bad;
+    P.bad_count = bad_count;
+    P.verify_tol2 = 1e-18;       // relative residual 1e-9 on the probe vector
+    bool redo = false;
     if (m > kPadMaxHost) {
         P.n_seg = ns = F;
         P.seg_len = 1;
         void* scratch = ws + align_up((size_t)p * F * 16) + align_up((size_t)n_win * F * m * sizeof(double));
         rc = launch_transfer_generic(P, scratch, st);
+    } else if (k5_mode == 0) {
+        rc = launch_transfer_dtf(P, ng, 0, st);
     } else {
-        rc = launch_transfer_dtf(P, ng, st);
+        redo = true;
+        P.rowpart2 = d_ffdtf ? rowpart2 : nullptr;
+        if (cudaMemsetAsync(bad, 0, (size_t)n_win * F * sizeof(int) + 256 + sizeof(int), st) != cudaSuccess ||
+            (d_ffdtf && cudaMemsetAsync(rowpart2, 0, (size_t)n_win * ns * m * sizeof(double), st) != cudaSuccess))
+            return set_error(HS_ERR_CUDA, "hs_transfer_dtf_f64: memset failed");
+        rc = launch_transfer_dtf(P, ng, 1, st);
+        if (rc) return rc;
+        rc = launch_transfer_dtf(P, ng, 2, st);      // returns immediately on the device when nothing was flagged
     }
     if (rc) return rc;
-    if (d_ffdtf) rc = launch_ffdtf_normalize(P.dtf, rowpart, n_win, m, F, ns, d_ffdtf, st);
+    if (d_ffdtf) rc = launch_ffdtf_normalize(P.dtf, rowpart, redo ? rowpart2 : nullptr, n_win, m, F, ns, d_ffdtf, st);
     return rc;
 }
 

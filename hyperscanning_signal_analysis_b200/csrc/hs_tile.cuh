@@ -215,6 +215,110 @@ __device__ __forceinline__ void gj_inverse(double (&ar)[T][T], double (&ai)[T][T
 }
 
 // ---------------------------------------------------------------------------------
+// Optimistic Gauss-Jordan: static diagonal pivots (pivot row of column k is row k).
+// Nothing about the step is data dependent, so there is no search, no row bookkeeping and no
+// permutation; the (unscaled) pivot row is broadcast with width-8 shuffles BEFORE the step's only
+// barrier, overlapping the column owners' reciprocal, and the multipliers are published already
+// scaled (c~ = c / p) so the rank-1 update needs nothing else.  The result is H itself
+// (rowmap = colmap = identity).  It is only as stable as unpivoted elimination: callers either know
+// the matrix is SPD (LWR residual covariances) or verify the result and fall back to gj_inverse.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ double rcp_newton(const double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));     // ~20 bits, branch free
+    y = fma(y, fma(-x, y, 1.0), y);
+    y = fma(y, fma(-x, y, 1.0), y);
+    y = fma(y, fma(-x, y, 1.0), y);
+    return y;
+}
+
+template <int T, bool CPLX>
+__device__ __forceinline__ void gj_inverse_static(double (&ar)[T][T], double (&ai)[T][T], const int m,
+                                                  const Group& g, GJScratch* sh) {
+    int step = 0;
+    group_sync(g);   // previous user of the scratch is done
+#pragma unroll
+    for (int b = 0; b < T; ++b) {
+#pragma unroll 1
+        for (int kc = 0; kc < 8; ++kc) {
+            const int k = kc + 8 * b;
+            if (k >= m) break;
+            const int par = step & 1;
+            const bool col_owner = (g.tc == kc);
+            // ---- unscaled pivot row k (row slot b of the lanes with tr == kc), broadcast per 8-lane group
+            double rr[T], ri[T];
+#pragma unroll
+            for (int bb = 0; bb < T; ++bb) {
+                rr[bb] = __shfl_sync(0xffffffffu, ar[b][bb], kc, 8);
+                ri[bb] = CPLX ? __shfl_sync(0xffffffffu, ai[b][bb], kc, 8) : 0.0;
+            }
+            if ((kc & 1) == g.wpar) {
+                // this warp owns column k: rr[b] / ri[b] of the lanes with tc == kc is the pivot a_kk
+                double ivr, ivi = 0.0;
+                if (CPLX) {
+                    const double d = rcp_newton(fma(rr[b], rr[b], ri[b] * ri[b]));
+                    ivr = rr[b] * d;
+                    ivi = -ri[b] * d;
+                } else {
+                    ivr = rcp_newton(rr[b]);
+                }
+                if (col_owner) {
+#pragma unroll
+                    for (int a = 0; a < T; ++a) {
+                        double cr, ci = 0.0;
+                        if (CPLX) {
+                            cr = fma(ar[a][b], ivr, -ai[a][b] * ivi);
+                            ci = fma(ar[a][b], ivi, ai[a][b] * ivr);
+                        } else {
+                            cr = ar[a][b] * ivr;
+                        }
+                        const bool piv = (a == b) && (g.tr == kc);
+                        sh->c[par][g.tr + 8 * a] = piv ? make_double2(0.0, 0.0) : make_double2(cr, ci);
+                        ar[a][b] = piv ? ivr : -cr;          // column k of the result: -c~ and 1/p
+                        if (CPLX) ai[a][b] = piv ? ivi : -ci;
+                    }
+                    if (g.tr == kc) sh->inv[par] = make_double2(ivr, ivi);
+                    rr[b] = 0.0;                              // the update below must not touch column k
+                    ri[b] = 0.0;
+                }
+            }
+            group_sync(g);
+            // ---- row k := row k / p (its owners; column k of it was set above)
+            if (g.tr == kc) {
+                const double2 iv = sh->inv[par];
+#pragma unroll
+                for (int bb = 0; bb < T; ++bb) {
+                    if (!(col_owner && bb == b)) {
+                        const double xr = ar[b][bb], xi = CPLX ? ai[b][bb] : 0.0;
+                        if (CPLX) {
+                            ar[b][bb] = fma(xr, iv.x, -xi * iv.y);
+                            ai[b][bb] = fma(xr, iv.y, xi * iv.x);
+                        } else {
+                            ar[b][bb] = xr * iv.x;
+                        }
+                    }
+                }
+            }
+            // ---- rank-1 update with the scaled multipliers (0 for row k) and the unscaled row
+#pragma unroll
+            for (int a = 0; a < T; ++a) {
+                const double2 cv = sh->c[par][g.tr + 8 * a];
+#pragma unroll
+                for (int bb = 0; bb < T; ++bb) {
+                    if (CPLX) {
+                        ar[a][bb] = fma(-cv.x, rr[bb], fma(cv.y, ri[bb], ar[a][bb]));
+                        ai[a][bb] = fma(-cv.x, ri[bb], fma(-cv.y, rr[bb], ai[a][bb]));
+                    } else {
+                        ar[a][bb] = fma(-cv.x, rr[bb], ar[a][bb]);
+                    }
+                }
+            }
+            ++step;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // acc[a][b] += sign * sum_{k<depth} Pa[k*lda + tr+8a] * Pb[k*ldb + tc+8b]
 // Pa / Pb are k-major panels in shared memory (lda, ldb >= 8T).
 // ---------------------------------------------------------------------------------

@@ -43,49 +43,79 @@ __global__ void ztable_kernel(const double* __restrict__ freqs, int F, int p, do
 // =====================================================================================
 template <int T>
 struct K5Smem {
-    // doubles per coefficient row, chosen = 2 (mod 16) so that 8 consecutive rows hit 8 distinct 16 B bank groups
+    // doubles per coefficient row, chosen = 2 (mod 16) so that 8 consecutive rows hit 8 distinct 16 B bank groups;
     // rows and columns are zero-padded to the 8T x 8T tile grid so the assembly loop needs no bounds checks
     static __host__ __device__ size_t coef_stride(int m, int p) { const int mp = 8 * T * p; return (size_t)(mp + ((2 - (mp & 15) + 16) & 15)); }
     static __host__ __device__ size_t coef_bytes(int m, int p) { return coef_stride(m, p) * 8 * T * sizeof(double); }
-    static __host__ __device__ size_t total(int m, int p, int ng) {
-        return coef_bytes(m, p) + (size_t)ng * sizeof(GJScratch) + (size_t)ng * 2 * kPadMax * sizeof(double) + 64;
-    }
+    static __host__ __device__ size_t group_bytes() { return sizeof(GJScratch) + 2 * kPadMax * sizeof(double) + 4 * kPadMax * sizeof(double2) + 16; }
+    static __host__ __device__ size_t total(int m, int p, int ng) { return coef_bytes(m, p) + (size_t)ng * group_bytes() + 64; }
 };
 
-template <int T, int NG, bool PIVOT = true>
+// probe vector of the a-posteriori check (any fixed vector without structure the elimination could preserve)
+__device__ __forceinline__ double2 probe_u(const int j) {
+    return make_double2(1.0 + 0.03125 * j, ((j & 1) ? -1.0 : 1.0) * (0.5 + 0.015625 * j));
+}
+
+// out_part[warp][i] = sum over this warp's columns of tile[i][j] * x[j]   (x given per column slot b)
+template <int T>
+__device__ __forceinline__ void tile_matvec_partial(const double (&ar)[T][T], const double (&ai)[T][T], const double2 (&x)[T],
+                                                    double2* __restrict__ out_part, const Group& g) {
+#pragma unroll
+    for (int a = 0; a < T; ++a) {
+        double sr = 0.0, si = 0.0;
+#pragma unroll
+        for (int b = 0; b < T; ++b) {
+            sr = fma(ar[a][b], x[b].x, fma(-ai[a][b], x[b].y, sr));
+            si = fma(ar[a][b], x[b].y, fma(ai[a][b], x[b].x, si));
+        }
+        sr += __shfl_xor_sync(0xffffffffu, sr, 8);
+        si += __shfl_xor_sync(0xffffffffu, si, 8);
+        sr += __shfl_xor_sync(0xffffffffu, sr, 16);
+        si += __shfl_xor_sync(0xffffffffu, si, 16);
+        if ((g.l64 & 24) == 0) out_part[(g.l64 >> 5) * kPadMax + g.tr + 8 * a] = make_double2(sr, si);
+    }
+}
+
+// MODE 0: pivoted Gauss-Jordan for every matrix.
+// MODE 1: optimistic static-pivot Gauss-Jordan + a-posteriori check ||H (A u) - u|| <= tol; failures are flagged in
+//         P.bad / P.bad_count and left to a MODE 2 launch.
+// MODE 2: pivoted Gauss-Jordan for the flagged matrices only (row sums go to P.rowpart2).
+template <int T, int NG, int MODE>
 __global__ void __launch_bounds__(NG * 64, 1) transfer_dtf_kernel(const K5Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int m = P.m, p = P.p, F = P.F;
+    if (MODE == 2 && *P.bad_count == 0) return;
     const int cstride = (int)K5Smem<T>::coef_stride(m, p);
     double* coef = reinterpret_cast<double*>(smem_raw);
-    GJScratch* gjs = reinterpret_cast<GJScratch*>(smem_raw + K5Smem<T>::coef_bytes(m, p));
-    double* rsg = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(gjs) + NG * sizeof(GJScratch));   // [NG][2][40]
-
     const Group g = make_group(P.flip);
-    GJScratch* sh = gjs + g.gid;
-    double* rs_mine = rsg + (size_t)(g.gid * 2 + (g.l64 >> 5)) * kPadMax;
-    const int nthreads = NG * 64;
+    unsigned char* gbase = smem_raw + K5Smem<T>::coef_bytes(m, p) + (size_t)g.gid * K5Smem<T>::group_bytes();
+    GJScratch* sh = reinterpret_cast<GJScratch*>(gbase);
+    double* rs_grp = reinterpret_cast<double*>(gbase + sizeof(GJScratch));                       // [2][40]
+    double2* vpart = reinterpret_cast<double2*>(gbase + sizeof(GJScratch) + 2 * kPadMax * sizeof(double));   // [2][40] A u
+    double2* wpart = vpart + 2 * kPadMax;                                                        // [2][40] H (A u)
+    double* rs_mine = rs_grp + (g.l64 >> 5) * kPadMax;
     const int n_units = P.n_win * P.n_seg;
     const bool vec_ok = ((p & 1) == 0);
-    // offset (doubles) of this thread's tile entry (a = 0, b = 0) inside the coefficient block
-    const int off00 = g.tr * cstride + g.tc * p;
+    const int off00 = g.tr * cstride + g.tc * p;      // this thread's tile entry (a = 0, b = 0) in the coefficient block
+    double* rowpart = (MODE == 2) ? P.rowpart2 : P.rowpart;
 
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const int w = unit / P.n_seg, seg = unit % P.n_seg;
         const int f_begin = seg * P.seg_len, f_end = min(F, f_begin + P.seg_len);
         __syncthreads();
-        {   // AR coefficients of window w -> shared (row i padded to cstride doubles)
+        {   // AR coefficients of window w -> shared (zero padded to 8T x 8T, row stride cstride)
             const double* Aw = P.A + (size_t)w * m * m * p;
             const int row_len = m * p, pad_len = 8 * T * p;
             for (int i = g.gid * 2 + (g.l64 >> 5); i < 8 * T; i += NG * 2) {       // one warp per row
                 for (int c = threadIdx.x & 31; c < pad_len; c += 32)
                     coef[i * cstride + c] = (i < m && c < row_len) ? Aw[(size_t)i * row_len + c] : 0.0;
             }
-            for (int e = threadIdx.x; e < NG * 2 * kPadMax; e += nthreads) rsg[e] = 0.0;
+            for (int e = g.l64; e < 2 * kPadMax; e += 64) rs_grp[e] = 0.0;
         }
         __syncthreads();
 
         for (int f = f_begin + g.gid; f < f_end; f += NG) {
+            if (MODE == 2 && P.bad[(size_t)w * F + f] == 0) continue;      // group-uniform
             double ar[T][T], ai[T][T];
             // ---- build A(f) = I - sum_k A_k z_k(f)
 #pragma unroll
@@ -126,7 +156,7 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_dtf_kernel(const K5Params
                 }
             }
             const size_t wbase = (size_t)w * m * m;
-            if (P.Af) {
+            if (P.Af && MODE != 2) {
 #pragma unroll
                 for (int a = 0; a < T; ++a)
 #pragma unroll
@@ -135,56 +165,96 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_dtf_kernel(const K5Params
                         if (i < m && j < m) P.Af[(wbase + (size_t)i * m + j) * F + f] = make_double2(ar[a][b], ai[a][b]);
                     }
             }
-            // ---- invert
-            gj_inverse<T, true, PIVOT>(ar, ai, m, g, sh);
-            if (g.l64 == 0 && sh->singular) atomicOr(&P.status[w], 1);
-            // ---- |H|^2 straight to global (8 B stores; the 32 B sectors are completed in L2 by the
-            //      neighbouring bins, which other groups of this CTA write within the same ~100 us),
-            //      plus this bin's contribution to the ffDTF row sums.
-            int cj[T];
+            bool good = true;
+            if (MODE == 1) {
+                // v = A(f) u, kept as per-warp partials in shared memory until the check
+                double2 x[T];
 #pragma unroll
-            for (int b = 0; b < T; ++b) cj[b] = sh->colmap[min(g.tc + 8 * b, kPadMax - 1)];
-#pragma unroll
-            for (int a = 0; a < T; ++a) {
-                const int i = g.tr + 8 * a;
-                const int ri = sh->rowmap[min(i, kPadMax - 1)];
-                double rsum = 0.0;
+                for (int b = 0; b < T; ++b) x[b] = (g.tc + 8 * b < m) ? probe_u(g.tc + 8 * b) : make_double2(0.0, 0.0);
+                group_sync(g);                      // previous matrix' check has finished reading vpart / wpart
+                tile_matvec_partial<T>(ar, ai, x, vpart, g);
+                gj_inverse_static<T, true>(ar, ai, m, g, sh);
+                group_sync(g);
 #pragma unroll
                 for (int b = 0; b < T; ++b) {
                     const int j = g.tc + 8 * b;
-                    if (i < m && j < m) {
-                        const double v = fma(ar[a][b], ar[a][b], ai[a][b] * ai[a][b]);
-                        rsum += v;
-                        const size_t o = (wbase + (size_t)ri * m + cj[b]) * F + f;
-                        if (P.dtf) P.dtf[o] = v;
-                        if (P.H) P.H[o] = make_double2(ar[a][b], ai[a][b]);
-                    }
+                    const double2 v0 = vpart[j], v1 = vpart[kPadMax + j];
+                    x[b] = (j < m) ? make_double2(v0.x + v1.x, v0.y + v1.y) : make_double2(0.0, 0.0);
                 }
-                // reduce over the 4 column groups of this warp (lane bits 3, 4), fixed order
-                rsum += __shfl_xor_sync(0xffffffffu, rsum, 8);
-                rsum += __shfl_xor_sync(0xffffffffu, rsum, 16);
-                if ((g.l64 & 24) == 0 && i < m) rs_mine[ri] += rsum;      // one writer per (warp, row): deterministic
+                if (g.l64 == 0) sh->singular = 0;
+                tile_matvec_partial<T>(ar, ai, x, wpart, g);
+                group_sync(g);
+                if (g.l64 < m) {
+                    const double2 u = probe_u(g.l64);
+                    const double er = wpart[g.l64].x + wpart[kPadMax + g.l64].x - u.x;
+                    const double ei = wpart[g.l64].y + wpart[kPadMax + g.l64].y - u.y;
+                    const double err = fma(er, er, ei * ei), ref = fma(u.x, u.x, u.y * u.y);
+                    if (!(err <= P.verify_tol2 * ref)) sh->singular = 1;      // also catches NaN / Inf
+                }
+                group_sync(g);
+                good = (sh->singular == 0);
+                if (!good && g.l64 == 0) {
+                    P.bad[(size_t)w * F + f] = 1;
+                    atomicAdd(P.bad_count, 1);
+                }
+            } else {
+                gj_inverse<T, true>(ar, ai, m, g, sh);
+                if (g.l64 == 0 && sh->singular) atomicOr(&P.status[w], 1);
+            }
+            if (good) {
+                // ---- |H|^2 straight to global (8 B stores; the 32 B sectors are completed in L2 by the neighbouring
+                //      bins, written by the other groups of this CTA within the same ~100 us), plus this bin's
+                //      contribution to the ffDTF row sums.
+                int cj[T];
+#pragma unroll
+                for (int b = 0; b < T; ++b) cj[b] = (MODE == 1) ? (g.tc + 8 * b) : sh->colmap[min(g.tc + 8 * b, kPadMax - 1)];
+#pragma unroll
+                for (int a = 0; a < T; ++a) {
+                    const int i = g.tr + 8 * a;
+                    const int ri = (MODE == 1) ? i : sh->rowmap[min(i, kPadMax - 1)];
+                    double rsum = 0.0;
+#pragma unroll
+                    for (int b = 0; b < T; ++b) {
+                        const int j = g.tc + 8 * b;
+                        if (i < m && j < m) {
+                            const double v = fma(ar[a][b], ar[a][b], ai[a][b] * ai[a][b]);
+                            rsum += v;
+                            const size_t o = (wbase + (size_t)ri * m + cj[b]) * F + f;
+                            if (P.dtf) P.dtf[o] = v;
+                            if (P.H) P.H[o] = make_double2(ar[a][b], ai[a][b]);
+                        }
+                    }
+                    // reduce over the 4 column groups of this warp (lane bits 3, 4), fixed order
+                    rsum += __shfl_xor_sync(0xffffffffu, rsum, 8);
+                    rsum += __shfl_xor_sync(0xffffffffu, rsum, 16);
+                    if ((g.l64 & 24) == 0 && i < m) rs_mine[ri] += rsum;      // one writer per (warp, row): deterministic
+                }
             }
         }
         // ---- per-unit row sums (fixed summation order -> deterministic)
         __syncthreads();
-        if (P.rowpart && threadIdx.x < m) {
+        if (rowpart && threadIdx.x < m) {
             double acc = 0.0;
-            for (int q = 0; q < NG * 2; ++q) acc += rsg[q * kPadMax + threadIdx.x];
-            P.rowpart[((size_t)w * P.n_seg + seg) * m + threadIdx.x] = acc;
+            for (int q = 0; q < NG; ++q) {
+                const double* rg = reinterpret_cast<const double*>(smem_raw + K5Smem<T>::coef_bytes(m, p) + (size_t)q * K5Smem<T>::group_bytes() + sizeof(GJScratch));
+                acc += rg[threadIdx.x] + rg[kPadMax + threadIdx.x];
+            }
+            rowpart[((size_t)w * P.n_seg + seg) * m + threadIdx.x] = acc;
         }
     }
 }
 
 // ffdtf[w][i][j][f] = dtf[w][i][j][f] / sum_seg rowpart[w][seg][i]     (mtmvar.py:281-283)
-__global__ void ffdtf_normalize_kernel(double* __restrict__ dtf, const double* __restrict__ rowpart, int m, int F, int n_seg,
-                                       double* __restrict__ out) {
+__global__ void ffdtf_normalize_kernel(double* __restrict__ dtf, const double* __restrict__ rowpart, const double* __restrict__ rowpart2, int m,
+                                       int F, int n_seg, double* __restrict__ out) {
     const int w = blockIdx.y;
     const int i = blockIdx.x;
     __shared__ double inv_s;
     if (threadIdx.x == 0) {
         double acc = 0.0;
         for (int s = 0; s < n_seg; ++s) acc += rowpart[((size_t)w * n_seg + s) * m + i];
+        if (rowpart2)
+            for (int s = 0; s < n_seg; ++s) acc += rowpart2[((size_t)w * n_seg + s) * m + i];
         inv_s = acc;
     }
     __syncthreads();
@@ -205,49 +275,46 @@ __global__ void ffdtf_normalize_kernel(double* __restrict__ dtf, const double* _
     }
 }
 
-template <int T, int NG, bool PIVOT = true>
+template <int T, int NG, int MODE>
 static int launch_k5_t(const K5Params& P, int sm_count, cudaStream_t stream) {
     const size_t smem = K5Smem<T>::total(P.m, P.p, NG);
-    cudaError_t e = cudaFuncSetAttribute(transfer_dtf_kernel<T, NG, PIVOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(transfer_dtf_kernel<T, NG, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "transfer_dtf: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
     const int n_units = P.n_win * P.n_seg;
     const int grid = n_units < sm_count ? n_units : sm_count;
-    transfer_dtf_kernel<T, NG, PIVOT><<<grid, NG * 64, smem, stream>>>(P);
+    transfer_dtf_kernel<T, NG, MODE><<<grid, NG * 64, smem, stream>>>(P);
     return check_launch("transfer_dtf_kernel");
 }
 
-int launch_transfer_dtf(const K5Params& P, int ng, cudaStream_t stream) {
-    const int T = (P.m + 7) / 8;
-    const int sm = device_sm_count();
-    if (ng == 6 && T == 5 && getenv("HS_K5_NOPIVOT")) return launch_k5_t<5, 6, false>(P, sm, stream);   // experiment only
-    if (ng == 8) {
-        switch (T) {
-            case 1: return launch_k5_t<1, 8>(P, sm, stream);
-            case 2: return launch_k5_t<2, 8>(P, sm, stream);
-            case 3: return launch_k5_t<3, 8>(P, sm, stream);
-            case 4: return launch_k5_t<4, 8>(P, sm, stream);
-            case 5: return launch_k5_t<5, 8>(P, sm, stream);
-        }
-    } else if (ng == 6) {
-        switch (T) {
-            case 1: return launch_k5_t<1, 6>(P, sm, stream);
-            case 2: return launch_k5_t<2, 6>(P, sm, stream);
-            case 3: return launch_k5_t<3, 6>(P, sm, stream);
-            case 4: return launch_k5_t<4, 6>(P, sm, stream);
-            case 5: return launch_k5_t<5, 6>(P, sm, stream);
-        }
-    } else if (ng == 4) {
-        switch (T) {
-            case 1: return launch_k5_t<1, 4>(P, sm, stream);
-            case 2: return launch_k5_t<2, 4>(P, sm, stream);
-            case 3: return launch_k5_t<3, 4>(P, sm, stream);
-            case 4: return launch_k5_t<4, 4>(P, sm, stream);
-            case 5: return launch_k5_t<5, 4>(P, sm, stream);
-        }
+template <int NG, int MODE>
+static int launch_k5_ng(const K5Params& P, int sm, cudaStream_t stream) {
+    switch ((P.m + 7) / 8) {
+        case 1: return launch_k5_t<1, NG, MODE>(P, sm, stream);
+        case 2: return launch_k5_t<2, NG, MODE>(P, sm, stream);
+        case 3: return launch_k5_t<3, NG, MODE>(P, sm, stream);
+        case 4: return launch_k5_t<4, NG, MODE>(P, sm, stream);
+        case 5: return launch_k5_t<5, NG, MODE>(P, sm, stream);
     }
-    return set_error(HS_ERR_UNSUPPORTED, "transfer_dtf: no kernel for m=%d ng=%d", P.m, ng);
+    return set_error(HS_ERR_UNSUPPORTED, "transfer_dtf: no register-tile kernel for m=%d", P.m);
 }
 
+// mode 0: pivoted only; mode 1: optimistic + verify; mode 2: pivoted redo of the flagged matrices
+int launch_transfer_dtf(const K5Params& P, int ng, int mode, cudaStream_t stream) {
+    const int sm = device_sm_count();
+    if (ng == 8) {
+        if (mode == 0) return launch_k5_ng<8, 0>(P, sm, stream);
+        if (mode == 1) return launch_k5_ng<8, 1>(P, sm, stream);
+        return launch_k5_ng<8, 2>(P, sm, stream);
+    }
+    if (ng == 7) {
+        if (mode == 0) return launch_k5_ng<7, 0>(P, sm, stream);
+        if (mode == 1) return launch_k5_ng<7, 1>(P, sm, stream);
+        return launch_k5_ng<7, 2>(P, sm, stream);
+    }
+    if (mode == 0) return launch_k5_ng<6, 0>(P, sm, stream);
+    if (mode == 1) return launch_k5_ng<6, 1>(P, sm, stream);
+    return launch_k5_ng<6, 2>(P, sm, stream);
+}
 
 // =====================================================================================
 // K3  lag_cov :  R(L)[i][j] = 1/(n*trials) * sum_trials sum_{t=0}^{n-1-L} x_i(t) x_j(t+L),
@@ -472,17 +539,22 @@ __global__ void __launch_bounds__(kK4Groups * 64, 1) lwr_kernel(const K4Params P
                             const int i = g.tr + 8 * a, j = g.tc + 8 * b;
                             iv[a][b] = (i < m && j < m) ? Vt[a][b] : ((i == j) ? 1.0 : 0.0);
                         }
-                    gj_inverse<T, false>(iv, dummy, m, g, sh);
-                    if (g.l64 == 0 && sh->singular) atomicOr(&P.status[w], 2);
+                    // residual covariances are symmetric positive definite: unpivoted elimination is stable
+                    gj_inverse_static<T, false>(iv, dummy, m, g, sh);
+                    bool finite = true;
 #pragma unroll
                     for (int a = 0; a < T; ++a) {
                         const int i = g.tr + 8 * a;
 #pragma unroll
                         for (int b = 0; b < T; ++b) {
                             const int j = g.tc + 8 * b;
-                            if (i < m && j < m) pB[sh->rowmap[i] * kPadMax + sh->colmap[j]] = iv[a][b];
+                            if (i < m && j < m) {
+                                pB[i * kPadMax + j] = iv[a][b];
+                                finite = finite && (fabs(iv[a][b]) <= 1.79e308);
+                            }
                         }
                     }
+                    if (!finite) atomicOr(&P.status[w], 2);      // singular (or not positive definite) residual covariance
                 }
             }
             __syncthreads();
@@ -563,9 +635,10 @@ int launch_ztable(const double* freqs, int F, int p, double fs, void* z, cudaStr
     return check_launch("ztable_kernel");
 }
 
-int launch_ffdtf_normalize(double* dtf, const double* rowpart, int n_win, int m, int F, int n_seg, double* out, cudaStream_t stream) {
+int launch_ffdtf_normalize(double* dtf, const double* rowpart, const double* rowpart2, int n_win, int m, int F, int n_seg, double* out,
+                           cudaStream_t stream) {
     dim3 grid(m, n_win);
-    ffdtf_normalize_kernel<<<grid, 256, 0, stream>>>(dtf, rowpart, m, F, n_seg, out);
+    ffdtf_normalize_kernel<<<grid, 256, 0, stream>>>(dtf, rowpart, rowpart2, m, F, n_seg, out);
     return check_launch("ffdtf_normalize_kernel");
 }
 

@@ -35,6 +35,10 @@ struct K5Params {
     int* status;            // (n_win) sticky singular flags
     int n_win, m, p, F, n_seg, seg_len;
     int flip;               // 1: alternate the column-owner parity between groups sharing an SMSP pair
+    double* rowpart2;       // row sums of the matrices redone with pivoting (mode 2)
+    int* bad;               // (n_win * F) flags set by the optimistic pass
+    int* bad_count;         // number of flagged matrices
+    double verify_tol2;     // squared relative tolerance of the a-posteriori check
 };
 
 int launch_lagcov(const K3Params& P, cudaStream_t stream);
@@ -43,8 +47,9 @@ size_t lwr_ws_doubles(int grid, int m, int p);
 int lwr_grid(int n_win);
 int launch_lwr(const K4Params& P, int grid, cudaStream_t stream);
 int launch_ztable(const double* freqs, int F, int p, double fs, void* z, cudaStream_t stream);
-int launch_transfer_dtf(const K5Params& P, int ng, cudaStream_t stream);
-int launch_ffdtf_normalize(double* dtf, const double* rowpart, int n_win, int m, int F, int n_seg, double* out, cudaStream_t stream);
+int launch_transfer_dtf(const K5Params& P, int ng, int mode, cudaStream_t stream);
+int launch_ffdtf_normalize(double* dtf, const double* rowpart, const double* rowpart2, int n_win, int m, int F, int n_seg, double* out,
+                           cudaStream_t stream);
 size_t lwr_generic_ws_doubles(int n_win, int m, int p);
 int launch_lwr_generic(const K4Params& P, cudaStream_t stream);
 size_t transfer_generic_scratch_bytes(int m);

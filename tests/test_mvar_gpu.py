@@ -247,3 +247,29 @@ def test_cfg5_shape_high_channel_multi_trial(mv):
     sel = [0, 100, 511]
     Hr, _ = mo.mvar_transfer_function(Ar, freqs[sel], 256.0)
     assert relerr(H[:, :, sel], Hr) < TOL_MODEL
+
+
+def test_optimistic_elimination_falls_back_to_pivoting(mv):
+    """A(f) with a zero diagonal at f = 0 (A_1 = I - P, P a cyclic shift): unpivoted elimination breaks down, the
+    a-posteriori check must flag those bins and the pivoted redo must deliver np.linalg.inv's answer."""
+    m, p = 38, 2
+    rng = np.random.default_rng(5)
+    P = np.roll(np.eye(m), 1, axis=1)
+    A = np.zeros((m, m, p))
+    A[:, :, 0] = np.eye(m) - P
+    A[:, :, 1] = 0.01 * rng.standard_normal((m, m))
+    freqs = np.array([0.0, 3.0, 17.0, 40.0, 64.0, 90.0, 127.5])
+    H, Af = mv.mvar_transfer_function(A, freqs, 256.0)
+    Hr, Afr = mo.mvar_transfer_function(A, freqs, 256.0)
+    assert abs(np.diagonal(Afr[:, :, 0])).max() < 0.05            # (nearly) zero diagonal at f = 0
+    assert relerr(Af, Afr) < 1e-12
+    for fi in range(len(freqs)):
+        assert relerr(H[:, :, fi], Hr[:, :, fi]) < TOL_MODEL, fi
+    # ffDTF over a grid that mixes flagged and unflagged bins (row sums come from both passes)
+    from hyperscanning_signal_analysis_b200 import mtmvar
+    import torch
+    res = mtmvar.batched_transfer(torch.from_numpy(A[None]).cuda(), freqs, 256.0, want=("ffdtf", "dtf"))
+    dtf_r = np.abs(Hr) ** 2
+    ff_r = dtf_r / dtf_r.sum(axis=(1, 2), keepdims=True)
+    assert relerr(res["dtf"][0].cpu().numpy(), dtf_r) < TOL_MODEL
+    assert relerr(res["ffdtf"][0].cpu().numpy(), ff_r) < TOL_MODEL

@@ -33,6 +33,7 @@ SIGNATURES = {
     "hs_yw_solve_f64": (c_int, [c_dp, c_int, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "hs_ztable_f64": (c_int, [c_dp, c_int, c_int, c_dbl, c_dp, c_dp]),
     "hs_transfer_ws_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
+    "hs_transfer_ws_flag_offset": (c_sz, [c_int, c_int, c_int, c_int]),
     "hs_transfer_dtf_f64": (c_int, [c_dp, c_dp, c_int, c_dbl, c_int, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "hs_spectra_f64": (c_int, [c_dp, c_dp, c_int, c_int, c_int, c_dp, c_dp]),
     "hs_mvar_ffdtf_ws_bytes": (c_sz, [c_int, c_int, c_int, c_int]),

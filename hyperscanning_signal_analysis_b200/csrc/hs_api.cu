@@ -186,8 +186,16 @@ size_t hs_transfer_ws_bytes(int n_win, int m, int p, int F) {
     k5_segments(F, k5_groups(), &ns, &sl);
     if (m > kPadMaxHost)      // generic path: one partial row sum per bin + per-CTA scratch matrices
         return align_up((size_t)p * F * 16) + align_up((size_t)n_win * F * m * sizeof(double)) + align_up(transfer_generic_scratch_bytes(m)) + 256;
-    // z table, row sums (optimistic pass + pivoted redo), per-matrix flags, flag counter
-    return align_up((size_t)p * F * 16) + 2 * align_up((size_t)n_win * ns * m * sizeof(double)) + align_up((size_t)n_win * F * sizeof(int)) + 512;
+    // z table, row sums of the optimistic pass, per-matrix flags, list of flagged matrices, counter, |H|^2 staging (n_win, F, m, m)
+    return align_up((size_t)p * F * 16) + align_up((size_t)n_win * ns * m * sizeof(double)) + 2 * align_up((size_t)n_win * F * sizeof(int)) + 512 +
+           align_up((size_t)n_win * F * m * m * sizeof(double));
+}
+
+size_t hs_transfer_ws_flag_offset(int n_win, int m, int p, int F) {
+    if (m > kPadMaxHost) return (size_t)-1;
+    int ns, sl;
+    k5_segments(F, k5_groups(), &ns, &sl);
+    return align_up((size_t)p * F * 16) + align_up((size_t)n_win * ns * m * sizeof(double)) + 2 * align_up((size_t)n_win * F * sizeof(int));
 }
 
 int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double fs, int n_win, int m, int p, void* d_H,
@@ -205,20 +213,28 @@ int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double 
     double* rowpart2 = nullptr;
     int* bad = nullptr;
     int* bad_count = nullptr;
+    double* stage = nullptr;
     static int k5_mode = -1;       // 1 (default): optimistic elimination + check + pivoted redo; 0: pivoted only
     if (k5_mode < 0) { const char* e = getenv("HS_K5_PIVOT_ONLY"); k5_mode = (e && atoi(e)) ? 0 : 1; }
+    int* bad_list = nullptr;
     if (m <= kPadMaxHost) {
         const size_t rp = align_up((size_t)n_win * ns * m * sizeof(double));
-        rowpart2 = reinterpret_cast<double*>(ws + align_up((size_t)p * F * 16) + rp);
-        bad = reinterpret_cast<int*>(ws + align_up((size_t)p * F * 16) + 2 * rp);
-        bad_count = reinterpret_cast<int*>(ws + align_up((size_t)p * F * 16) + 2 * rp + align_up((size_t)n_win * F * sizeof(int)));
+        const size_t fl = align_up((size_t)n_win * F * sizeof(int));
+        unsigned char* q = ws + align_up((size_t)p * F * 16) + rp;
+        bad = reinterpret_cast<int*>(q);
+        bad_list = reinterpret_cast<int*>(q + fl);
+        bad_count = reinterpret_cast<int*>(q + 2 * fl);
+        stage = reinterpret_cast<double*>(q + 2 * fl + 512);
     }
     int rc = launch_ztable(d_freqs, F, p, fs, z, st);
     if (rc) return rc;
     K5Params P;
     P.A = d_A;
     P.z = z;
-    P.dtf = d_dtf ? d_dtf : d_ffdtf;
+    const bool want_dtf = d_dtf || d_ffdtf;
+    const bool staged = want_dtf && stage;       // m <= 40: |H|^2 goes through the (w, f, i, j) staging buffer
+    P.dtf = staged ? stage : (d_dtf ? d_dtf : d_ffdtf);
+    P.dtf_fij = staged ? 1 : 0;
     P.rowpart = d_ffdtf ? rowpart : nullptr;
     P.H = reinterpret_cast<double2*>(d_H);
     P.Af = reinterpret_cast<double2*>(d_Af);
@@ -233,6 +249,7 @@ int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double 
     P.rowpart2 = nullptr;
     P.bad = bad;
     P.bad_count = bad_count;
+    P.bad_list = bad_list;
     P.verify_tol2 = 1e-18;       // relative residual 1e-9 on the probe vector
     bool redo = false;
     if (m > kPadMaxHost) {
@@ -244,15 +261,17 @@ int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double 
         rc = launch_transfer_dtf(P, ng, 0, st);
     } else {
         redo = true;
-        P.rowpart2 = d_ffdtf ? rowpart2 : nullptr;
-        if (cudaMemsetAsync(bad, 0, (size_t)n_win * F * sizeof(int) + 256 + sizeof(int), st) != cudaSuccess ||
-            (d_ffdtf && cudaMemsetAsync(rowpart2, 0, (size_t)n_win * ns * m * sizeof(double), st) != cudaSuccess))
+        // flags and the counter are cleared; the list needs no clearing (only entries below the counter are read)
+        if (cudaMemsetAsync(bad, 0, (size_t)n_win * F * sizeof(int), st) != cudaSuccess || cudaMemsetAsync(bad_count, 0, sizeof(int), st) != cudaSuccess)
             return set_error(HS_ERR_CUDA, "hs_transfer_dtf_f64: memset failed");
-        rc = launch_transfer_dtf(P, ng, 1, st);
+        static int use_mma = -1;   // default: blocked elimination on the FP64 tensor pipe; HS_K5_MMA=0 -> register-tile DFMA kernel
+        if (use_mma < 0) { const char* e = getenv("HS_K5_MMA"); use_mma = (e && atoi(e) == 0) ? 0 : 1; }
+        rc = (use_mma && transfer_mma_fits(p, ng)) ? launch_transfer_mma(P, ng, st) : launch_transfer_dtf(P, ng, 1, st);
         if (rc) return rc;
         rc = launch_transfer_dtf(P, ng, 2, st);      // returns immediately on the device when nothing was flagged
     }
     if (rc) return rc;
+    if (staged) return launch_dtf_finalize(stage, d_ffdtf ? rowpart : nullptr, redo ? bad : nullptr, n_win, m, F, ns, d_dtf, d_ffdtf, st);
     if (d_ffdtf) rc = launch_ffdtf_normalize(P.dtf, rowpart, redo ? rowpart2 : nullptr, n_win, m, F, ns, d_ffdtf, st);
     return rc;
 }

@@ -319,6 +319,138 @@ __device__ __forceinline__ void gj_inverse_static(double (&ar)[T][T], double (&a
 }
 
 // ---------------------------------------------------------------------------------
+// Look-ahead Gauss-Jordan (static diagonal pivots, deferred row scaling).
+//
+// Same optimistic elimination as gj_inverse_static, restructured so that nothing but the rank-1
+// update sits between two barriers:
+//   * the pivot row and the SCALED multipliers of step k+1 are published to shared memory DURING
+//     step k: the entries of column k+1 / row k+1 are updated first, their owners publish, and the
+//     other 16 of the 25 tile entries are updated afterwards, so the reciprocal / scaling / store
+//     latency of the next step overlaps this step's bulk DFMAs;
+//   * both operands of the update come from shared memory as broadcast LDS.128 (10 per step and
+//     thread) -- no shuffles in the steady state apart from the pivot broadcast of the owner warp;
+//   * the pivot row is never scaled: row k keeps the factor p_k it had when it was eliminated and
+//     1/p_k is recorded in sh->pinv[k].  The elimination is linear in each row, so the true inverse
+//     is  H[i][j] = pinv[i] * S[i][j]  with S the register tiles on exit; |H|^2 needs one real scale
+//     per row.  Column k of S is produced by the update itself: its owners zero it when they
+//     publish, the published pivot-row entry for that column is 1 and the multiplier of row k is 0.
+// One 64-thread barrier per step.  Stability is that of unpivoted elimination: callers know the
+// matrix is SPD or verify the result a posteriori and fall back to gj_inverse.
+// ---------------------------------------------------------------------------------
+struct __align__(16) GJLScratch {
+    double2 row[2][kPadMax];   // pivot row of the step (unscaled), double buffered by step parity
+    double2 col[2][kPadMax];   // scaled multipliers a_ik / p_k (0 for i == k)
+    double2 pinv[kPadMax];     // 1 / p_k
+};
+
+// publish pivot row / multipliers of step k1 = kc1 + 8*B1 into buffer `par1`
+template <int T, bool CPLX, int B1>
+__device__ __forceinline__ void gjl_publish(double (&ar)[T][T], double (&ai)[T][T], const int kc1, const int par1,
+                                            const Group& g, GJLScratch* sh) {
+    const bool col_lane = (g.tc == kc1);
+    if (g.tr == kc1) {
+#pragma unroll
+        for (int bb = 0; bb < T; ++bb) {
+            const bool piv = col_lane && (bb == B1);
+            sh->row[par1][g.tc + 8 * bb] = piv ? make_double2(1.0, 0.0) : make_double2(ar[B1][bb], CPLX ? ai[B1][bb] : 0.0);
+        }
+    }
+    if ((kc1 & 1) == g.wpar) {      // warp-uniform: this warp holds column k1
+        const double pr = __shfl_sync(0xffffffffu, ar[B1][B1], kc1, 8);
+        double ivr, ivi = 0.0;
+        if (CPLX) {
+            const double pi = __shfl_sync(0xffffffffu, ai[B1][B1], kc1, 8);
+            const double d = rcp_newton(fma(pr, pr, pi * pi));
+            ivr = pr * d;
+            ivi = -pi * d;
+        } else {
+            ivr = rcp_newton(pr);
+        }
+#pragma unroll
+        for (int a = 0; a < T; ++a) {
+            double cr, ci = 0.0;
+            if (CPLX) {
+                cr = fma(ar[a][B1], ivr, -ai[a][B1] * ivi);
+                ci = fma(ar[a][B1], ivi, ai[a][B1] * ivr);
+            } else {
+                cr = ar[a][B1] * ivr;
+            }
+            if (col_lane) {
+                const bool piv = (a == B1) && (g.tr == kc1);
+                sh->col[par1][g.tr + 8 * a] = piv ? make_double2(0.0, 0.0) : make_double2(cr, ci);
+                ar[a][B1] = piv ? 1.0 : 0.0;
+                if (CPLX) ai[a][B1] = 0.0;
+            }
+        }
+        if (col_lane && g.tr == kc1) sh->pinv[kc1 + 8 * B1] = make_double2(ivr, ivi);
+    }
+}
+
+template <int T, bool CPLX>
+__device__ __forceinline__ void gjl_update(double (&ar)[T][T], double (&ai)[T][T], const double2 (&cc)[T], const double2 (&rr)[T],
+                                           const int a, const int bb) {
+    if (CPLX) {
+        ar[a][bb] = fma(-cc[a].x, rr[bb].x, fma(cc[a].y, rr[bb].y, ar[a][bb]));
+        ai[a][bb] = fma(-cc[a].x, rr[bb].y, fma(-cc[a].y, rr[bb].x, ai[a][bb]));
+    } else {
+        ar[a][bb] = fma(-cc[a].x, rr[bb].x, ar[a][bb]);
+    }
+}
+
+// one elimination step k = kc + 8*B; LOOK: also publish step k+1 = kc1 + 8*B1
+template <int T, bool CPLX, int B, int B1, bool LOOK>
+__device__ __forceinline__ void gjl_step(double (&ar)[T][T], double (&ai)[T][T], const int kc, const int kc1, const int par,
+                                         const Group& g, GJLScratch* sh) {
+    group_sync(g);
+    double2 cc[T], rr[T];
+#pragma unroll
+    for (int a = 0; a < T; ++a) cc[a] = sh->col[par][g.tr + 8 * a];
+#pragma unroll
+    for (int bb = 0; bb < T; ++bb) rr[bb] = sh->row[par][g.tc + 8 * bb];
+    if (LOOK) {
+#pragma unroll
+        for (int a = 0; a < T; ++a) gjl_update<T, CPLX>(ar, ai, cc, rr, a, B1);
+#pragma unroll
+        for (int bb = 0; bb < T; ++bb)
+            if (bb != B1) gjl_update<T, CPLX>(ar, ai, cc, rr, B1, bb);
+        gjl_publish<T, CPLX, B1>(ar, ai, kc1, par ^ 1, g, sh);
+    }
+#pragma unroll
+    for (int a = 0; a < T; ++a)
+#pragma unroll
+        for (int bb = 0; bb < T; ++bb)
+            if (!LOOK || (a != B1 && bb != B1)) gjl_update<T, CPLX>(ar, ai, cc, rr, a, bb);
+}
+
+template <int T, bool CPLX, int B>
+__device__ __forceinline__ void gjl_block(double (&ar)[T][T], double (&ai)[T][T], const int m, const Group& g, GJLScratch* sh) {
+    if constexpr (B < T) {
+        const int left = m - 8 * B;                  // steps of this block: kc = 0 .. min(8, left) - 1
+        if (left > 0) {
+            const int nk = left < 8 ? left : 8;
+#pragma unroll 1
+            for (int kc = 0; kc < nk - 1; ++kc) gjl_step<T, CPLX, B, B, true>(ar, ai, kc, kc + 1, kc & 1, g, sh);
+            if (left > 8) {
+                if constexpr (B + 1 < T) gjl_step<T, CPLX, B, B + 1, true>(ar, ai, 7, 0, 1, g, sh);
+            } else {
+                gjl_step<T, CPLX, B, B, false>(ar, ai, nk - 1, 0, (nk - 1) & 1, g, sh);      // last step of the matrix
+            }
+            gjl_block<T, CPLX, B + 1>(ar, ai, m, g, sh);
+        }
+    }
+}
+
+// On exit: inverse[i][j] = sh->pinv[i] * tile[i][j]; the last barrier executed is the one that
+// opens step m-1, so every pinv entry is visible to the whole group.
+template <int T, bool CPLX>
+__device__ __forceinline__ void gj_inverse_la(double (&ar)[T][T], double (&ai)[T][T], const int m, const Group& g,
+                                              GJLScratch* sh) {
+    group_sync(g);   // previous readers of the scratch (pinv, row/col of the previous matrix) are done
+    gjl_publish<T, CPLX, 0>(ar, ai, 0, 0, g, sh);
+    gjl_block<T, CPLX, 0>(ar, ai, m, g, sh);
+}
+
+// ---------------------------------------------------------------------------------
 // acc[a][b] += sign * sum_{k<depth} Pa[k*lda + tr+8a] * Pb[k*ldb + tc+8b]
 // Pa / Pb are k-major panels in shared memory (lda, ldb >= 8T).
 // ---------------------------------------------------------------------------------

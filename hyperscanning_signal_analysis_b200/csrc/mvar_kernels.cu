@@ -47,8 +47,12 @@ struct K5Smem {
     // rows and columns are zero-padded to the 8T x 8T tile grid so the assembly loop needs no bounds checks
     static __host__ __device__ size_t coef_stride(int m, int p) { const int mp = 8 * T * p; return (size_t)(mp + ((2 - (mp & 15) + 16) & 15)); }
     static __host__ __device__ size_t coef_bytes(int m, int p) { return coef_stride(m, p) * 8 * T * sizeof(double); }
-    static __host__ __device__ size_t group_bytes() { return sizeof(GJScratch) + 2 * kPadMax * sizeof(double) + 4 * kPadMax * sizeof(double2) + 16; }
-    static __host__ __device__ size_t total(int m, int p, int ng) { return coef_bytes(m, p) + (size_t)ng * group_bytes() + 64; }
+    static __host__ __device__ size_t group_bytes() {
+        return sizeof(GJScratch) + sizeof(GJLScratch) + 2 * kPadMax * sizeof(double) + 3 * kPadMax * sizeof(double2) + 16;
+    }
+    // probe[i][k] = sum_j A_k[i][j] u_j (complex), the per-window part of the a-posteriori check vector A(f) u
+    static __host__ __device__ size_t probe_bytes(int p) { return (size_t)kPadMax * p * sizeof(double2); }
+    static __host__ __device__ size_t total(int m, int p, int ng) { return coef_bytes(m, p) + probe_bytes(p) + (size_t)ng * group_bytes() + 64; }
 };
 
 // probe vector of the a-posteriori check (any fixed vector without structure the elimination could preserve)
@@ -84,24 +88,35 @@ template <int T, int NG, int MODE>
 __global__ void __launch_bounds__(NG * 64, 1) transfer_dtf_kernel(const K5Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int m = P.m, p = P.p, F = P.F;
-    if (MODE == 2 && *P.bad_count == 0) return;
+    // MODE 2 walks the compact list of flagged matrices: one unit = one matrix, handled by group 0 of the CTA
+    const int n_bad = (MODE == 2) ? min(*P.bad_count, P.n_win * P.F) : 0;
+    if (MODE == 2 && n_bad == 0) return;
     const int cstride = (int)K5Smem<T>::coef_stride(m, p);
     double* coef = reinterpret_cast<double*>(smem_raw);
     const Group g = make_group(P.flip);
-    unsigned char* gbase = smem_raw + K5Smem<T>::coef_bytes(m, p) + (size_t)g.gid * K5Smem<T>::group_bytes();
+    double2* probe = reinterpret_cast<double2*>(smem_raw + K5Smem<T>::coef_bytes(m, p));          // [40][p]
+    unsigned char* gbase0 = smem_raw + K5Smem<T>::coef_bytes(m, p) + K5Smem<T>::probe_bytes(p);
+    unsigned char* gbase = gbase0 + (size_t)g.gid * K5Smem<T>::group_bytes();
     GJScratch* sh = reinterpret_cast<GJScratch*>(gbase);
-    double* rs_grp = reinterpret_cast<double*>(gbase + sizeof(GJScratch));                       // [2][40]
-    double2* vpart = reinterpret_cast<double2*>(gbase + sizeof(GJScratch) + 2 * kPadMax * sizeof(double));   // [2][40] A u
-    double2* wpart = vpart + 2 * kPadMax;                                                        // [2][40] H (A u)
+    GJLScratch* shl = reinterpret_cast<GJLScratch*>(gbase + sizeof(GJScratch));
+    double* rs_grp = reinterpret_cast<double*>(gbase + sizeof(GJScratch) + sizeof(GJLScratch));                  // [2][40]
+    double2* vfull = reinterpret_cast<double2*>(gbase + sizeof(GJScratch) + sizeof(GJLScratch) + 2 * kPadMax * sizeof(double));   // [40] A u
+    double2* wpart = vfull + kPadMax;                                                            // [2][40] S (A u)
     double* rs_mine = rs_grp + (g.l64 >> 5) * kPadMax;
-    const int n_units = P.n_win * P.n_seg;
+    const int n_units = (MODE == 2) ? n_bad : P.n_win * P.n_seg;
     const bool vec_ok = ((p & 1) == 0);
     const int off00 = g.tr * cstride + g.tc * p;      // this thread's tile entry (a = 0, b = 0) in the coefficient block
     double* rowpart = (MODE == 2) ? P.rowpart2 : P.rowpart;
 
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        const int w = unit / P.n_seg, seg = unit % P.n_seg;
-        const int f_begin = seg * P.seg_len, f_end = min(F, f_begin + P.seg_len);
+        int w = unit / P.n_seg, seg = unit % P.n_seg;
+        int f_begin = seg * P.seg_len, f_end = min(F, f_begin + P.seg_len);
+        if (MODE == 2) {
+            const int idx = P.bad_list[unit];
+            w = idx / F;
+            f_begin = idx - w * F;
+            f_end = f_begin + 1;
+        }
         __syncthreads();
         {   // AR coefficients of window w -> shared (zero padded to 8T x 8T, row stride cstride)
             const double* Aw = P.A + (size_t)w * m * m * p;
@@ -113,9 +128,26 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_dtf_kernel(const K5Params
             for (int e = g.l64; e < 2 * kPadMax; e += 64) rs_grp[e] = 0.0;
         }
         __syncthreads();
+        if (MODE == 1) {
+            // probe[i][k] = sum_j A_k[i][j] u_j : the window-dependent part of v = A(f) u = u - sum_k z_k(f) probe[.][k]
+            for (int e = threadIdx.x; e < kPadMax * p; e += NG * 64) {
+                const int i = e / p, k = e - i * p;
+                double sr = 0.0, si = 0.0;
+                if (i < 8 * T) {
+                    const double* cp = coef + i * cstride + k;
+                    for (int j = 0; j < m; ++j) {
+                        const double2 u = probe_u(j);
+                        const double c = cp[j * p];
+                        sr = fma(c, u.x, sr);
+                        si = fma(c, u.y, si);
+                    }
+                }
+                probe[e] = make_double2(sr, si);
+            }
+            __syncthreads();
+        }
 
         for (int f = f_begin + g.gid; f < f_end; f += NG) {
-            if (MODE == 2 && P.bad[(size_t)w * F + f] == 0) continue;      // group-uniform
             double ar[T][T], ai[T][T];
             // ---- build A(f) = I - sum_k A_k z_k(f)
 #pragma unroll
@@ -125,6 +157,9 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_dtf_kernel(const K5Params
                     ar[a][b] = ((g.tr + 8 * a) == (g.tc + 8 * b)) ? 1.0 : 0.0;
                     ai[a][b] = 0.0;
                 }
+            // v = A(f) u for the check: thread l64 (< 40) accumulates entry l64 next to the assembly
+            const int vi = min(g.l64, kPadMax - 1);
+            double2 vacc = (MODE == 1 && g.l64 < m) ? probe_u(g.l64) : make_double2(0.0, 0.0);
             if (vec_ok) {
                 for (int k = 0; k < p; k += 2) {
                     const double2 z0 = __ldg(&P.z[(size_t)k * F + f]);
@@ -138,6 +173,11 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_dtf_kernel(const K5Params
                             ar[a][b] = fma(-c.x, z0.x, fma(-c.y, z1.x, ar[a][b]));
                             ai[a][b] = fma(-c.x, z0.y, fma(-c.y, z1.y, ai[a][b]));
                         }
+                    }
+                    if (MODE == 1) {
+                        const double2 q0 = probe[vi * p + k], q1 = probe[vi * p + k + 1];
+                        vacc.x = fma(-q0.x, z0.x, fma(q0.y, z0.y, fma(-q1.x, z1.x, fma(q1.y, z1.y, vacc.x))));
+                        vacc.y = fma(-q0.x, z0.y, fma(-q0.y, z0.x, fma(-q1.x, z1.y, fma(-q1.y, z1.x, vacc.y))));
                     }
                 }
             } else {
@@ -153,6 +193,11 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_dtf_kernel(const K5Params
                             ai[a][b] = fma(-c, zz.y, ai[a][b]);
                         }
                     }
+                    if (MODE == 1) {
+                        const double2 q0 = probe[vi * p + k];
+                        vacc.x = fma(-q0.x, zz.x, fma(q0.y, zz.y, vacc.x));
+                        vacc.y = fma(-q0.x, zz.y, fma(-q0.y, zz.x, vacc.y));
+                    }
                 }
             }
             const size_t wbase = (size_t)w * m * m;
@@ -166,28 +211,24 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_dtf_kernel(const K5Params
                     }
             }
             bool good = true;
+            double2 sc[T];          // MODE 1: H[i][j] = sc[a] * tile[a][b] (deferred row scaling of gj_inverse_la)
             if (MODE == 1) {
-                // v = A(f) u, kept as per-warp partials in shared memory until the check
+                group_sync(g);                      // previous matrix' check has finished reading vfull / wpart
+                if (g.l64 < kPadMax) vfull[g.l64] = vacc;
+                if (g.l64 == 0) sh->singular = 0;
+                gj_inverse_la<T, true>(ar, ai, m, g, shl);
                 double2 x[T];
 #pragma unroll
-                for (int b = 0; b < T; ++b) x[b] = (g.tc + 8 * b < m) ? probe_u(g.tc + 8 * b) : make_double2(0.0, 0.0);
-                group_sync(g);                      // previous matrix' check has finished reading vpart / wpart
-                tile_matvec_partial<T>(ar, ai, x, vpart, g);
-                gj_inverse_static<T, true>(ar, ai, m, g, sh);
-                group_sync(g);
+                for (int b = 0; b < T; ++b) x[b] = vfull[g.tc + 8 * b];         // 0 in the padding
 #pragma unroll
-                for (int b = 0; b < T; ++b) {
-                    const int j = g.tc + 8 * b;
-                    const double2 v0 = vpart[j], v1 = vpart[kPadMax + j];
-                    x[b] = (j < m) ? make_double2(v0.x + v1.x, v0.y + v1.y) : make_double2(0.0, 0.0);
-                }
-                if (g.l64 == 0) sh->singular = 0;
+                for (int a = 0; a < T; ++a) sc[a] = shl->pinv[g.tr + 8 * a];
                 tile_matvec_partial<T>(ar, ai, x, wpart, g);
                 group_sync(g);
                 if (g.l64 < m) {
-                    const double2 u = probe_u(g.l64);
-                    const double er = wpart[g.l64].x + wpart[kPadMax + g.l64].x - u.x;
-                    const double ei = wpart[g.l64].y + wpart[kPadMax + g.l64].y - u.y;
+                    const double2 u = probe_u(g.l64), iv = shl->pinv[g.l64];
+                    const double sr = wpart[g.l64].x + wpart[kPadMax + g.l64].x, si = wpart[g.l64].y + wpart[kPadMax + g.l64].y;
+                    const double er = fma(iv.x, sr, -iv.y * si) - u.x;
+                    const double ei = fma(iv.x, si, iv.y * sr) - u.y;
                     const double err = fma(er, er, ei * ei), ref = fma(u.x, u.x, u.y * u.y);
                     if (!(err <= P.verify_tol2 * ref)) sh->singular = 1;      // also catches NaN / Inf
                 }
@@ -195,7 +236,7 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_dtf_kernel(const K5Params
                 good = (sh->singular == 0);
                 if (!good && g.l64 == 0) {
                     P.bad[(size_t)w * F + f] = 1;
-                    atomicAdd(P.bad_count, 1);
+                    P.bad_list[atomicAdd(P.bad_count, 1)] = w * F + f;
                 }
             } else {
                 gj_inverse<T, true>(ar, ai, m, g, sh);
@@ -212,16 +253,22 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_dtf_kernel(const K5Params
                 for (int a = 0; a < T; ++a) {
                     const int i = g.tr + 8 * a;
                     const int ri = (MODE == 1) ? i : sh->rowmap[min(i, kPadMax - 1)];
+                    const double s2 = (MODE == 1) ? fma(sc[a].x, sc[a].x, sc[a].y * sc[a].y) : 1.0;
                     double rsum = 0.0;
 #pragma unroll
                     for (int b = 0; b < T; ++b) {
                         const int j = g.tc + 8 * b;
                         if (i < m && j < m) {
-                            const double v = fma(ar[a][b], ar[a][b], ai[a][b] * ai[a][b]);
+                            double v = fma(ar[a][b], ar[a][b], ai[a][b] * ai[a][b]);
+                            if (MODE == 1) v *= s2;
                             rsum += v;
                             const size_t o = (wbase + (size_t)ri * m + cj[b]) * F + f;
-                            if (P.dtf) P.dtf[o] = v;
-                            if (P.H) P.H[o] = make_double2(ar[a][b], ai[a][b]);
+                            if (P.dtf) P.dtf[P.dtf_fij ? (((size_t)w * F + f) * m + ri) * m + cj[b] : o] = v;
+                            if (P.H) {
+                                double2 h = make_double2(ar[a][b], ai[a][b]);
+                                if (MODE == 1) h = make_double2(fma(sc[a].x, ar[a][b], -sc[a].y * ai[a][b]), fma(sc[a].x, ai[a][b], sc[a].y * ar[a][b]));
+                                P.H[o] = h;
+                            }
                         }
                     }
                     // reduce over the 4 column groups of this warp (lane bits 3, 4), fixed order
@@ -233,10 +280,10 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_dtf_kernel(const K5Params
         }
         // ---- per-unit row sums (fixed summation order -> deterministic)
         __syncthreads();
-        if (rowpart && threadIdx.x < m) {
+        if (MODE != 2 && rowpart && threadIdx.x < m) {
             double acc = 0.0;
             for (int q = 0; q < NG; ++q) {
-                const double* rg = reinterpret_cast<const double*>(smem_raw + K5Smem<T>::coef_bytes(m, p) + (size_t)q * K5Smem<T>::group_bytes() + sizeof(GJScratch));
+                const double* rg = reinterpret_cast<const double*>(gbase0 + (size_t)q * K5Smem<T>::group_bytes() + sizeof(GJScratch) + sizeof(GJLScratch));
                 acc += rg[threadIdx.x] + rg[kPadMax + threadIdx.x];
             }
             rowpart[((size_t)w * P.n_seg + seg) * m + threadIdx.x] = acc;
@@ -275,12 +322,75 @@ __global__ void ffdtf_normalize_kernel(double* __restrict__ dtf, const double* _
     }
 }
 
+// Transposing finalize:  stage (n_win, F, m, m)  ->  dtf / ffdtf (n_win, m, m, F)  with
+// ffdtf[w][i][j][f] = dtf[w][i][j][f] / sum_{j,f} dtf[w][i][j][f]   (mtmvar.py:281-283).
+// One CTA per (window, row i): the F runs of m contiguous doubles are read coalesced, transposed through shared
+// memory in chunks of kFinChunk bins and written as contiguous runs along f.
+constexpr int kFinChunk = 32;
+__global__ void __launch_bounds__(256) dtf_finalize_kernel(const double* __restrict__ stage, const double* __restrict__ rowpart,
+                                                           const int* __restrict__ bad, int m, int F, int n_seg,
+                                                           double* __restrict__ dtf_out, double* __restrict__ ffdtf_out) {
+    extern __shared__ double tile[];                 // [m][kFinChunk + 1]
+    const int w = blockIdx.y, i = blockIdx.x;
+    __shared__ double denom_s;
+    __shared__ int any_bad;
+    if (threadIdx.x == 0) any_bad = 0;
+    __syncthreads();
+    if (rowpart && bad) {
+        int mine = 0;
+        for (int f = threadIdx.x; f < F; f += blockDim.x) mine |= bad[(size_t)w * F + f];
+        if (mine) any_bad = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // row sum of |H|^2 over (j, f): per-segment partials of the optimistic pass (which skips the bins it flagged) ...
+        double acc = 0.0;
+        if (rowpart)
+            for (int s = 0; s < n_seg; ++s) acc += rowpart[((size_t)w * n_seg + s) * m + i];
+        // ... plus the bins redone with pivoting, summed here in a fixed order (rare)
+        if (rowpart && any_bad)
+            for (int f = 0; f < F; ++f)
+                if (bad[(size_t)w * F + f])
+                    for (int j = 0; j < m; ++j) acc += stage[(((size_t)w * F + f) * m + i) * m + j];
+        denom_s = acc;
+    }
+    __syncthreads();
+    const double denom = denom_s;
+    const size_t obase = ((size_t)w * m + i) * (size_t)m * F;
+    for (int f0 = 0; f0 < F; f0 += kFinChunk) {
+        const int nf = min(kFinChunk, F - f0);
+        for (int e = threadIdx.x; e < nf * m; e += blockDim.x) {
+            const int f = e / m, j = e - f * m;
+            tile[j * (kFinChunk + 1) + f] = stage[(((size_t)w * F + f0 + f) * m + i) * m + j];
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < m * kFinChunk; e += blockDim.x) {
+            const int j = e / kFinChunk, f = e - j * kFinChunk;
+            if (f < nf) {
+                const double v = tile[j * (kFinChunk + 1) + f];
+                const size_t o = obase + (size_t)j * F + f0 + f;
+                if (dtf_out) dtf_out[o] = v;
+                if (ffdtf_out) ffdtf_out[o] = v / denom;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+int launch_dtf_finalize(const double* stage, const double* rowpart, const int* bad, int n_win, int m, int F, int n_seg,
+                        double* dtf_out, double* ffdtf_out, cudaStream_t stream) {
+    dim3 grid(m, n_win);
+    const size_t smem = (size_t)m * (kFinChunk + 1) * sizeof(double);
+    dtf_finalize_kernel<<<grid, 256, smem, stream>>>(stage, rowpart, bad, m, F, n_seg, dtf_out, ffdtf_out);
+    return check_launch("dtf_finalize_kernel");
+}
+
 template <int T, int NG, int MODE>
 static int launch_k5_t(const K5Params& P, int sm_count, cudaStream_t stream) {
     const size_t smem = K5Smem<T>::total(P.m, P.p, NG);
     cudaError_t e = cudaFuncSetAttribute(transfer_dtf_kernel<T, NG, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "transfer_dtf: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
-    const int n_units = P.n_win * P.n_seg;
+    const int n_units = (MODE == 2) ? P.n_win * P.F : P.n_win * P.n_seg;
     const int grid = n_units < sm_count ? n_units : sm_count;
     transfer_dtf_kernel<T, NG, MODE><<<grid, NG * 64, smem, stream>>>(P);
     return check_launch("transfer_dtf_kernel");

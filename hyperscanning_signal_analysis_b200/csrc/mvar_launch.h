@@ -38,7 +38,10 @@ struct K5Params {
     double* rowpart2;       // row sums of the matrices redone with pivoting (mode 2)
     int* bad;               // (n_win * F) flags set by the optimistic pass
     int* bad_count;         // number of flagged matrices
+    int* bad_list;          // (n_win * F) compact list of flagged matrices (w * F + f), filled by the optimistic pass
     double verify_tol2;     // squared relative tolerance of the a-posteriori check
+    int dtf_fij;            // 1: P.dtf is a staging buffer laid out (n_win, F, m, m) -- one contiguous matrix per bin --
+                            //    that launch_dtf_finalize transposes to the reference's (n_win, m, m, F)
 };
 
 int launch_lagcov(const K3Params& P, cudaStream_t stream);
@@ -48,6 +51,10 @@ int lwr_grid(int n_win);
 int launch_lwr(const K4Params& P, int grid, cudaStream_t stream);
 int launch_ztable(const double* freqs, int F, int p, double fs, void* z, cudaStream_t stream);
 int launch_transfer_dtf(const K5Params& P, int ng, int mode, cudaStream_t stream);
+bool transfer_mma_fits(int p, int ng);       // shared memory for the coefficient planes of order p fits next to ng groups
+int launch_transfer_mma(const K5Params& P, int ng, cudaStream_t stream);      // optimistic pass on the FP64 tensor pipe (transfer_mma.cu)
+int launch_dtf_finalize(const double* stage, const double* rowpart, const int* bad, int n_win, int m, int F, int n_seg,
+                        double* dtf_out, double* ffdtf_out, cudaStream_t stream);
 int launch_ffdtf_normalize(double* dtf, const double* rowpart, const double* rowpart2, int n_win, int m, int F, int n_seg, double* out,
                            cudaStream_t stream);
 size_t lwr_generic_ws_doubles(int n_win, int m, int p);

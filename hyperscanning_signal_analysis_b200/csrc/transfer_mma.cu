@@ -1,0 +1,506 @@
+// K5 on the FP64 tensor pipe:  A(f) = I - sum_k A_k z_k(f),  H = A(f)^-1,  |H|^2  (m <= 40).
+//
+// Replaces, per (window, frequency bin), the body of the reference's loop in
+// mvar_transfer_function (/root/reference src/mtmvar.py:155-159: A(f) assembly + np.linalg.inv) and the
+// |H|^2 of dtf_multivariate / full_freq_dtf (:232, :278).
+//
+// Why DMMA: a rank-1 Gauss-Jordan update on register tiles is one DFMA per matrix entry with three
+// distinct 64-bit register operands, which this chip issues at 2.46 cycles/warp-instruction instead of 2
+// (tools/lat_probe.cu), plus ~1 non-FMA instruction per FMA.  mma.sync.m8n8k4.f64 does 8 FMAs per lane and
+// instruction from 4 register operands and reaches the FP64 pipe's peak with the matrix resident in
+// registers (tools/dmma_probe.cu: 100 % of peak with fragment LDS + barriers).  So the elimination is a
+// BLOCK Gauss-Jordan with 4 x 4 pivot blocks, and everything except the 4 x 4 inverse is DMMA.
+//
+// Layout: one matrix = one GROUP of two warps; warp 0 holds Re S, warp 1 holds Im S, both as T x T
+// tiles of 8 x 8 in the m8n8k4 accumulator layout (lane l: row l>>2, columns 2(l&3), 2(l&3)+1), 50 doubles
+// per lane for T = 5.  Re/Im split => both warps do identical work.
+//
+// Block step for the pivot block K = {k0..k0+3}, D = S[K,K], C = S[:,K], R = S[K,:]:
+//   P = D^-1                                (16 lanes, in-place Gauss-Jordan with shuffles)
+//   L = C P          for rows outside K     (DMMA: A = C as extracted, B = -P with Re/Im interleaved by column,
+//   L = I - P        for the rows K          so the accumulator IS the (-L_re, -L_im) A-fragment of the next DMMAs)
+//   S[:,K] := identity pattern (0, and I on D);  U := R with the same pattern
+//   S <- S - L U                            (2 DMMAs per real tile: Re S += (-Lr) Ur + (+Li) Ui, Im S += (-Lr) Ui + (-Li) Ur)
+// which yields  S[K,:] = P U  (scaled pivot rows incl. P itself in the columns K),  S[i,K] = -L  and the rank-4
+// update everywhere else: the in-place block Gauss-Jordan inverse.  After ceil(m/4) steps S = H.
+// Data flow per step: both warps copy their part of the NEXT panel (columns as A fragments, rows as B
+// fragments) to shared memory right after the update, one 64-thread barrier, then each warp inverts D for itself.
+//
+// Stability is that of elimination without pivoting across blocks; the kernel verifies every matrix
+// (|| H (A u) - u || on a probe vector) and flags failures for the pivoted register-tile kernel
+// (transfer_dtf_kernel MODE 2).
+#include "hs_tile.cuh"
+#include "hs_internal.h"
+#include "mvar_launch.h"
+
+namespace hs {
+
+namespace {
+
+constexpr int kMP = 40;                     // padded matrix dimension (5 tiles of 8)
+constexpr int kRowD = 2 * kMP + 2;          // doubles per coefficient row of one lag pair: 40 x (2 lags) + 16 B skew
+constexpr int kPlaneD = kMP * kRowD + 4;    // doubles per lag-pair plane (+32 B skew between planes)
+constexpr int kUS = 52;                     // row stride of the B-fragment buffer (= 4 mod 16 doubles: conflict-free fragment loads)
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, const double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double flip_sign(const double v, const int mask_hi) {
+    return __hiloint2double(__double2hiint(v) ^ mask_hi, __double2loint(v));
+}
+
+__device__ __forceinline__ double rcp_newton2(const double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));     // ~20 bits
+    y = fma(y, fma(-x, y, 1.0), y);                             // ~40
+    y = fma(y, fma(-x, y, 1.0), y);                             // full
+    return y;
+}
+
+struct __align__(16) MmaGroupSmem {
+    union {
+        struct {
+            double Craw[2][2][kMP * 4];    // [buf][part][row*4 + k]   panel columns  (A-fragment order)
+            double Rraw[2][2][4 * kUS];    // [buf][part][k*52 + col]  panel rows with the identity pattern (B-fragment order)
+            double2 P[2][16];              // [warp][i*4 + j]          D^-1, private copy per warp
+        } p;
+        double2 X[25][32];                 // Re/Im exchange of the epilogue (after the elimination)
+    } u;
+    double2 vfull[kMP];                    // A(f) u
+    double wpart[2][2][kMP];               // [part][vr|vi][row]  partial S v
+    double rs[2][kMP];                     // ffDTF row sums of this unit, per warp
+    int flag;
+    int pad_[3];
+};
+
+struct MmaCtx {
+    int part, lane, g4, t4, bar;
+    MmaGroupSmem* gs;
+};
+
+__device__ __forceinline__ void mma_group_sync(const MmaCtx& x) { asm volatile("bar.sync %0, 64;" ::"r"(x.bar) : "memory"); }
+
+// ---- copy the panel (tile t, half h: columns / rows 8t+4h .. 8t+4h+3) of the own part to shared memory, then put
+//      the identity pattern into the panel columns of the register tiles
+template <int T, int t>
+__device__ __forceinline__ void mma_extract(double (&c)[T][T][2], const int h, const MmaCtx& x) {
+    MmaGroupSmem* gs = x.gs;
+    const bool col_lane = (x.t4 >> 1) == h;
+    if (col_lane) {
+#pragma unroll
+        for (int ta = 0; ta < T; ++ta)
+            *reinterpret_cast<double2*>(&gs->u.p.Craw[h][x.part][(8 * ta + x.g4) * 4 + 2 * (x.t4 & 1)]) = make_double2(c[ta][t][0], c[ta][t][1]);
+    }
+    // identity pattern of the panel columns
+    const double d0 = (x.part == 0 && x.g4 == 2 * x.t4) ? 1.0 : 0.0, d1 = (x.part == 0 && x.g4 == 2 * x.t4 + 1) ? 1.0 : 0.0;
+    if (col_lane) {
+#pragma unroll
+        for (int ta = 0; ta < T; ++ta) {
+            c[ta][t][0] = (ta == t) ? d0 : 0.0;
+            c[ta][t][1] = (ta == t) ? d1 : 0.0;
+        }
+    }
+    if ((x.lane >> 4) == h) {
+#pragma unroll
+        for (int tb = 0; tb < T; ++tb)
+            *reinterpret_cast<double2*>(&gs->u.p.Rraw[h][x.part][(x.g4 & 3) * kUS + 8 * tb + 2 * x.t4]) = make_double2(c[t][tb][0], c[t][tb][1]);
+    }
+}
+
+// ---- P = D^-1 of the panel in buffer `buf`: lanes 0..15 (mirrored in 16..31) hold D[i][j], in-place Gauss-Jordan with shuffles
+__device__ __forceinline__ void mma_inverse4(const MmaCtx& x, const int K0, const int buf) {
+    MmaGroupSmem* gs = x.gs;
+    const int i = (x.lane >> 2) & 3, j = x.lane & 3;
+    double dr = gs->u.p.Craw[buf][0][(K0 + i) * 4 + j];
+    double di = gs->u.p.Craw[buf][1][(K0 + i) * 4 + j];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const double pr = __shfl_sync(0xffffffffu, dr, s * 5, 16), pi = __shfl_sync(0xffffffffu, di, s * 5, 16);
+        const double rjr = __shfl_sync(0xffffffffu, dr, s * 4 + j, 16), rji = __shfl_sync(0xffffffffu, di, s * 4 + j, 16);
+        const double cir = __shfl_sync(0xffffffffu, dr, i * 4 + s, 16), cii = __shfl_sync(0xffffffffu, di, i * 4 + s, 16);
+        const double y = rcp_newton2(fma(pr, pr, pi * pi));
+        const double ivr = pr * y, ivi = -pi * y;
+        const bool prow = (i == s), pcol = (j == s);
+        const double sr = prow ? dr : cir, si = prow ? di : cii;       // pivot row: scale the own entry; other rows: multiplier
+        const double tr = fma(sr, ivr, -si * ivi), ti = fma(sr, ivi, si * ivr);
+        const double ur = fma(-tr, rjr, fma(ti, rji, dr)), ui = fma(-tr, rji, fma(-ti, rjr, di));
+        dr = prow ? (pcol ? ivr : tr) : (pcol ? -tr : ur);
+        di = prow ? (pcol ? ivi : ti) : (pcol ? -ti : ui);
+    }
+    if (x.lane < 16) gs->u.p.P[x.part][x.lane] = make_double2(dr, di);
+    __syncwarp();
+}
+
+// ---- the two block steps of tile t (h = 0, 1): hand-over of the panel, 4 x 4 inverse, L panel by DMMA, rank-4 update
+template <int T, int t>
+__device__ __forceinline__ void mma_tile_steps(double (&c)[T][T][2], const int m, const MmaCtx& x) {
+    MmaGroupSmem* gs = x.gs;
+    const int fo = x.g4 * 4 + x.t4;           // A-fragment offset inside a tile row
+    const int sgn = x.part ? 0 : (int)0x80000000;       // Re warp needs +Li = -(NL_i)
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+        const int K0 = 8 * t + 4 * h;
+        if (K0 >= m) break;
+        mma_extract<T, t>(c, h, x);
+        mma_group_sync(x);
+        mma_inverse4(x, K0, h);
+        // B fragments of -P with Re/Im interleaved by output column:  n = 2j -> Re, n = 2j+1 -> Im
+        double a0[T], a1[T];
+        {
+            const double2 pv = gs->u.p.P[x.part][x.t4 * 4 + (x.g4 >> 1)];
+            const bool odd = x.g4 & 1;
+            const double bB1 = odd ? -pv.y : -pv.x;        // multiplies Re C
+            const double bB2 = odd ? -pv.x : pv.y;         // multiplies Im C
+            const double* Cr = gs->u.p.Craw[h][0] + fo;
+            const double* Ci = gs->u.p.Craw[h][1] + fo;
+#pragma unroll
+            for (int ta = 0; ta < T; ++ta) {
+                double l0 = 0.0, l1 = 0.0;
+                dmma884(l0, l1, Cr[32 * ta], bB1);
+                dmma884(l0, l1, Ci[32 * ta], bB2);
+                a0[ta] = l0;
+                a1[ta] = l1;
+            }
+            // rows K of the panel: -L = P - I
+            const double2 pk = gs->u.p.P[x.part][(x.g4 & 3) * 4 + x.t4];
+            if ((x.g4 >> 2) == h) {
+                a0[t] = pk.x - (((x.g4 & 3) == x.t4) ? 1.0 : 0.0);
+                a1[t] = pk.y;
+            }
+#pragma unroll
+            for (int ta = 0; ta < T; ++ta) a1[ta] = flip_sign(a1[ta], sgn);
+        }
+        {
+            const double* Ua = gs->u.p.Rraw[h][x.part] + x.t4 * kUS + x.g4;
+            const double* Ub = gs->u.p.Rraw[h][x.part ^ 1] + x.t4 * kUS + x.g4;
+            double b0[T], b1[T];
+#pragma unroll
+            for (int tb = 0; tb < T; ++tb) {
+                b0[tb] = Ua[8 * tb];
+                b1[tb] = Ub[8 * tb];
+            }
+#pragma unroll
+            for (int ta = 0; ta < T; ++ta) {
+#pragma unroll
+                for (int tb = 0; tb < T; ++tb) {
+                    dmma884(c[ta][tb][0], c[ta][tb][1], a0[ta], b0[tb]);
+                    dmma884(c[ta][tb][0], c[ta][tb][1], a1[ta], b1[tb]);
+                }
+            }
+        }
+    }
+}
+
+template <int T, int t>
+__device__ __forceinline__ void mma_all_tiles(double (&c)[T][T][2], const int m, const MmaCtx& x) {
+    if constexpr (t < T) {
+        mma_tile_steps<T, t>(c, m, x);
+        mma_all_tiles<T, t + 1>(c, m, x);
+    }
+}
+
+// in-place inverse of the matrix held by the two warps of the group
+template <int T>
+__device__ __forceinline__ void mma_gauss_jordan(double (&c)[T][T][2], const int m, const MmaCtx& x) {
+    mma_group_sync(x);                 // previous users of the panel buffers (assembly exchange) are done
+    mma_all_tiles<T, 0>(c, m, x);
+}
+
+
+// ---- A(f) = I - sum_k A_k z_k(f).  Each warp assembles ONE of the two entries every lane owns per tile
+//      (Re warp: column 2*t4, Im warp: column 2*t4 + 1) as a complex number, keeps the part it owns and hands the
+//      other part to the partner warp through gs->u.X: every coefficient is read from shared memory once per
+//      matrix, and both warps run the same code (the part only selects operands).
+template <int T>
+__device__ __forceinline__ void mma_assemble(double (&c)[T][T][2], const double* __restrict__ coef, const double2* __restrict__ zf,
+                                             const int F, const int p, const int n_planes, const MmaCtx& x) {
+    double vr[T][T], vi[T][T];
+#pragma unroll
+    for (int ta = 0; ta < T; ++ta)
+#pragma unroll
+        for (int tb = 0; tb < T; ++tb) vr[ta][tb] = vi[ta][tb] = 0.0;
+    const double* cbase = coef + x.g4 * kRowD + 4 * x.t4 + 2 * x.part;
+    for (int kp = 0; kp < n_planes; ++kp) {
+        const double2 z0 = __ldg(&zf[(size_t)(2 * kp) * F]);
+        const double2 z1 = (2 * kp + 1 < p) ? __ldg(&zf[(size_t)(2 * kp + 1) * F]) : make_double2(0.0, 0.0);
+        const double* cp = cbase + kp * kPlaneD;
+#pragma unroll
+        for (int ta = 0; ta < T; ++ta) {
+#pragma unroll
+            for (int tb = 0; tb < T; ++tb) {
+                const double2 q = *reinterpret_cast<const double2*>(cp + ta * 8 * kRowD + tb * 16);
+                vr[ta][tb] = fma(-q.x, z0.x, fma(-q.y, z1.x, vr[ta][tb]));
+                vi[ta][tb] = fma(-q.x, z0.y, fma(-q.y, z1.y, vi[ta][tb]));
+            }
+        }
+    }
+    const double dg = (x.g4 == 2 * x.t4 + x.part) ? 1.0 : 0.0;      // identity (real part) of the entry this warp assembled
+    double* X = reinterpret_cast<double*>(x.gs->u.X) + x.part * (25 * 32) + x.lane;          // outbox of this warp
+#pragma unroll
+    for (int ta = 0; ta < T; ++ta) {
+#pragma unroll
+        for (int tb = 0; tb < T; ++tb) {
+            if (ta == tb) vr[ta][tb] += dg;
+            X[(ta * T + tb) * 32] = x.part ? vr[ta][tb] : vi[ta][tb];      // the part the partner owns
+        }
+    }
+    mma_group_sync(x);
+    const double* Xo = reinterpret_cast<const double*>(x.gs->u.X) + (x.part ^ 1) * (25 * 32) + x.lane;      // the partner's outbox
+#pragma unroll
+    for (int ta = 0; ta < T; ++ta) {
+#pragma unroll
+        for (int tb = 0; tb < T; ++tb) {
+            const double own = x.part ? vi[ta][tb] : vr[ta][tb];
+            const double got = Xo[(ta * T + tb) * 32];
+            c[ta][tb][0] = x.part ? got : own;
+            c[ta][tb][1] = x.part ? own : got;
+        }
+    }
+}
+
+// Outputs in the reference's (w, i, j, f) layout (A(f), H, or |H|^2 without the staging buffer): not the metric path.
+// The register tiles must never have their address taken (the compiler would mirror them in local memory), so both
+// warps dump their part to gs->u.X, one of the two entries per lane and tile at a time, and a compact loop with one
+// thread per matrix row does the addressing.  FINAL: H / |H|^2 / row sums; otherwise A(f).
+template <int T, bool FINAL>
+__device__ __forceinline__ void mma_store_generic(const double (&c)[T][T][2], const K5Params& P, const int w, const int f, const MmaCtx& x) {
+    const int m = P.m;
+    const size_t sF = (size_t)P.F;
+    const int l64 = x.part * 32 + x.lane;
+    double* Xd = reinterpret_cast<double*>(x.gs->u.X);
+    double rsum = 0.0;
+#pragma unroll 1
+    for (int e = 0; e < 2; ++e) {
+        mma_group_sync(x);
+#pragma unroll
+        for (int q = 0; q < T * T; ++q) Xd[x.part * (25 * 32) + q * 32 + x.lane] = e ? c[q / T][q % T][1] : c[q / T][q % T][0];
+        mma_group_sync(x);
+        if (l64 < m) {
+            const int i = l64, ta = i >> 3, g4 = i & 7;
+            for (int j = e; j < m; j += 2) {
+                const int tb = j >> 3, t4 = (j & 7) >> 1;
+                const int off = (ta * T + tb) * 32 + g4 * 4 + t4;
+                const double re = Xd[off], im = Xd[25 * 32 + off];
+                const size_t o = (((size_t)w * m + i) * m + j) * sF + f;
+                if (FINAL) {
+                    const double v = fma(re, re, im * im);
+                    rsum += v;
+                    if (P.dtf) P.dtf[P.dtf_fij ? (((size_t)w * sF + f) * m + i) * m + j : o] = v;
+                    if (P.H) P.H[o] = make_double2(re, im);
+                } else {
+                    P.Af[o] = make_double2(re, im);
+                }
+            }
+        }
+    }
+    if (FINAL && l64 < m) x.gs->rs[0][l64] += rsum;
+    mma_group_sync(x);
+}
+
+__device__ __forceinline__ double2 probe_u2(const int j) {
+    return make_double2(1.0 + 0.03125 * j, ((j & 1) ? -1.0 : 1.0) * (0.5 + 0.015625 * j));
+}
+
+template <int T>
+struct MmaSmem {
+    static __host__ __device__ int planes(int p) { return (p + 1) / 2; }
+    static __host__ __device__ size_t coef_bytes(int p) { return (size_t)planes(p) * kPlaneD * sizeof(double); }
+    static __host__ __device__ size_t probe_bytes(int p) { return (size_t)kMP * p * sizeof(double2); }
+    static __host__ __device__ size_t total(int p, int ng) { return coef_bytes(p) + probe_bytes(p) + (size_t)ng * sizeof(MmaGroupSmem) + 64; }
+};
+
+template <int T, int NG>
+__global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int m = P.m, p = P.p, F = P.F;
+    double* coef = reinterpret_cast<double*>(smem_raw);
+    double2* probe = reinterpret_cast<double2*>(smem_raw + MmaSmem<T>::coef_bytes(p));
+    MmaGroupSmem* groups = reinterpret_cast<MmaGroupSmem*>(smem_raw + MmaSmem<T>::coef_bytes(p) + MmaSmem<T>::probe_bytes(p));
+    const int warp = threadIdx.x >> 5;
+    MmaCtx x;
+    x.lane = threadIdx.x & 31;
+    x.part = warp & 1;
+    x.g4 = x.lane >> 2;
+    x.t4 = x.lane & 3;
+    const int gid = warp >> 1;
+    x.bar = 1 + gid;
+    x.gs = groups + gid;
+    MmaGroupSmem* gs = x.gs;
+    const int l64 = x.part * 32 + x.lane;
+    const int n_units = P.n_win * P.n_seg;
+    const int n_planes = MmaSmem<T>::planes(p);
+
+    // zero the coefficient planes once: padding rows / columns / the odd lag stay zero for every unit
+    for (int e = threadIdx.x; e < n_planes * kPlaneD; e += NG * 64) coef[e] = 0.0;
+
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int w = unit / P.n_seg, seg = unit % P.n_seg;
+        const int f_begin = seg * P.seg_len, f_end = min(F, f_begin + P.seg_len);
+        __syncthreads();
+        {   // AR coefficients of window w -> shared, layout [lag pair][row][col][lag & 1]
+            const double* Aw = P.A + (size_t)w * m * m * p;
+            const int row_len = m * p;
+            for (int i = warp; i < m; i += NG * 2) {       // one warp per row
+                for (int cidx = x.lane; cidx < row_len; cidx += 32) {
+                    const int j = cidx / p, k = cidx - j * p;
+                    coef[(k >> 1) * kPlaneD + i * kRowD + 2 * j + (k & 1)] = Aw[(size_t)i * row_len + cidx];
+                }
+            }
+            for (int e = l64; e < 2 * kMP; e += 64) (&gs->rs[0][0])[e] = 0.0;
+        }
+        __syncthreads();
+        // probe[i][k] = sum_j A_k[i][j] u_j : the window-dependent part of v = A(f) u = u - sum_k z_k(f) probe[.][k]
+        for (int e = threadIdx.x; e < kMP * p; e += NG * 64) {
+            const int i = e / p, k = e - i * p;
+            double sr = 0.0, si = 0.0;
+            const double* cp = coef + (k >> 1) * kPlaneD + i * kRowD + (k & 1);
+            for (int j = 0; j < m; ++j) {
+                const double2 u = probe_u2(j);
+                const double cv = cp[2 * j];
+                sr = fma(cv, u.x, sr);
+                si = fma(cv, u.y, si);
+            }
+            probe[e] = make_double2(sr, si);
+        }
+        __syncthreads();
+
+        for (int f = f_begin + gid; f < f_end; f += NG) {
+            double c[T][T][2];
+            // ---- v = A(f) u for the check (thread l64 < 40 owns entry l64)
+            const int vi = min(l64, kMP - 1);
+            double2 vacc = (l64 < m) ? probe_u2(l64) : make_double2(0.0, 0.0);
+            for (int k = 0; k < p; ++k) {
+                const double2 zz = __ldg(&P.z[(size_t)k * F + f]);
+                const double2 q0 = probe[vi * p + k];
+                vacc.x = fma(-q0.x, zz.x, fma(q0.y, zz.y, vacc.x));
+                vacc.y = fma(-q0.x, zz.y, fma(-q0.y, zz.x, vacc.y));
+            }
+            mma_group_sync(x);                      // previous matrix' check / epilogue is done with vfull, wpart, X
+            if (l64 < kMP) gs->vfull[l64] = vacc;
+            if (l64 == 0) gs->flag = 0;
+            // ---- A(f) = I - sum_k A_k z_k(f)
+            mma_assemble<T>(c, coef, P.z + f, F, p, n_planes, x);
+            if (P.Af) mma_store_generic<T, false>(c, P, w, f, x);
+            // ---- blocked Gauss-Jordan on the tensor pipe
+            mma_gauss_jordan<T>(c, m, x);
+            // ---- a-posteriori check:  S v == u ?   (v = A(f) u)
+            {
+                double sr[T], si[T];
+#pragma unroll
+                for (int ta = 0; ta < T; ++ta) sr[ta] = si[ta] = 0.0;
+#pragma unroll
+                for (int tb = 0; tb < T; ++tb) {
+                    const double2 v0 = gs->vfull[8 * tb + 2 * x.t4], v1 = gs->vfull[8 * tb + 2 * x.t4 + 1];
+#pragma unroll
+                    for (int ta = 0; ta < T; ++ta) {
+                        sr[ta] = fma(c[ta][tb][0], v0.x, fma(c[ta][tb][1], v1.x, sr[ta]));
+                        si[ta] = fma(c[ta][tb][0], v0.y, fma(c[ta][tb][1], v1.y, si[ta]));
+                    }
+                }
+#pragma unroll
+                for (int ta = 0; ta < T; ++ta) {
+                    sr[ta] += __shfl_xor_sync(0xffffffffu, sr[ta], 1);
+                    si[ta] += __shfl_xor_sync(0xffffffffu, si[ta], 1);
+                    sr[ta] += __shfl_xor_sync(0xffffffffu, sr[ta], 2);
+                    si[ta] += __shfl_xor_sync(0xffffffffu, si[ta], 2);
+                    if (x.t4 == 0) {
+                        gs->wpart[x.part][0][8 * ta + x.g4] = sr[ta];
+                        gs->wpart[x.part][1][8 * ta + x.g4] = si[ta];
+                    }
+                }
+            }
+            mma_group_sync(x);
+            if (l64 < m) {
+                // S v = (Sr vr - Si vi) + i (Sr vi + Si vr)
+                const double wr = gs->wpart[0][0][l64] - gs->wpart[1][1][l64];
+                const double wi = gs->wpart[0][1][l64] + gs->wpart[1][0][l64];
+                const double2 u = probe_u2(l64);
+                const double er = wr - u.x, ei = wi - u.y;
+                const double err = fma(er, er, ei * ei), ref = fma(u.x, u.x, u.y * u.y);
+                if (!(err <= P.verify_tol2 * ref)) gs->flag = 1;      // also catches NaN / Inf
+            }
+            // ---- Re/Im exchange for |H|^2 (the panel buffers are free: the barrier above is past every fragment load).
+            //      The Re warp finishes the entries in even columns, the Im warp those in odd columns.
+            {
+                double* X = reinterpret_cast<double*>(gs->u.X) + x.part * (25 * 32) + x.lane;      // outbox of this warp
+#pragma unroll
+                for (int q = 0; q < T * T; ++q) X[q * 32] = x.part ? c[q / T][q % T][0] : c[q / T][q % T][1];
+            }
+            mma_group_sync(x);
+            const bool good = (gs->flag == 0);
+            if (!good) {
+                if (l64 == 0) {
+                    P.bad[(size_t)w * F + f] = 1;
+                    P.bad_list[atomicAdd(P.bad_count, 1)] = w * F + f;
+                }
+                continue;
+            }
+            if (P.H || (P.dtf && !P.dtf_fij)) {
+                mma_store_generic<T, true>(c, P, w, f, x);        // outputs in the reference layout: not the metric path
+            } else {
+                const double* X = reinterpret_cast<const double*>(gs->u.X) + (x.part ^ 1) * (25 * 32) + x.lane;      // the partner's outbox
+                const int j0 = 2 * x.t4 + x.part;
+                double* dst = P.dtf ? P.dtf + (((size_t)w * F + f) * m + x.g4) * m + j0 : nullptr;
+                const size_t row_step = (size_t)8 * m;
+#pragma unroll
+                for (int ta = 0; ta < T; ++ta) {
+                    double rsum = 0.0;
+                    const bool row_ok = (8 * ta + x.g4 < m);
+#pragma unroll
+                    for (int tb = 0; tb < T; ++tb) {
+                        const double mine = x.part ? c[ta][tb][1] : c[ta][tb][0];
+                        const double got = X[(ta * T + tb) * 32];
+                        const double v = fma(mine, mine, got * got);
+                        if (row_ok && (8 * tb + j0 < m)) {
+                            rsum += v;
+                            if (dst) dst[ta * row_step + 8 * tb] = v;
+                        }
+                    }
+                    rsum += __shfl_xor_sync(0xffffffffu, rsum, 1);
+                    rsum += __shfl_xor_sync(0xffffffffu, rsum, 2);
+                    if (x.t4 == 0 && row_ok) gs->rs[x.part][8 * ta + x.g4] += rsum;      // one writer per (warp, row): deterministic
+                }
+            }
+        }
+        // ---- per-unit row sums (fixed summation order -> deterministic)
+        __syncthreads();
+        if (P.rowpart && threadIdx.x < m) {
+            double acc = 0.0;
+            for (int q = 0; q < NG; ++q) acc += groups[q].rs[0][threadIdx.x] + groups[q].rs[1][threadIdx.x];
+            P.rowpart[((size_t)w * P.n_seg + seg) * m + threadIdx.x] = acc;
+        }
+    }
+}
+
+template <int T, int NG>
+int launch_mma_t(const K5Params& P, int sm_count, cudaStream_t stream) {
+    const size_t smem = MmaSmem<T>::total(P.p, NG);
+    if (smem > 227 * 1024) return set_error(HS_ERR_UNSUPPORTED, "transfer_mma: model order %d needs %zu B shared memory", P.p, smem);
+    cudaError_t e = cudaFuncSetAttribute(transfer_mma_kernel<T, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "transfer_mma: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
+    const int n_units = P.n_win * P.n_seg;
+    const int grid = n_units < sm_count ? n_units : sm_count;
+    transfer_mma_kernel<T, NG><<<grid, NG * 64, smem, stream>>>(P);
+    return check_launch("transfer_mma_kernel");
+}
+
+}  // namespace
+
+bool transfer_mma_fits(int p, int ng) { return ng == 6 && MmaSmem<5>::total(p, ng) <= 227 * 1024; }
+
+// optimistic (unpivoted, verified) pass on the tensor pipe; the caller follows up with the pivoted redo
+int launch_transfer_mma(const K5Params& P, int ng, cudaStream_t stream) {
+    const int sm = device_sm_count();
+    if (ng != 6) return set_error(HS_ERR_INVALID, "transfer_mma: %d groups per CTA not built", ng);
+    switch ((P.m + 7) / 8) {
+        case 1: return launch_mma_t<1, 6>(P, sm, stream);
+        case 2: return launch_mma_t<2, 6>(P, sm, stream);
+        case 3: return launch_mma_t<3, 6>(P, sm, stream);
+        case 4: return launch_mma_t<4, 6>(P, sm, stream);
+        case 5: return launch_mma_t<5, 6>(P, sm, stream);
+    }
+    return set_error(HS_ERR_UNSUPPORTED, "transfer_mma: no kernel for m=%d", P.m);
+}
+
+}  // namespace hs

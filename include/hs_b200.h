@@ -84,6 +84,10 @@ int hs_ztable_f64(const double* d_freqs, int F, int p, double fs, void* d_z, voi
  *   d_H, d_Af   (n_win, m, m, F) complex128       d_dtf, d_ffdtf (n_win, m, m, F) float64
  * d_ffdtf may alias d_dtf.  d_ws: hs_transfer_ws_bytes(n_win, m, p, F) bytes.                */
 size_t hs_transfer_ws_bytes(int n_win, int m, int p, int F);
+/* Diagnostics: byte offset inside d_ws of the int32 counter of matrices whose optimistic (unpivoted)
+ * elimination failed the a-posteriori check and were redone with pivoting by the last
+ * hs_transfer_dtf_f64 call on that workspace; (size_t)-1 when the shape takes the generic path.  */
+size_t hs_transfer_ws_flag_offset(int n_win, int m, int p, int F);
 int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double fs, int n_win, int m, int p,
                         void* d_H, void* d_Af, double* d_dtf, double* d_ffdtf, int32_t* d_status, void* d_ws,
                         void* stream);

@@ -266,7 +266,7 @@ int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double 
             return set_error(HS_ERR_CUDA, "hs_transfer_dtf_f64: memset failed");
         static int use_mma = -1;   // default: blocked elimination on the FP64 tensor pipe; HS_K5_MMA=0 -> register-tile DFMA kernel
         if (use_mma < 0) { const char* e = getenv("HS_K5_MMA"); use_mma = (e && atoi(e) == 0) ? 0 : 1; }
-        rc = (use_mma && transfer_mma_fits(p, ng)) ? launch_transfer_mma(P, ng, st) : launch_transfer_dtf(P, ng, 1, st);
+        rc = (use_mma && transfer_mma_fits(p, ng, sl)) ? launch_transfer_mma(P, ng, st) : launch_transfer_dtf(P, ng, 1, st);
         if (rc) return rc;
         rc = launch_transfer_dtf(P, ng, 2, st);      // returns immediately on the device when nothing was flagged
     }

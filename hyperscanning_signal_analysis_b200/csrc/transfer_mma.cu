@@ -214,7 +214,7 @@ __device__ __forceinline__ void mma_gauss_jordan(double (&c)[T][T][2], const int
 //      matrix, and both warps run the same code (the part only selects operands).
 template <int T>
 __device__ __forceinline__ void mma_assemble(double (&c)[T][T][2], const double* __restrict__ coef, const double2* __restrict__ zf,
-                                             const int F, const int p, const int n_planes, const MmaCtx& x) {
+                                             const int n_planes, const MmaCtx& x) {
     double vr[T][T], vi[T][T];
 #pragma unroll
     for (int ta = 0; ta < T; ++ta)
@@ -222,8 +222,7 @@ __device__ __forceinline__ void mma_assemble(double (&c)[T][T][2], const double*
         for (int tb = 0; tb < T; ++tb) vr[ta][tb] = vi[ta][tb] = 0.0;
     const double* cbase = coef + x.g4 * kRowD + 4 * x.t4 + 2 * x.part;
     for (int kp = 0; kp < n_planes; ++kp) {
-        const double2 z0 = __ldg(&zf[(size_t)(2 * kp) * F]);
-        const double2 z1 = (2 * kp + 1 < p) ? __ldg(&zf[(size_t)(2 * kp + 1) * F]) : make_double2(0.0, 0.0);
+        const double2 z0 = zf[2 * kp], z1 = zf[2 * kp + 1];       // shared memory, zero padded to an even number of lags
         const double* cp = cbase + kp * kPlaneD;
 #pragma unroll
         for (int ta = 0; ta < T; ++ta) {
@@ -307,7 +306,10 @@ struct MmaSmem {
     static __host__ __device__ int planes(int p) { return (p + 1) / 2; }
     static __host__ __device__ size_t coef_bytes(int p) { return (size_t)planes(p) * kPlaneD * sizeof(double); }
     static __host__ __device__ size_t probe_bytes(int p) { return (size_t)kMP * p * sizeof(double2); }
-    static __host__ __device__ size_t total(int p, int ng) { return coef_bytes(p) + probe_bytes(p) + (size_t)ng * sizeof(MmaGroupSmem) + 64; }
+    static __host__ __device__ size_t z_bytes(int p, int seg_len) { return (size_t)seg_len * 2 * planes(p) * sizeof(double2); }    // z of the unit's bins
+    static __host__ __device__ size_t total(int p, int ng, int seg_len) {
+        return coef_bytes(p) + probe_bytes(p) + z_bytes(p, seg_len) + (size_t)ng * sizeof(MmaGroupSmem) + 64;
+    }
 };
 
 template <int T, int NG>
@@ -316,7 +318,8 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
     const int m = P.m, p = P.p, F = P.F;
     double* coef = reinterpret_cast<double*>(smem_raw);
     double2* probe = reinterpret_cast<double2*>(smem_raw + MmaSmem<T>::coef_bytes(p));
-    MmaGroupSmem* groups = reinterpret_cast<MmaGroupSmem*>(smem_raw + MmaSmem<T>::coef_bytes(p) + MmaSmem<T>::probe_bytes(p));
+    double2* zs = reinterpret_cast<double2*>(smem_raw + MmaSmem<T>::coef_bytes(p) + MmaSmem<T>::probe_bytes(p));      // [bin of the unit][2 * n_planes]
+    MmaGroupSmem* groups = reinterpret_cast<MmaGroupSmem*>(smem_raw + MmaSmem<T>::coef_bytes(p) + MmaSmem<T>::probe_bytes(p) + MmaSmem<T>::z_bytes(p, P.seg_len));
     const int warp = threadIdx.x >> 5;
     MmaCtx x;
     x.lane = threadIdx.x & 31;
@@ -348,6 +351,10 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
                 }
             }
             for (int e = l64; e < 2 * kMP; e += 64) (&gs->rs[0][0])[e] = 0.0;
+            for (int e = threadIdx.x; e < (f_end - f_begin) * 2 * n_planes; e += NG * 64) {
+                const int fi = e / (2 * n_planes), k = e - fi * (2 * n_planes);
+                zs[e] = (k < p) ? P.z[(size_t)k * F + f_begin + fi] : make_double2(0.0, 0.0);
+            }
         }
         __syncthreads();
         // probe[i][k] = sum_j A_k[i][j] u_j : the window-dependent part of v = A(f) u = u - sum_k z_k(f) probe[.][k]
@@ -371,7 +378,7 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
             const int vi = min(l64, kMP - 1);
             double2 vacc = (l64 < m) ? probe_u2(l64) : make_double2(0.0, 0.0);
             for (int k = 0; k < p; ++k) {
-                const double2 zz = __ldg(&P.z[(size_t)k * F + f]);
+                const double2 zz = zs[(f - f_begin) * 2 * n_planes + k];
                 const double2 q0 = probe[vi * p + k];
                 vacc.x = fma(-q0.x, zz.x, fma(q0.y, zz.y, vacc.x));
                 vacc.y = fma(-q0.x, zz.y, fma(-q0.y, zz.x, vacc.y));
@@ -380,7 +387,7 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
             if (l64 < kMP) gs->vfull[l64] = vacc;
             if (l64 == 0) gs->flag = 0;
             // ---- A(f) = I - sum_k A_k z_k(f)
-            mma_assemble<T>(c, coef, P.z + f, F, p, n_planes, x);
+            mma_assemble<T>(c, coef, zs + (f - f_begin) * 2 * n_planes, n_planes, x);
             if (P.Af) mma_store_generic<T, false>(c, P, w, f, x);
             // ---- blocked Gauss-Jordan on the tensor pipe
             mma_gauss_jordan<T>(c, m, x);
@@ -475,7 +482,7 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
 
 template <int T, int NG>
 int launch_mma_t(const K5Params& P, int sm_count, cudaStream_t stream) {
-    const size_t smem = MmaSmem<T>::total(P.p, NG);
+    const size_t smem = MmaSmem<T>::total(P.p, NG, P.seg_len);
     if (smem > 227 * 1024) return set_error(HS_ERR_UNSUPPORTED, "transfer_mma: model order %d needs %zu B shared memory", P.p, smem);
     cudaError_t e = cudaFuncSetAttribute(transfer_mma_kernel<T, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "transfer_mma: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
@@ -487,7 +494,7 @@ int launch_mma_t(const K5Params& P, int sm_count, cudaStream_t stream) {
 
 }  // namespace
 
-bool transfer_mma_fits(int p, int ng) { return ng == 6 && MmaSmem<5>::total(p, ng) <= 227 * 1024; }
+bool transfer_mma_fits(int p, int ng, int seg_len) { return ng == 6 && MmaSmem<5>::total(p, ng, seg_len) <= 227 * 1024; }
 
 // optimistic (unpivoted, verified) pass on the tensor pipe; the caller follows up with the pivoted redo
 int launch_transfer_mma(const K5Params& P, int ng, cudaStream_t stream) {

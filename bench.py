@@ -243,8 +243,11 @@ def run_b200(args):
                                                               status.data_ptr(), tr_ws.data_ptr(), sp),
     }
     stage_ms = {}
+    k5_kernel_ms = []
+    import ctypes as C
     for name, fn in stages.items():
         ts = []
+        lib.hs_timing_enable(1 if name == "transfer+normalise" else 0)
         for i in range(3 + max(3, args.steps)):
             flush.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -254,25 +257,39 @@ def run_b200(args):
             torch.cuda.synchronize()
             if i >= 3:
                 ts.append(a.elapsed_time(b))
+                if name == "transfer+normalise":
+                    kms = C.c_double(0.0)
+                    _lib.check(lib.hs_timing_last_k5_ms(C.byref(kms)), "hs_timing_last_k5_ms")
+                    k5_kernel_ms.append(kms.value)
         stage_ms[name] = float(np.mean(ts))
-    import ctypes as C
+    lib.hs_timing_enable(0)
+    # the dominant kernel alone (CUDA events recorded by the library around its launch, same stream)
+    k5_ms = float(np.mean(k5_kernel_ms))
+    stage_ms["transfer_kernel"] = k5_ms
+    off = lib.hs_transfer_ws_flag_offset(n_win, M, P, F)
+    flagged = int(tr_ws[off:off + 4].view(torch.int32).item())
     tf = C.c_double(0.0)
     _lib.check(lib.hs_measure_dfma_tflops(C.byref(tf), flush.data_ptr(), 5), "hs_measure_dfma_tflops")
     dfma_peak = tf.value
-    k5_tflops = fl["transfer"] * n_win / (stage_ms["transfer"] * 1e-3) * 1e-12
+    k5_tflops = fl["transfer"] * n_win / (k5_ms * 1e-3) * 1e-12
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    roofline = {"kernel": "transfer_dtf_kernel (A(f) assembly + complex 38x38 inverse + |H|^2, 599*256 matrices per launch)",
+    roofline = {"kernel": "transfer_mma_kernel: A(f) assembly + complex 38x38 block Gauss-Jordan on the FP64 tensor pipe (DMMA m8n8k4) + |H|^2, "
+                          "599*256 matrices per launch",
                 "bound": "fp64", "achieved": k5_tflops, "peak": dfma_peak, "unit": "TFLOP/s", "frac": k5_tflops / dfma_peak if dfma_peak else None,
-                "peak_source": "hs_measure_dfma_tflops: register-only DFMA loop on all SMs, measured in this run "
-                               "(MEASURED_PEAKS.json has no FP64 figure; its hbm_gbs is %s)" % peaks.get("hbm_gbs"),
-                "flops_per_launch": fl["transfer"] * n_win, "ms_per_launch": stage_ms["transfer"], "traffic": None,
-                "hbm_write_gbs": n_win * M * M * F * 8 / (stage_ms["transfer"] * 1e-3) * 1e-9,
+                "peak_source": "hs_measure_dfma_tflops: register-only DFMA loop on all SMs, measured in this run; DMMA m8n8k4 peaks at the same "
+                               "rate (tools/fp64_peak.cu). MEASURED_PEAKS.json has no FP64 figure (its hbm_gbs is %s)" % peaks.get("hbm_gbs"),
+                "flops_per_launch": fl["transfer"] * n_win, "ms_per_launch": k5_ms, "traffic": None,
+                "algorithmic_flops_per_matrix": "4*p*m^2 + 8*m^3 (SURVEY 8d: assembly + complex LU/inverse as the reference computes it)",
+                "matrices_redone_with_pivoting": flagged,
                 "stages_ms": stage_ms,
-                "stages_tflops": {k: fl[k] * n_win / (stage_ms[k] * 1e-3) * 1e-12 for k in ("lagcov", "yule_walker", "transfer")},
+                "stages_tflops": {"lagcov": fl["lagcov"] * n_win / (stage_ms["lagcov"] * 1e-3) * 1e-12,
+                                  "yule_walker": fl["yule_walker"] * n_win / (stage_ms["yule_walker"] * 1e-3) * 1e-12,
+                                  "transfer_kernel": k5_tflops},
+                "finalize_hbm_gbs": 2 * n_win * M * M * F * 8 / (max(stage_ms["transfer+normalise"] - k5_ms, 1e-6) * 1e-3) * 1e-9,
                 "step_tflops": fl["total"] * n_win * args.steps * world / (total_ms * 1e-3) * 1e-12}
 
     # ---------------- e2e through the host-buffer API (pinned NumPy in, pinned NumPy out)

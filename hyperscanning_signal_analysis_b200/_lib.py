@@ -26,6 +26,8 @@ SIGNATURES = {
     "hs_last_error": (C.c_char_p, []),
     "hs_version": (c_int, []),
     "hs_launch_count": (C.c_longlong, []),
+    "hs_timing_enable": (None, [c_int]),
+    "hs_timing_last_k5_ms": (c_int, [C.POINTER(C.c_double)]),
     "hs_measure_dfma_tflops": (c_int, [C.POINTER(C.c_double), c_dp, c_int]),
     "hs_lagcov_f64": (c_int, [c_dp, c_dp, c_i64, c_int, c_int, c_int, c_int, c_int, c_dp, c_dp]),
     "hs_yw_assemble_f64": (c_int, [c_dp, c_int, c_int, c_int, c_dp, c_dp, c_dp]),

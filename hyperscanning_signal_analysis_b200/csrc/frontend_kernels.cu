@@ -18,6 +18,7 @@
 // Forward and backward sweeps use the same three kernels (the backward sweep walks the index backwards).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -180,19 +181,199 @@ __global__ void __launch_bounds__(128) iir_apply_kernel(const IirPass P, const I
     }
 }
 
-// per-signal mean (fixed pairwise-ish order: 256 strided partials per signal, then a tree)
-__global__ void __launch_bounds__(256) mean_kernel(const double* x, long long n, long long sig_stride, long long t_stride, double* mean) {
+// ------------------------------------------------------------------ K1, tiled path (state dimension <= 2, unit time stride)
+// The thread-per-chunk kernels above stream every chunk through its own thread, i.e. with 4 KB between the addresses of
+// neighbouring lanes.  For the biquads of the loader (notch / low-pass / high-pass, dataloader.py:687-708) the sweep is
+// re-tiled so that global memory only sees coalesced traffic:
+//   * a CTA owns a TILE of 8192 consecutive sweep positions, staged in shared memory TRANSPOSED (sample i of thread t at
+//     [i][t], row stride 257) by coalesced loads; thread t then walks "its" 32 samples conflict-free;
+//   * tile_local : zero-state response of every 32-sample piece, folded into the tile's zero-state end state
+//                  sum_t P^(255-t) z_t  with the table P^j = M^(32 j)  (fixed-order block reduction);
+//   * the existing one-warp-per-signal carry kernel turns the tile end states into tile start states (powers of M^8192);
+//   * tile_apply : stages the tile again, repeats the zero-state pieces, scans them inside the CTA (warp scan with
+//                  P^(2^k), then the 8 warp totals), adds P^t s_in, re-runs the 32 samples from the true state, and writes
+//                  the tile back coalesced.
+// Per sweep: 2 coalesced reads + 1 coalesced write of the signal (the thread-per-chunk path does the same amount of
+// traffic, uncoalesced).
+constexpr int kTileThreads = 256;
+constexpr int kTilePer = 32;
+constexpr int kTile = kTileThreads * kTilePer;      // 8192 sweep positions per CTA
+constexpr int kTileLd = kTileThreads + 1;
+constexpr int kPpowEntries = kTileThreads + 1;      // P^0 .. P^256, 4 doubles each (row-major 2 x 2, zero padded for D = 1)
+
+template <int D>
+__device__ __forceinline__ void mv2(const double* __restrict__ Pm, const double (&v)[D], double (&out)[D]) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        double a = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) a = fma(Pm[i * 2 + j], v[j], a);
+        out[i] = a;
+    }
+}
+
+template <int D>
+__device__ __forceinline__ void tile_stage_and_local(const IirPass& P, const IirCoef& c, double* sm, const int s, const long long tile,
+                                                     double (&z)[D]) {
+    const double* base = P.in + (long long)s * P.in_sig_stride;
+    const double dc = P.mean ? P.mean[s] : 0.0;
+    const long long u0 = tile * kTile;
+    // interior tile of a contiguous source: branch-free coalesced loads, 16 in flight per thread
+    const bool interior = P.in_t_stride == 1 && (P.forward ? (u0 >= P.e && u0 + kTile <= P.e + P.n_in) : (u0 + kTile <= P.L));
+    const double* src = P.forward ? base + (u0 - P.e) : base + (P.L - u0 - kTile);      // forward: x[u - e]; backward: f[L-1-u], walked downwards
+    if (interior) {
+#pragma unroll 1
+        for (int it = 0; it < kTilePer; it += 16) {
+            double v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = src[(it + k) * kTileThreads + threadIdx.x];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int j = (it + k) * kTileThreads + threadIdx.x;               // offset inside the staged span
+                const int i0 = P.forward ? j : kTile - 1 - j;
+                sm[(i0 & (kTilePer - 1)) * kTileLd + (i0 >> 5)] = v[k] - dc;
+            }
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < kTile; idx += kTileThreads) {
+            const long long u = u0 + idx;
+            sm[(idx & (kTilePer - 1)) * kTileLd + (idx >> 5)] = (u < P.L) ? sweep_read(P, base, dc, u) : 0.0;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < D; ++k) z[k] = 0.0;
+#pragma unroll 8
+    for (int i = 0; i < kTilePer; ++i) df2t_step<D>(c, z, sm[i * kTileLd + threadIdx.x]);
+}
+
+template <int D>
+__global__ void __launch_bounds__(kTileThreads) iir_tile_local_kernel(const IirPass P, const IirCoef c, const double* __restrict__ ppow) {
+    extern __shared__ double tile_sm[];
+    __shared__ double red[kTileThreads / 32][2];
+    const int s = blockIdx.y;
+    const long long tile = blockIdx.x;
+    double z[D];
+    tile_stage_and_local<D>(P, c, tile_sm, s, tile, z);
+    double w[D];
+    mv2<D>(ppow + (size_t)(kTileThreads - 1 - threadIdx.x) * 4, z, w);
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) w[k] += __shfl_xor_sync(0xffffffffu, w[k], off);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = w[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < D) {
+        double acc = 0.0;
+        for (int q = 0; q < kTileThreads / 32; ++q) acc += red[q][threadIdx.x];
+        P.states[((long long)s * P.n_chunks + tile) * D + threadIdx.x] = acc;
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kTileThreads) iir_tile_apply_kernel(const IirPass P, const IirCoef c, const double* __restrict__ ppow) {
+    extern __shared__ double tile_sm[];
+    __shared__ double wtot[kTileThreads / 32][2];
+    const int s = blockIdx.y;
+    const long long tile = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double z[D];
+    tile_stage_and_local<D>(P, c, tile_sm, s, tile, z);
+    // inclusive scan of the zero-state pieces inside the warp:  v_l = sum_{l' <= l} P^(l-l') z_l'
+    double v[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) v[k] = z[k];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        double o[D], t[D];
+#pragma unroll
+        for (int q = 0; q < D; ++q) o[q] = __shfl_up_sync(0xffffffffu, v[q], 1 << k);
+        mv2<D>(ppow + (size_t)(1 << k) * 4, o, t);
+        if (lane >= (1 << k)) {
+#pragma unroll
+            for (int q = 0; q < D; ++q) v[q] += t[q];
+        }
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int q = 0; q < D; ++q) wtot[warp][q] = v[q];
+    }
+    __syncthreads();
+    // state contributed by the warps before this one
+    double W[D];
+#pragma unroll
+    for (int q = 0; q < D; ++q) W[q] = 0.0;
+    for (int j = 0; j < warp; ++j) {
+        double t[D];
+        mv2<D>(ppow + (size_t)32 * 4, W, t);
+#pragma unroll
+        for (int q = 0; q < D; ++q) W[q] = t[q] + wtot[j][q];
+    }
+    // true start state of this thread's piece: P^t s_in + (pieces before it)
+    double sin_[D], st[D], e[D];
+#pragma unroll
+    for (int q = 0; q < D; ++q) sin_[q] = P.states[((long long)s * P.n_chunks + tile) * D + q];
+    mv2<D>(ppow + (size_t)threadIdx.x * 4, sin_, st);
+    mv2<D>(ppow + (size_t)lane * 4, W, e);
+#pragma unroll
+    for (int q = 0; q < D; ++q) {
+        const double prev = __shfl_up_sync(0xffffffffu, v[q], 1);
+        st[q] += e[q] + (lane ? prev : 0.0);
+    }
+#pragma unroll 8
+    for (int i = 0; i < kTilePer; ++i) {
+        double* slot = tile_sm + i * kTileLd + threadIdx.x;
+        *slot = df2t_step<D>(c, st, *slot);
+    }
+    __syncthreads();
+    double* ob = P.out + (long long)s * P.out_sig_stride;
+    const long long u0 = tile * kTile;
+    const long long n = P.L - 2 * (long long)P.e;
+    for (int idx = threadIdx.x; idx < kTile; idx += kTileThreads) {
+        const long long u = u0 + idx;
+        if (u >= P.L) break;
+        const double y = tile_sm[(idx & (kTilePer - 1)) * kTileLd + (idx >> 5)];
+        if (P.forward) {
+            ob[u] = y;
+        } else {
+            const long long t = P.L - 1 - u - P.e;
+            if (t >= 0 && t < n) ob[t] = y;
+        }
+    }
+}
+
+// per-signal mean in two deterministic stages: kMeanParts CTAs per signal reduce contiguous slices (fixed tree order),
+// one more CTA per signal adds the partials in index order.
+constexpr int kMeanParts = 64;
+__global__ void __launch_bounds__(256) mean_partial_kernel(const double* __restrict__ x, long long n, long long sig_stride, long long t_stride,
+                                                           double* __restrict__ partial) {
     __shared__ double sh[256];
-    const double* base = x + (long long)blockIdx.x * sig_stride;
-    double acc = 0.0;
-    for (long long t = threadIdx.x; t < n; t += 256) acc += base[t * t_stride];
-    sh[threadIdx.x] = acc;
+    const double* base = x + (long long)blockIdx.y * sig_stride;
+    const long long per = (n + kMeanParts - 1) / kMeanParts;
+    const long long t0 = (long long)blockIdx.x * per, t1 = min(n, t0 + per);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    long long t = t0 + threadIdx.x;
+    for (; t + 3 * 256 < t1; t += 4 * 256) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] += base[(t + k * 256) * t_stride];
+    }
+    for (; t < t1; t += 256) acc[0] += base[t * t_stride];
+    sh[threadIdx.x] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
     __syncthreads();
     for (int off = 128; off > 0; off >>= 1) {
         if (threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
         __syncthreads();
     }
-    if (threadIdx.x == 0) mean[blockIdx.x] = sh[0] / (double)n;
+    if (threadIdx.x == 0) partial[(long long)blockIdx.y * kMeanParts + blockIdx.x] = sh[0];
+}
+
+__global__ void mean_finish_kernel(const double* __restrict__ partial, long long n, int n_sig, double* __restrict__ mean) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_sig) return;
+    double acc = 0.0;
+    for (int k = 0; k < kMeanParts; ++k) acc += partial[(long long)s * kMeanParts + k];
+    mean[s] = acc / (double)n;
 }
 
 __global__ void sub_mean_kernel(double* x, long long n, long long sig_stride, long long t_stride, const double* mean, int n_sig) {
@@ -286,6 +467,63 @@ static int prepare_filter(const double* b, const double* a, int ntaps, IirCoef* 
     return HS_OK;
 }
 
+// Tables of the tiled path: ppow[j] = M^(32 j), j = 0..256, by running the homogeneous recurrence in long double;
+// ct->pw[k] = (M^8192)^(2^k) by squaring M^8192 in long double (for a stable biquad these are tiny numbers).
+static void prepare_tile_tables(const IirCoef& c, std::vector<double>& ppow, IirCoef* ct) {
+    const int d = c.d;
+    ppow.assign((size_t)kPpowEntries * 4, 0.0);
+    long double zst[2][2] = {{1.0L, 0.0L}, {0.0L, 1.0L}};        // zst[j] = image of e_j
+    for (int j = 0; j <= kTileThreads; ++j) {
+        for (int i = 0; i < d; ++i)
+            for (int q = 0; q < d; ++q) ppow[(size_t)j * 4 + i * 2 + q] = (double)zst[q][i];
+        if (j == kTileThreads) break;
+        for (int step = 0; step < kTilePer; ++step) {
+            for (int q = 0; q < d; ++q) {
+                const long double y = zst[q][0];
+                for (int k = 0; k < d - 1; ++k) zst[q][k] = zst[q][k + 1] - (long double)c.a[k + 1] * y;
+                zst[q][d - 1] = -(long double)c.a[d] * y;
+            }
+        }
+    }
+    *ct = c;
+    long double Q[2][2] = {{0, 0}, {0, 0}};
+    for (int i = 0; i < d; ++i)
+        for (int q = 0; q < d; ++q) Q[i][q] = zst[q][i];
+    for (int kpow = 0; kpow < 6; ++kpow) {
+        for (int i = 0; i < d; ++i)
+            for (int q = 0; q < d; ++q) ct->pw[kpow][i * d + q] = (double)Q[i][q];
+        long double R[2][2] = {{0, 0}, {0, 0}};
+        for (int i = 0; i < d; ++i)
+            for (int q = 0; q < d; ++q)
+                for (int r = 0; r < d; ++r) R[i][q] += Q[i][r] * Q[r][q];
+        for (int i = 0; i < d; ++i)
+            for (int q = 0; q < d; ++q) Q[i][q] = R[i][q];
+    }
+}
+
+template <int D>
+static int run_sweep_tiled(IirPass P, const IirCoef& c, const IirCoef& ct, const double* d_ppow, cudaStream_t st) {
+    const long long n_tiles = (P.L + kTile - 1) / kTile;
+    P.n_chunks = n_tiles;
+    const size_t smem = (size_t)kTilePer * kTileLd * sizeof(double);
+    static bool attr_done[3] = {false, false, false};
+    if (!attr_done[D]) {
+        if (cudaFuncSetAttribute(iir_tile_local_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaFuncSetAttribute(iir_tile_apply_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return set_error(HS_ERR_CUDA, "filtfilt: cannot reserve %zu B shared memory", smem);
+        attr_done[D] = true;
+    }
+    dim3 grid((unsigned)n_tiles, (unsigned)P.n_sig);
+    iir_tile_local_kernel<D><<<grid, kTileThreads, smem, st>>>(P, c, d_ppow);
+    int rc = check_launch("iir_tile_local_kernel");
+    if (rc) return rc;
+    iir_carry_kernel<D><<<(P.n_sig + 3) / 4, 128, 0, st>>>(P, ct);
+    rc = check_launch("iir_carry_kernel");
+    if (rc) return rc;
+    iir_tile_apply_kernel<D><<<grid, kTileThreads, smem, st>>>(P, c, d_ppow);
+    return check_launch("iir_tile_apply_kernel");
+}
+
 template <int D>
 static int run_sweep(const IirPass& P, const IirCoef& c, cudaStream_t st) {
     const long long n_thr = (long long)P.n_sig * P.n_chunks;
@@ -311,24 +549,92 @@ static int run_sweep_d(int d, const IirPass& P, const IirCoef& c, cudaStream_t s
 }
 
 // ------------------------------------------------------------------ K2
-// y[k] = sum_j b[j] x[q k + half - j], zero outside [0, n).  One thread per output sample; consecutive
-// threads read overlapping, consecutive input spans (L1-resident), taps come through the read-only path.
-__global__ void __launch_bounds__(256) fir_decimate_kernel(const double* __restrict__ x, long long n, long long sig_stride, int q,
-                                                          const double* __restrict__ b, int ntaps, double* __restrict__ y,
-                                                          long long n_out, long long y_stride) {
-    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_out) return;
+// y[k] = sum_j b[j] x[q k + half - j], zero outside [0, n)   (scipy.signal.decimate(..., ftype='fir', zero_phase=True),
+// data_structures.py:792).  HBM-bound: every input sample is read from global memory exactly once.
+// One CTA = kDecOut consecutive outputs of one signal.  The input span (q*kDecOut + ntaps - 1 samples) is staged in shared
+// memory de-interleaved into its q polyphase components, so that for a fixed tap every thread reads the same component at
+// consecutive positions.  With jj = ntaps-1-j:  y[o] = sum_r sum_u b[ntaps-1-(q u + r)] * S_r[o + u]:  a thread owns 4
+// consecutive outputs and slides a 4-register window along S_r (1 shared load per 4 FMAs).  Positions are skewed by
+// pos + (pos >> 2) so the 32 B-strided window loads of a half-warp hit distinct banks.
+constexpr int kDecThreads = 256;
+constexpr int kDecPer = 4;
+constexpr int kDecOut = kDecThreads * kDecPer;
+
+__host__ __device__ inline int dec_phase_len(int q, int ntaps) { return kDecOut + (ntaps - 1 + q - 1) / q + 1; }
+__host__ __device__ inline int dec_phase_stride(int q, int ntaps) {
+    const int pl = dec_phase_len(q, ntaps);
+    int st = pl + (pl >> 2) + 1;
+    st += (2 - (st & 15) + 16) & 15;          // = 2 (mod 16) doubles: the q components start 16 B apart modulo 128 B
+    return st;
+}
+
+template <int Q>      // Q > 0: compile-time decimation factor (divisions become shifts for powers of two); 0: runtime q
+__global__ void __launch_bounds__(kDecThreads) fir_decimate_kernel(const double* __restrict__ x, long long n, long long sig_stride, int q_rt,
+                                                                   const double* __restrict__ b, int ntaps, double* __restrict__ y,
+                                                                   long long n_out, long long y_stride) {
+    extern __shared__ double dec_smem[];
+    const int q = Q > 0 ? Q : q_rt;
+    const int pst = dec_phase_stride(q, ntaps);
+    double* S = dec_smem;                       // [q][pst]
+    double* taps = dec_smem + (size_t)q * pst;  // taps[jj] = b[ntaps-1-jj]
+    const long long k0 = (long long)blockIdx.x * kDecOut;
     const double* xs = x + (long long)blockIdx.y * sig_stride;
     const int half = (ntaps - 1) / 2;
-    const long long centre = (long long)q * k + half;       // index paired with tap 0
-    // j ranges over taps with 0 <= centre - j < n
-    long long j_lo = centre - (n - 1);
-    if (j_lo < 0) j_lo = 0;
-    long long j_hi = centre;                                  // inclusive
-    if (j_hi > ntaps - 1) j_hi = ntaps - 1;
-    double acc = 0.0;
-    for (long long j = j_lo; j <= j_hi; ++j) acc = fma(__ldg(&b[j]), xs[centre - j], acc);
-    y[(long long)blockIdx.y * y_stride + k] = acc;
+    const long long lo = (long long)q * k0 - half;            // input index of staged element 0
+    const int span = q * kDecOut + ntaps - 1;
+    if (lo >= 0 && lo + span <= n) {          // interior span: branch-free coalesced loads, 8 in flight per thread
+        const double* src = xs + lo;
+        int i = threadIdx.x;
+        for (; i + 7 * kDecThreads < span; i += 8 * kDecThreads) {
+            double v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = src[i + k * kDecThreads];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int ii = i + k * kDecThreads, r = ii % q, pos = ii / q;
+                S[(size_t)r * pst + pos + (pos >> 2)] = v[k];
+            }
+        }
+        for (; i < span; i += kDecThreads) {
+            const int r = i % q, pos = i / q;
+            S[(size_t)r * pst + pos + (pos >> 2)] = src[i];
+        }
+    } else {
+        for (int i = threadIdx.x; i < span; i += kDecThreads) {
+            const long long g = lo + i;
+            const int r = i % q, pos = i / q;
+            S[(size_t)r * pst + pos + (pos >> 2)] = (g >= 0 && g < n) ? xs[g] : 0.0;
+        }
+    }
+    for (int j = threadIdx.x; j < ntaps; j += kDecThreads) taps[j] = b[ntaps - 1 - j];
+    __syncthreads();
+    const int o0 = threadIdx.x * kDecPer;
+    double acc[kDecPer];
+#pragma unroll
+    for (int i = 0; i < kDecPer; ++i) acc[i] = 0.0;
+    for (int r = 0; r < q; ++r) {
+        const double* Sr = S + (size_t)r * pst;
+        const int nu = (ntaps - r + q - 1) / q;            // taps jj = q u + r < ntaps
+        double w[kDecPer];
+#pragma unroll
+        for (int i = 0; i < kDecPer - 1; ++i) {
+            const int pos = o0 + i;
+            w[i + 1] = Sr[pos + (pos >> 2)];
+        }
+        for (int u = 0; u < nu; ++u) {
+#pragma unroll
+            for (int i = 0; i < kDecPer - 1; ++i) w[i] = w[i + 1];
+            const int pos = o0 + kDecPer - 1 + u;
+            w[kDecPer - 1] = Sr[pos + (pos >> 2)];
+            const double t = taps[q * u + r];
+#pragma unroll
+            for (int i = 0; i < kDecPer; ++i) acc[i] = fma(t, w[i], acc[i]);
+        }
+    }
+    double* ys = y + (long long)blockIdx.y * y_stride + k0 + o0;
+#pragma unroll
+    for (int i = 0; i < kDecPer; ++i)
+        if (k0 + o0 + i < n_out) ys[i] = acc[i];
 }
 
 // =====================================================================================
@@ -533,6 +839,8 @@ static int launch_mt_psd(const double* x, int n_sig, long long n, const double* 
 
 using namespace hs;
 
+constexpr int kMaxTiledFilters = 16;
+
 extern "C" {
 
 size_t hs_filtfilt_ws_bytes(int n_sig, int64_t n) {
@@ -542,7 +850,8 @@ size_t hs_filtfilt_ws_bytes(int n_sig, int64_t n) {
     size_t b = 0;
     b += ((size_t)n_sig * L * sizeof(double) + 255) / 256 * 256;                        // forward output f
     b += ((size_t)n_sig * n_chunks * kMaxOrder * sizeof(double) + 255) / 256 * 256;     // chunk states
-    b += ((size_t)n_sig * sizeof(double) + 255) / 256 * 256;                            // means
+    b += (((size_t)n_sig + 31) / 32 * 32 + (size_t)n_sig * kMeanParts) * sizeof(double) / 256 * 256 + 256;   // means + partial sums
+    b += (size_t)kMaxTiledFilters * kPpowEntries * 4 * sizeof(double);                  // power tables of the tiled path
     return b + 256;
 }
 
@@ -563,10 +872,19 @@ int hs_iir_filtfilt_f64(double* d_x, int n_sig, int64_t n, int64_t sig_stride, i
     double* states = reinterpret_cast<double*>(ws);
     ws += ((size_t)n_sig * chunks_max * kMaxOrder * sizeof(double) + 255) / 256 * 256;
     double* mean = reinterpret_cast<double*>(ws);
+    ws += (((size_t)n_sig + 31) / 32 * 32 + (size_t)n_sig * kMeanParts) * sizeof(double) / 256 * 256 + 256;
+    double* ppow_dev = reinterpret_cast<double*>(ws);
+    static int tiled_mode = -1;      // HS_IIR_TILED=0 forces the thread-per-chunk kernels
+    if (tiled_mode < 0) { const char* ev = getenv("HS_IIR_TILED"); tiled_mode = (ev && atoi(ev) == 0) ? 0 : 1; }
+    std::vector<double> ppow_host;
 
     if (remove_dc) {
-        mean_kernel<<<n_sig, 256, 0, st>>>(d_x, n, sig_stride, t_stride, mean);
-        int rc = check_launch("mean_kernel");
+        double* mean_part = mean + (((size_t)n_sig + 31) / 32 * 32);
+        mean_partial_kernel<<<dim3(kMeanParts, n_sig), 256, 0, st>>>(d_x, n, sig_stride, t_stride, mean_part);
+        int rc = check_launch("mean_partial_kernel");
+        if (rc) return rc;
+        mean_finish_kernel<<<(n_sig + 127) / 128, 128, 0, st>>>(mean_part, n, n_sig, mean);
+        rc = check_launch("mean_finish_kernel");
         if (rc) return rc;
         if (n_filt == 0) {
             const long long tot = (long long)n * n_sig;
@@ -574,11 +892,29 @@ int hs_iir_filtfilt_f64(double* d_x, int n_sig, int64_t n, int64_t sig_stride, i
             return check_launch("sub_mean_kernel");
         }
     }
+    // host-side preparation of every filter first (coefficients, zi, power tables), ONE upload, then only launches:
+    // the device never waits for the host between sweeps
+    std::vector<IirCoef> coefs(n_filt), coefs_tile(n_filt);
+    std::vector<char> use_tiled(n_filt, 0);
+    std::vector<double> all_tables;
     for (int k = 0; k < n_filt; ++k) {
-        IirCoef c;
         // trailing zero taps do not change the filter but would change padlen: the caller passes ntaps = max(len(a), len(b))
-        int rc = prepare_filter(h_b + (size_t)k * ntaps, h_a + (size_t)k * ntaps, ntaps, &c);
+        int rc = prepare_filter(h_b + (size_t)k * ntaps, h_a + (size_t)k * ntaps, ntaps, &coefs[k]);
         if (rc) return rc;
+        const long long L = n + 2LL * coefs[k].e;
+        use_tiled[k] = tiled_mode && coefs[k].d <= 2 && t_stride == 1 && k < kMaxTiledFilters && L >= kTile;
+        if (use_tiled[k]) {
+            prepare_tile_tables(coefs[k], ppow_host, &coefs_tile[k]);
+            all_tables.resize((size_t)(k + 1) * kPpowEntries * 4, 0.0);
+            memcpy(all_tables.data() + (size_t)k * kPpowEntries * 4, ppow_host.data(), ppow_host.size() * sizeof(double));
+        }
+    }
+    if (!all_tables.empty() &&
+        cudaMemcpyAsync(ppow_dev, all_tables.data(), all_tables.size() * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess)
+        return set_error(HS_ERR_CUDA, "filtfilt: table upload failed");
+    for (int k = 0; k < n_filt; ++k) {
+        const IirCoef& c = coefs[k];
+        int rc = 0;
         const long long L = n + 2LL * c.e;
         IirPass P;
         P.n_sig = n_sig;
@@ -596,7 +932,10 @@ int hs_iir_filtfilt_f64(double* d_x, int n_sig, int64_t n, int64_t sig_stride, i
         P.out_t_stride = 1;
         P.forward = 1;
         P.mean = (remove_dc && k == 0) ? mean : nullptr;
-        rc = run_sweep_d(c.d, P, c, st);
+        const bool tiled = use_tiled[k];
+        const IirCoef& ct = coefs_tile[k];
+        double* d_ppow = ppow_dev + (size_t)k * kPpowEntries * 4;
+        rc = tiled ? (c.d == 1 ? run_sweep_tiled<1>(P, c, ct, d_ppow, st) : run_sweep_tiled<2>(P, c, ct, d_ppow, st)) : run_sweep_d(c.d, P, c, st);
         if (rc) return rc;
         // backward: f reversed -> x (middle n samples), in place
         P.in = f;
@@ -608,7 +947,7 @@ int hs_iir_filtfilt_f64(double* d_x, int n_sig, int64_t n, int64_t sig_stride, i
         P.out_t_stride = t_stride;
         P.forward = 0;
         P.mean = nullptr;
-        rc = run_sweep_d(c.d, P, c, st);
+        rc = tiled ? (c.d == 1 ? run_sweep_tiled<1>(P, c, ct, d_ppow, st) : run_sweep_tiled<2>(P, c, ct, d_ppow, st)) : run_sweep_d(c.d, P, c, st);
         if (rc) return rc;
     }
     return HS_OK;
@@ -620,9 +959,21 @@ int hs_fir_decimate_f64(const double* d_x, int n_sig, int64_t n, int64_t sig_str
     if (q < 1 || ntaps < 1 || (ntaps & 1) == 0) return set_error(HS_ERR_INVALID, "hs_fir_decimate_f64: q >= 1 and an odd tap count are required");
     if (n_sig <= 0 || n <= 0) return HS_OK;
     const long long n_out = (n + q - 1) / q;
-    dim3 grid((unsigned)((n_out + 255) / 256), n_sig);
-    fir_decimate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_x, n, sig_stride, q, d_b, ntaps, d_y, n_out, y_stride);
-    return check_launch("fir_decimate_kernel");
+    const size_t smem = ((size_t)q * dec_phase_stride(q, ntaps) + ntaps) * sizeof(double);
+    if (smem > 200 * 1024) return set_error(HS_ERR_UNSUPPORTED, "hs_fir_decimate_f64: q=%d, ntaps=%d need %zu B shared memory", q, ntaps, smem);
+    dim3 grid((unsigned)((n_out + kDecOut - 1) / kDecOut), n_sig);
+    auto launch = [&](auto kern) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "hs_fir_decimate_f64: %s", cudaGetErrorString(e));
+        kern<<<grid, kDecThreads, smem, (cudaStream_t)stream>>>(d_x, n, sig_stride, q, d_b, ntaps, d_y, n_out, y_stride);
+        return check_launch("fir_decimate_kernel");
+    };
+    switch (q) {
+        case 2: return launch(fir_decimate_kernel<2>);
+        case 4: return launch(fir_decimate_kernel<4>);
+        case 8: return launch(fir_decimate_kernel<8>);
+        default: return launch(fir_decimate_kernel<0>);
+    }
 }
 
 size_t hs_mt_psd_ws_bytes(int n_sig, int64_t n, int K) {

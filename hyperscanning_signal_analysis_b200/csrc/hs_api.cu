@@ -44,6 +44,12 @@ int device_sm_count() {
 
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
+// Optional CUDA-event bracket around the dominant kernel (the optimistic K5 pass), for bench.py's roofline:
+// events are recorded on the stream the kernel is launched on, only while hs_timing_enable(1) is in effect.
+static int g_timing = 0;
+static cudaEvent_t g_ev[2] = {nullptr, nullptr};
+static bool g_ev_valid = false;
+
 static int k5_groups() {
     static int ng = 0;
     if (ng == 0) {
@@ -91,6 +97,18 @@ extern "C" {
 const char* hs_last_error(void) { return g_err; }
 int hs_version(void) { return 100; }
 long long hs_launch_count(void) { return g_launches.load(); }
+
+void hs_timing_enable(int on) { g_timing = on ? 1 : 0; }
+
+int hs_timing_last_k5_ms(double* ms) {
+    if (!ms) return set_error(HS_ERR_INVALID, "hs_timing_last_k5_ms: null pointer");
+    if (!g_ev_valid) return set_error(HS_ERR_INVALID, "hs_timing_last_k5_ms: no timed launch yet (call hs_timing_enable(1) first)");
+    if (cudaEventSynchronize(g_ev[1]) != cudaSuccess) return set_error(HS_ERR_CUDA, "hs_timing_last_k5_ms: event synchronize failed");
+    float f = 0.f;
+    if (cudaEventElapsedTime(&f, g_ev[0], g_ev[1]) != cudaSuccess) return set_error(HS_ERR_CUDA, "hs_timing_last_k5_ms: elapsed time failed");
+    *ms = f;
+    return HS_OK;
+}
 
 int hs_measure_dfma_tflops(double* tflops, double* d_scratch, int reps) {
     if (!tflops || !d_scratch) return set_error(HS_ERR_INVALID, "hs_measure_dfma_tflops: null pointer");
@@ -266,7 +284,16 @@ int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double 
             return set_error(HS_ERR_CUDA, "hs_transfer_dtf_f64: memset failed");
         static int use_mma = -1;   // default: blocked elimination on the FP64 tensor pipe; HS_K5_MMA=0 -> register-tile DFMA kernel
         if (use_mma < 0) { const char* e = getenv("HS_K5_MMA"); use_mma = (e && atoi(e) == 0) ? 0 : 1; }
+        if (g_timing) {
+            if (!g_ev[0] && (cudaEventCreate(&g_ev[0]) != cudaSuccess || cudaEventCreate(&g_ev[1]) != cudaSuccess))
+                return set_error(HS_ERR_CUDA, "hs_transfer_dtf_f64: cannot create timing events");
+            cudaEventRecord(g_ev[0], st);
+        }
         rc = (use_mma && transfer_mma_fits(p, ng, sl)) ? launch_transfer_mma(P, ng, st) : launch_transfer_dtf(P, ng, 1, st);
+        if (g_timing) {
+            cudaEventRecord(g_ev[1], st);
+            g_ev_valid = true;
+        }
         if (rc) return rc;
         rc = launch_transfer_dtf(P, ng, 2, st);      // returns immediately on the device when nothing was flagged
     }

@@ -81,13 +81,25 @@ def decimate_taps(q):
     return firwin(20 * q + 1, 1.0 / q, window="hamming")
 
 
+_TAPS_DEV = {}      # (q, device) -> CUDA tensor of the default anti-alias taps (designed once per factor)
+
+
 def decimate_dev(x_dev, q, taps=None):
     """(n_sig, n) CUDA float64 -> (n_sig, ceil(n/q)) CUDA float64."""
     torch = _torch()
     lib = _lib.load()
     assert x_dev.is_cuda and x_dev.dtype == torch.float64 and x_dev.dim() == 2 and x_dev.is_contiguous()
     n_sig, n = x_dev.shape
-    b = torch.from_numpy(np.ascontiguousarray(decimate_taps(q) if taps is None else taps, dtype=np.float64)).cuda()
+    if taps is None:
+        key = (int(q), x_dev.device.index)
+        b = _TAPS_DEV.get(key)
+        if b is None:
+            b = torch.from_numpy(np.ascontiguousarray(decimate_taps(q), dtype=np.float64)).to(x_dev.device)
+            _TAPS_DEV[key] = b
+    elif isinstance(taps, torch.Tensor):
+        b = taps.to(x_dev.device, torch.float64).contiguous()
+    else:
+        b = torch.from_numpy(np.ascontiguousarray(taps, dtype=np.float64)).to(x_dev.device)
     n_out = -(-n // q)
     y = torch.empty((n_sig, n_out), dtype=torch.float64, device="cuda")
     if n_sig and n:

@@ -45,6 +45,12 @@ int hs_version(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 long long hs_launch_count(void);
 
+/* Measurement hook for bench.py's roofline: while enabled, hs_transfer_dtf_f64 brackets its dominant kernel (the
+ * optimistic A(f)^-1 pass, transfer_mma_kernel / transfer_dtf_kernel) with CUDA events on the caller's stream;
+ * hs_timing_last_k5_ms synchronises on the closing event and returns that launch's duration.               */
+void hs_timing_enable(int on);
+int hs_timing_last_k5_ms(double* ms);
+
 /* Roofline probe: achieved FP64 FMA throughput (TFLOP/s, best of `reps` runs of a register-only
  * DFMA loop on every SM) -- the denominator bench.py reports K3-K5 against, because the
  * driver-written MEASURED_PEAKS.json holds no FP64 figure.  d_scratch: >= 8 MiB device memory.

@@ -146,3 +146,23 @@ def test_decimate_signals_object_semantics():
         assert np.array_equal(np.isnan(y), np.isnan(ref))
         ok = ~np.isnan(ref)
         assert relerr(y[ok], ref[ok]) < TOL_SIGNAL
+
+
+@pytest.mark.parametrize("n,fs", [(8192 * 3 + 517, 1024.0), (8192, 256.0), (50000, 256.0)])
+def test_long_signals_take_the_tiled_path(n, fs):
+    """Signals longer than one 8192-sample tile run through the coalesced tiled kernels (biquads, unit time stride);
+    compare with SciPy's filtfilt cascade as dataloader.py:788-792 applies it, and with the thread-per-chunk kernels."""
+    import os
+    import torch
+    from hyperscanning_signal_analysis_b200 import frontend
+    rng = np.random.default_rng(int(n))
+    t = np.arange(n) / fs
+    x = 20.0 * rng.standard_normal((3, n)) + 5.0 * np.sin(2 * np.pi * 50.0 * t) + 30.0 + 3.0 * t[None, :] / t[-1]
+    filt = fo.design_eeg_filters(fs, 1.0, min(64.0, 0.4 * fs))
+    ref = fo.apply_filters_iir(x, filt)
+    got = frontend.filtfilt_cascade(x, list(filt[:3]), remove_dc=True)
+    assert relerr(got, ref) < TOL_SIGNAL
+    # decimation of the long result (interior and edge spans of the polyphase kernel)
+    for q in (2, 8, 5):
+        d_ref = signal.decimate(ref, q, ftype="fir", zero_phase=True, axis=1)
+        assert relerr(frontend.decimate(got, q), d_ref) < TOL_SIGNAL

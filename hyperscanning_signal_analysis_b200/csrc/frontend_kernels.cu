@@ -20,6 +20,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <mutex>
 #include <vector>
 
 #include "hs_internal.h"
@@ -570,8 +572,8 @@ __host__ __device__ inline int dec_phase_stride(int q, int ntaps) {
 
 template <int Q>      // Q > 0: compile-time decimation factor (divisions become shifts for powers of two); 0: runtime q
 __global__ void __launch_bounds__(kDecThreads) fir_decimate_kernel(const double* __restrict__ x, long long n, long long sig_stride, int q_rt,
-                                                                   const double* __restrict__ b, int ntaps, double* __restrict__ y,
-                                                                   long long n_out, long long y_stride) {
+                                                                   long long off, const double* __restrict__ b, int ntaps,
+                                                                   double* __restrict__ y, long long n_out, long long y_stride) {
     extern __shared__ double dec_smem[];
     const int q = Q > 0 ? Q : q_rt;
     const int pst = dec_phase_stride(q, ntaps);
@@ -579,8 +581,7 @@ __global__ void __launch_bounds__(kDecThreads) fir_decimate_kernel(const double*
     double* taps = dec_smem + (size_t)q * pst;  // taps[jj] = b[ntaps-1-jj]
     const long long k0 = (long long)blockIdx.x * kDecOut;
     const double* xs = x + (long long)blockIdx.y * sig_stride;
-    const int half = (ntaps - 1) / 2;
-    const long long lo = (long long)q * k0 - half;            // input index of staged element 0
+    const long long lo = (long long)q * k0 + off - (ntaps - 1);      // input index of staged element 0 (y[k] = sum_j b[j] x[q k + off - j])
     const int span = q * kDecOut + ntaps - 1;
     if (lo >= 0 && lo + span <= n) {          // interior span: branch-free coalesced loads, 8 in flight per thread
         const double* src = xs + lo;
@@ -841,6 +842,14 @@ using namespace hs;
 
 constexpr int kMaxTiledFilters = 16;
 
+struct PreparedFilter {
+    int ntaps;
+    std::vector<double> b, a, ppow;
+    hs::IirCoef c, ct;
+};
+static std::mutex g_prep_mutex;
+static std::deque<PreparedFilter> g_prep_cache;
+
 extern "C" {
 
 size_t hs_filtfilt_ws_bytes(int n_sig, int64_t n) {
@@ -855,14 +864,17 @@ size_t hs_filtfilt_ws_bytes(int n_sig, int64_t n) {
     return b + 256;
 }
 
-int hs_iir_filtfilt_f64(double* d_x, int n_sig, int64_t n, int64_t sig_stride, int64_t t_stride, const double* h_b,
-                        const double* h_a, int n_filt, int ntaps, int remove_dc, void* d_ws, void* stream) {
+// causal_out == nullptr: zero-phase cascade in place (filtfilt).  Otherwise ONE causal filter (scipy.signal.lfilter, zero
+// initial state): a single forward sweep without extension, x -> causal_out (row stride causal_stride).
+static int iir_run(double* d_x, int n_sig, int64_t n, int64_t sig_stride, int64_t t_stride, const double* h_b, const double* h_a,
+                   int n_filt, int ntaps, int remove_dc, void* d_ws, void* stream, double* causal_out, int64_t causal_stride) {
+    const bool causal = causal_out != nullptr;
     if (!d_x || !d_ws) return set_error(HS_ERR_INVALID, "hs_iir_filtfilt_f64: null pointer");
     if (n_sig < 0 || n < 0 || n_filt < 0 || (n_filt > 0 && (!h_b || !h_a || ntaps < 2)))
         return set_error(HS_ERR_INVALID, "hs_iir_filtfilt_f64: bad arguments");
     if (n_sig == 0 || n == 0) return HS_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (n_filt > 0 && n <= 3 * (int64_t)ntaps)
+    if (!causal && n_filt > 0 && n <= 3 * (int64_t)ntaps)
         return set_error(HS_ERR_INVALID, "The length of the input vector x must be greater than padlen, which is %d.", 3 * ntaps);
     unsigned char* ws = reinterpret_cast<unsigned char*>(d_ws);
     const long long Lmax = n + 2 * 3 * (kMaxOrder + 1);
@@ -899,12 +911,45 @@ int hs_iir_filtfilt_f64(double* d_x, int n_sig, int64_t n, int64_t sig_stride, i
     std::vector<double> all_tables;
     for (int k = 0; k < n_filt; ++k) {
         // trailing zero taps do not change the filter but would change padlen: the caller passes ntaps = max(len(a), len(b))
-        int rc = prepare_filter(h_b + (size_t)k * ntaps, h_a + (size_t)k * ntaps, ntaps, &coefs[k]);
-        if (rc) return rc;
+        const double* bk = h_b + (size_t)k * ntaps;
+        const double* ak = h_a + (size_t)k * ntaps;
+        // the tables depend on the coefficients only: keep the last few designs (a loader applies the same three filters
+        // to every file)
+        const PreparedFilter* hit = nullptr;
+        {
+            std::lock_guard<std::mutex> lock(g_prep_mutex);
+            for (const PreparedFilter& e : g_prep_cache)
+                if (e.ntaps == ntaps && memcmp(e.b.data(), bk, ntaps * sizeof(double)) == 0 && memcmp(e.a.data(), ak, ntaps * sizeof(double)) == 0) {
+                    hit = &e;
+                    coefs[k] = e.c;
+                    coefs_tile[k] = e.ct;
+                    ppow_host = e.ppow;
+                    break;
+                }
+        }
+        if (!hit) {
+            int rc = prepare_filter(bk, ak, ntaps, &coefs[k]);
+            if (rc) return rc;
+            if (coefs[k].d <= 2) prepare_tile_tables(coefs[k], ppow_host, &coefs_tile[k]);
+            else ppow_host.clear();
+            PreparedFilter e;
+            e.ntaps = ntaps;
+            e.b.assign(bk, bk + ntaps);
+            e.a.assign(ak, ak + ntaps);
+            e.c = coefs[k];
+            e.ct = coefs_tile[k];
+            e.ppow = ppow_host;
+            std::lock_guard<std::mutex> lock(g_prep_mutex);
+            if (g_prep_cache.size() >= 32) g_prep_cache.erase(g_prep_cache.begin());
+            g_prep_cache.push_back(e);
+        }
+        if (causal) {       // lfilter: no extension, zero initial state
+            coefs[k].e = coefs_tile[k].e = 0;
+            for (int q = 0; q < kMaxOrder; ++q) coefs[k].zi[q] = coefs_tile[k].zi[q] = 0.0;
+        }
         const long long L = n + 2LL * coefs[k].e;
         use_tiled[k] = tiled_mode && coefs[k].d <= 2 && t_stride == 1 && k < kMaxTiledFilters && L >= kTile;
         if (use_tiled[k]) {
-            prepare_tile_tables(coefs[k], ppow_host, &coefs_tile[k]);
             all_tables.resize((size_t)(k + 1) * kPpowEntries * 4, 0.0);
             memcpy(all_tables.data() + (size_t)k * kPpowEntries * 4, ppow_host.data(), ppow_host.size() * sizeof(double));
         }
@@ -927,8 +972,8 @@ int hs_iir_filtfilt_f64(double* d_x, int n_sig, int64_t n, int64_t sig_stride, i
         P.in_sig_stride = sig_stride;
         P.in_t_stride = t_stride;
         P.n_in = n;
-        P.out = f;
-        P.out_sig_stride = L;
+        P.out = causal ? causal_out : f;
+        P.out_sig_stride = causal ? causal_stride : L;
         P.out_t_stride = 1;
         P.forward = 1;
         P.mean = (remove_dc && k == 0) ? mean : nullptr;
@@ -937,6 +982,7 @@ int hs_iir_filtfilt_f64(double* d_x, int n_sig, int64_t n, int64_t sig_stride, i
         double* d_ppow = ppow_dev + (size_t)k * kPpowEntries * 4;
         rc = tiled ? (c.d == 1 ? run_sweep_tiled<1>(P, c, ct, d_ppow, st) : run_sweep_tiled<2>(P, c, ct, d_ppow, st)) : run_sweep_d(c.d, P, c, st);
         if (rc) return rc;
+        if (causal) continue;
         // backward: f reversed -> x (middle n samples), in place
         P.in = f;
         P.in_sig_stride = L;
@@ -953,27 +999,45 @@ int hs_iir_filtfilt_f64(double* d_x, int n_sig, int64_t n, int64_t sig_stride, i
     return HS_OK;
 }
 
-int hs_fir_decimate_f64(const double* d_x, int n_sig, int64_t n, int64_t sig_stride, int q, const double* d_b, int ntaps,
-                        double* d_y, int64_t y_stride, void* stream) {
-    if (!d_x || !d_b || !d_y) return set_error(HS_ERR_INVALID, "hs_fir_decimate_f64: null pointer");
-    if (q < 1 || ntaps < 1 || (ntaps & 1) == 0) return set_error(HS_ERR_INVALID, "hs_fir_decimate_f64: q >= 1 and an odd tap count are required");
-    if (n_sig <= 0 || n <= 0) return HS_OK;
-    const long long n_out = (n + q - 1) / q;
+int hs_iir_filtfilt_f64(double* d_x, int n_sig, int64_t n, int64_t sig_stride, int64_t t_stride, const double* h_b,
+                        const double* h_a, int n_filt, int ntaps, int remove_dc, void* d_ws, void* stream) {
+    return iir_run(d_x, n_sig, n, sig_stride, t_stride, h_b, h_a, n_filt, ntaps, remove_dc, d_ws, stream, nullptr, 0);
+}
+
+int hs_iir_lfilter_f64(const double* d_x, int n_sig, int64_t n, int64_t sig_stride, const double* h_b, const double* h_a, int ntaps,
+                       int remove_dc, double* d_y, int64_t y_stride, void* d_ws, void* stream) {
+    if (!d_y || d_y == d_x) return set_error(HS_ERR_INVALID, "hs_iir_lfilter_f64: the output must be a separate buffer");
+    return iir_run(const_cast<double*>(d_x), n_sig, n, sig_stride, 1, h_b, h_a, 1, ntaps, remove_dc, d_ws, stream, d_y, y_stride);
+}
+
+int hs_fir_filter_f64(const double* d_x, int n_sig, int64_t n, int64_t sig_stride, int q, int64_t off, const double* d_b, int ntaps,
+                      double* d_y, int64_t n_out, int64_t y_stride, void* stream) {
+    if (!d_x || !d_b || !d_y) return set_error(HS_ERR_INVALID, "hs_fir_filter_f64: null pointer");
+    if (q < 1 || ntaps < 1) return set_error(HS_ERR_INVALID, "hs_fir_filter_f64: q >= 1 and ntaps >= 1 are required");
+    if (n_sig <= 0 || n <= 0 || n_out <= 0) return HS_OK;
     const size_t smem = ((size_t)q * dec_phase_stride(q, ntaps) + ntaps) * sizeof(double);
-    if (smem > 200 * 1024) return set_error(HS_ERR_UNSUPPORTED, "hs_fir_decimate_f64: q=%d, ntaps=%d need %zu B shared memory", q, ntaps, smem);
+    if (smem > 200 * 1024) return set_error(HS_ERR_UNSUPPORTED, "hs_fir_filter_f64: q=%d, ntaps=%d need %zu B shared memory", q, ntaps, smem);
     dim3 grid((unsigned)((n_out + kDecOut - 1) / kDecOut), n_sig);
     auto launch = [&](auto kern) -> int {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "hs_fir_decimate_f64: %s", cudaGetErrorString(e));
-        kern<<<grid, kDecThreads, smem, (cudaStream_t)stream>>>(d_x, n, sig_stride, q, d_b, ntaps, d_y, n_out, y_stride);
+        if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "hs_fir_filter_f64: %s", cudaGetErrorString(e));
+        kern<<<grid, kDecThreads, smem, (cudaStream_t)stream>>>(d_x, n, sig_stride, q, off, d_b, ntaps, d_y, n_out, y_stride);
         return check_launch("fir_decimate_kernel");
     };
     switch (q) {
+        case 1: return launch(fir_decimate_kernel<1>);
         case 2: return launch(fir_decimate_kernel<2>);
         case 4: return launch(fir_decimate_kernel<4>);
         case 8: return launch(fir_decimate_kernel<8>);
         default: return launch(fir_decimate_kernel<0>);
     }
+}
+
+int hs_fir_decimate_f64(const double* d_x, int n_sig, int64_t n, int64_t sig_stride, int q, const double* d_b, int ntaps,
+                        double* d_y, int64_t y_stride, void* stream) {
+    if (ntaps < 1 || (ntaps & 1) == 0) return set_error(HS_ERR_INVALID, "hs_fir_decimate_f64: q >= 1 and an odd tap count are required");
+    if (q < 1) return set_error(HS_ERR_INVALID, "hs_fir_decimate_f64: q >= 1 and an odd tap count are required");
+    return hs_fir_filter_f64(d_x, n_sig, n, sig_stride, q, (ntaps - 1) / 2, d_b, ntaps, d_y, (n + q - 1) / q, y_stride, stream);
 }
 
 size_t hs_mt_psd_ws_bytes(int n_sig, int64_t n, int K) {

@@ -36,20 +36,25 @@ def _design_eeg_filters(multimodal_data, lowcut, highcut, notch_freq=50, notch_q
 
 
 def _apply_filters(multimodal_data, filters, raw_eeg_data, plot_flag=False):
-    """Reference ``_apply_filters`` (dataloader.py:767-814), IIR branch: every mapped channel row of
-    ``raw_eeg_data`` gets DC removal and filtfilt notch -> low -> high, written back IN PLACE (cast to the
+    """Reference ``_apply_filters`` (dataloader.py:767-814): every mapped channel row of ``raw_eeg_data`` gets DC removal
+    and either filtfilt notch -> low -> high (``'iir'``, :789-792) or the causal lfilter chain with the FIR delays rolled
+    out (any other ``filter_type``, the reference's default ``'fir'``, :793-801), written back IN PLACE (cast to the
     array's dtype like the reference's assignment at :803), ``applied`` flags set (:812-814).
-    All channels go through ONE batched GPU call instead of the per-channel Python loop (:786)."""
+    All channels go through batched GPU calls instead of the per-channel Python loop (:786)."""
     (b_notch, a_notch), (b_low, a_low), (b_high, a_high), filter_type = filters
     print(f"Applying {filter_type} filters to EEG data.")
-    if filter_type != "iir":
-        raise NotImplementedError(
-            "hyperscanning_signal_analysis_b200 implements the zero-phase IIR branch (dataloader.py:789-792); the causal "
-            "FIR branch (dataloader.py:793-801) is listed under 'next' in DESIGN.md and has no GPU kernel yet")
     rows = [multimodal_data.eeg_channel_mapping[ch] for ch in multimodal_data.eeg_channel_names_all()]
     if rows:
         block = np.ascontiguousarray(raw_eeg_data[rows, :], dtype=np.float64)
-        out = frontend.filtfilt_cascade(block, [(b_notch, a_notch), (b_low, a_low), (b_high, a_high)], remove_dc=True)
+        if filter_type == "iir":
+            out = frontend.filtfilt_cascade(block, [(b_notch, a_notch), (b_low, a_low), (b_high, a_high)], remove_dc=True)
+        else:
+            if np.size(a_low) != 1 or np.size(a_high) != 1:
+                raise NotImplementedError("the causal branch expects FIR low-/high-pass filters (a = 1) as _design_eeg_filters makes them")
+            bl = np.atleast_1d(np.asarray(b_low, dtype=np.float64)) / float(np.ravel(a_low)[0])
+            bh = np.atleast_1d(np.asarray(b_high, dtype=np.float64)) / float(np.ravel(a_high)[0])
+            import torch
+            out = frontend.lfilter_fir_chain_dev(torch.from_numpy(block).cuda(), (b_notch, a_notch), bl, bh, remove_dc=True).cpu().numpy()
         raw_eeg_data[rows, :] = out
     multimodal_data.eeg_filtration.notch["applied"] = True
     multimodal_data.eeg_filtration.low_pass["applied"] = True

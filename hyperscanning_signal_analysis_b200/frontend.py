@@ -75,6 +75,43 @@ def filtfilt_cascade(x, filters, remove_dc=False, axis=-1):
     return t.cpu().numpy()
 
 
+def lfilter_fir_chain_dev(x_dev, notch, b_low, b_high, remove_dc=True):
+    """FIR branch of the loader (dataloader.py:788, 793-801) on a (n_sig, n) CUDA float64 tensor; returns a new tensor:
+    causal ``lfilter`` notch (IIR) -> ``lfilter`` low-pass FIR -> ``lfilter`` high-pass FIR, ``np.roll`` by the two FIR
+    group delays and a zeroed tail.  The roll is folded into the last FIR pass (offset = delay)."""
+    torch = _torch()
+    lib = _lib.load()
+    assert x_dev.is_cuda and x_dev.dtype == torch.float64 and x_dev.dim() == 2 and x_dev.is_contiguous()
+    n_sig, n = x_dev.shape
+    b_n = np.ascontiguousarray(np.atleast_1d(notch[0]), dtype=np.float64)
+    a_n = np.ascontiguousarray(np.atleast_1d(notch[1]), dtype=np.float64)
+    nt = max(len(a_n), len(b_n))
+    bb = np.zeros(nt)
+    aa = np.zeros(nt)
+    bb[:len(b_n)] = b_n
+    aa[:len(a_n)] = a_n
+    stream = torch.cuda.current_stream().cuda_stream
+    out = torch.zeros_like(x_dev)
+    if n_sig == 0 or n == 0:
+        return out
+    ws = torch.empty(max(int(lib.hs_filtfilt_ws_bytes(n_sig, n)), 16), dtype=torch.uint8, device="cuda")
+    y1 = torch.empty_like(x_dev)
+    _lib.check(lib.hs_iir_lfilter_f64(x_dev.data_ptr(), n_sig, n, n, bb.ctypes.data, aa.ctypes.data, nt, int(remove_dc),
+                                      y1.data_ptr(), n, ws.data_ptr(), stream), "hs_iir_lfilter_f64")
+    bl = torch.from_numpy(np.ascontiguousarray(b_low, dtype=np.float64)).cuda()
+    bh = torch.from_numpy(np.ascontiguousarray(b_high, dtype=np.float64)).cuda()
+    y2 = torch.empty_like(x_dev)
+    _lib.check(lib.hs_fir_filter_f64(y1.data_ptr(), n_sig, n, n, 1, 0, bl.data_ptr(), bl.numel(), y2.data_ptr(), n, n, stream),
+               "hs_fir_filter_f64")
+    delay = (bl.numel() - 1) // 2 + (bh.numel() - 1) // 2
+    # np.roll(s, -delay); s[-delay:] = 0  ->  out[t] = s[t + delay] for t < n - delay, 0 after.  delay == 0 zeroes the whole
+    # signal in the reference (s[-0:] is s[0:]), and so does delay >= n.
+    if 0 < delay < n:
+        _lib.check(lib.hs_fir_filter_f64(y2.data_ptr(), n_sig, n, n, 1, delay, bh.data_ptr(), bh.numel(), out.data_ptr(),
+                                         n - delay, n, stream), "hs_fir_filter_f64")
+    return out
+
+
 def decimate_taps(q):
     """Anti-alias FIR of ``scipy.signal.decimate(..., ftype='fir')``: firwin(20 q + 1, 1/q, window='hamming')."""
     from scipy.signal import firwin

@@ -136,6 +136,20 @@ size_t hs_filtfilt_ws_bytes(int n_sig, int64_t n);
 int hs_iir_filtfilt_f64(double* d_x, int n_sig, int64_t n, int64_t sig_stride, int64_t t_stride, const double* h_b,
                         const double* h_a, int n_filt, int ntaps, int remove_dc, void* d_ws, void* stream);
 
+/* Causal IIR: scipy.signal.lfilter(b, a, x) with zero initial state, one forward sweep of the same scan kernels.
+ * Replaces the notch of the FIR branch of _apply_filters, src/dataloader.py:794 (DC removal :788 fused via remove_dc).
+ * d_x (n_sig rows, unit time stride) is NOT modified; d_y (n_sig, n) must be a different buffer.
+ * d_ws: hs_filtfilt_ws_bytes(n_sig, n) bytes.                                                 */
+int hs_iir_lfilter_f64(const double* d_x, int n_sig, int64_t n, int64_t sig_stride, const double* h_b, const double* h_a,
+                       int ntaps, int remove_dc, double* d_y, int64_t y_stride, void* d_ws, void* stream);
+
+/* General FIR with decimation and offset:  y[k] = sum_j b[j] x[q k + off - j],  k < n_out,  x = 0 outside [0, n).
+ * off = 0, q = 1 is scipy.signal.lfilter(b, 1, x) (src/dataloader.py:795-796, the 201-tap low-pass and 3049-tap
+ * high-pass of the loader's default FIR branch); off = delay, n_out = n - delay is lfilter followed by
+ * np.roll(y, -delay) (:798-799); off = (ntaps-1)/2 with q > 1 is hs_fir_decimate_f64.  d_b: DEVICE taps.        */
+int hs_fir_filter_f64(const double* d_x, int n_sig, int64_t n, int64_t sig_stride, int q, int64_t off, const double* d_b,
+                      int ntaps, double* d_y, int64_t n_out, int64_t y_stride, void* stream);
+
 /* scipy.signal.decimate(x, q, ftype='fir', zero_phase=True), src/data_structures.py:792:
  * y[k] = sum_j b[j] x[q k + half - j], half = (ntaps-1)/2, zero outside.  d_y (n_sig, ceil(n/q)). */
 int hs_fir_decimate_f64(const double* d_x, int n_sig, int64_t n, int64_t sig_stride, int q, const double* d_b,

@@ -47,6 +47,24 @@ def apply_filters_iir(x, filters):
     return out
 
 
+def apply_filters_fir(x, filters):
+    """FIR branch of ``_apply_filters`` (/root/reference src/dataloader.py:788, 793-801): DC removal, CAUSAL lfilter
+    notch -> 201-tap low-pass -> 3049-tap high-pass, then the two FIR group delays are rolled out and the wrapped tail
+    is zeroed (the notch's delay is not compensated: SURVEY.md Appendix B.8)."""
+    (b_n, a_n), (b_l, a_l), (b_h, a_h), _ = filters
+    out = np.empty_like(x, dtype=np.float64)
+    for r in range(x.shape[0]):
+        s = x[r] - np.mean(x[r])
+        s = signal.lfilter(b_n, a_n, s, axis=0)
+        s = signal.lfilter(b_l, a_l, s, axis=0)
+        s = signal.lfilter(b_h, a_h, s, axis=0)
+        delay = (len(b_l) - 1) // 2 + (len(b_h) - 1) // 2
+        s = np.roll(s, -delay)
+        s[-delay:] = 0.0
+        out[r] = s
+    return out
+
+
 # ------------------------------------------------------------- filtfilt A.1
 def _lfilter_zi(b, a):
     """Steady-state DF2T state for a unit step (scipy.signal.lfilter_zi)."""

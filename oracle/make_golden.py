@@ -131,6 +131,15 @@ def main():
                         b_notch=bn, a_notch=an, b_low=bl, a_low=al, b_high=bh, a_high=ah,
                         applied=np.array([md.eeg_filtration.notch["applied"], md.eeg_filtration.low_pass["applied"],
                                           md.eeg_filtration.high_pass["applied"]]))
+    # default branch of the loader: filter_type='fir' (causal lfilter chain + delay roll), 3 channels x 9000 samples
+    rawf = synth.dyad_eeg(seed=synth.BASE_SEED + 9, m=38, fs=256.0, n_samples=9000)
+    ffir = dataloader._design_eeg_filters(md, lowcut=1.0, highcut=40.0)
+    assert ffir[3] == "fir"
+    filt_f = rawf.copy()
+    quiet(dataloader._apply_filters, md, ffir, filt_f)
+    self_ = [0, 19, 37]
+    np.savez_compressed(os.path.join(OUT, "filters_fir.npz"), versions=versions, fs=256.0, raw=rawf[self_], out=filt_f[self_],
+                        b_low=ffir[1][0], b_high=ffir[2][0])
     # the reference's own unit-test input (tests/test_dataloader.py:181-197): 10 Hz + 60 Hz, fs 256, n 1000
     tt = np.arange(1000) / 256.0
     sig = np.sin(2 * np.pi * 10 * tt) + 0.5 * np.sin(2 * np.pi * 60 * tt) + 3.0

@@ -47,12 +47,40 @@ def test_apply_filters_against_reference_golden(capsys):
         dataloader._apply_filters(md1, f1, b1)
     assert not np.array_equal(b1, u["raw"])            # what the reference test asserts
     assert relerr(b1, u["out"]) < TOL_SIGNAL           # what it should have asserted
-    # default design branch stays 'fir' like the reference (tests/test_dataloader.py:129-173) and is refused loudly on apply
+    # default design branch stays 'fir' like the reference (tests/test_dataloader.py:129-173)
     ffir = dataloader._design_eeg_filters(md1, 1.0, 40.0)
     assert ffir[3] == "fir" and len(ffir[1][0]) == 201 and len(ffir[2][0]) == 3049
-    with pytest.raises(NotImplementedError):
-        with contextlib.redirect_stdout(io.StringIO()):
-            dataloader._apply_filters(md1, ffir, b1)
+
+
+def test_fir_branch_against_reference_golden():
+    """filter_type='fir' (the reference's default): causal lfilter notch + 201-tap low-pass + 3049-tap high-pass, the FIR
+    delays rolled out, tail zeroed (dataloader.py:793-801)."""
+    from hyperscanning_signal_analysis_b200 import dataloader
+    g = golden("filters_fir.npz")
+    md = _md(float(g["fs"]), 3)
+    filters = dataloader._design_eeg_filters(md, lowcut=1.0, highcut=40.0)
+    np.testing.assert_array_equal(filters[1][0], g["b_low"])
+    np.testing.assert_array_equal(filters[2][0], g["b_high"])
+    buf = g["raw"].copy()
+    with contextlib.redirect_stdout(io.StringIO()) as out:
+        dataloader._apply_filters(md, filters, buf)
+    assert "Applying fir filters to EEG data." in out.getvalue()
+    assert relerr(buf, g["out"]) < TOL_SIGNAL
+    delay = 100 + 1524
+    assert np.all(buf[:, -delay:] == 0.0)
+    assert md.eeg_filtration.high_pass["applied"] and md.eeg_filtration.high_pass["f_type"] == "firwin"
+    # a signal shorter than the combined delay comes back all zero, like np.roll + s[-delay:] = 0 does
+    short = g["raw"][:, :1000].copy()
+    with contextlib.redirect_stdout(io.StringIO()):
+        dataloader._apply_filters(md, filters, short)
+    assert np.all(short == 0.0)
+    # long signal: the notch takes the tiled scan path; compare with the oracle
+    rng = np.random.default_rng(5)
+    x = 20.0 * rng.standard_normal((3, 30000)) + 40.0
+    ref = fo.apply_filters_fir(x, fo.design_eeg_filters(256.0, 1.0, 40.0, filter_type="fir"))
+    with contextlib.redirect_stdout(io.StringIO()):
+        dataloader._apply_filters(md, filters, x)
+    assert relerr(x, ref) < TOL_SIGNAL
 
 
 def test_float32_storage_quirk():

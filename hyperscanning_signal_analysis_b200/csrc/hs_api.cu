@@ -55,7 +55,7 @@ static int k5_groups() {
     if (ng == 0) {
         const char* e = getenv("HS_K5_GROUPS");
         ng = e ? atoi(e) : 6;
-        if (ng != 6 && ng != 7 && ng != 8) ng = 6;
+        if (ng < 4 || ng > 8) ng = 6;
     }
     return ng;
 }

@@ -119,12 +119,16 @@ __device__ __forceinline__ void mma_inverse4(const MmaCtx& x, const int K0, cons
         const double pr = __shfl_sync(0xffffffffu, dr, s * 5, 16), pi = __shfl_sync(0xffffffffu, di, s * 5, 16);
         const double rjr = __shfl_sync(0xffffffffu, dr, s * 4 + j, 16), rji = __shfl_sync(0xffffffffu, di, s * 4 + j, 16);
         const double cir = __shfl_sync(0xffffffffu, dr, i * 4 + s, 16), cii = __shfl_sync(0xffffffffu, di, i * 4 + s, 16);
-        const double y = rcp_newton2(fma(pr, pr, pi * pi));
-        const double ivr = pr * y, ivi = -pi * y;
         const bool prow = (i == s), pcol = (j == s);
         const double sr = prow ? dr : cir, si = prow ? di : cii;       // pivot row: scale the own entry; other rows: multiplier
-        const double tr = fma(sr, ivr, -si * ivi), ti = fma(sr, ivi, si * ivr);
-        const double ur = fma(-tr, rjr, fma(ti, rji, dr)), ui = fma(-tr, rji, fma(-ti, rjr, di));
+        // t = s / p = y q,  u = d - t r = d - y (q r)  with  y = 1 / |p|^2,  q = s conj(p):  q and q r are computed next to the
+        // reciprocal chain, so only ONE dependent FMA follows it
+        const double y = rcp_newton2(fma(pr, pr, pi * pi));
+        const double qr = fma(sr, pr, si * pi), qi = fma(si, pr, -sr * pi);
+        const double wr = fma(qr, rjr, -qi * rji), wi = fma(qr, rji, qi * rjr);
+        const double tr = qr * y, ti = qi * y;
+        const double ivr = pr * y, ivi = -pi * y;
+        const double ur = fma(-y, wr, dr), ui = fma(-y, wi, di);
         dr = prow ? (pcol ? ivr : tr) : (pcol ? -tr : ur);
         di = prow ? (pcol ? ivi : ti) : (pcol ? -ti : ui);
     }
@@ -212,36 +216,59 @@ __device__ __forceinline__ void mma_gauss_jordan(double (&c)[T][T][2], const int
 //      (Re warp: column 2*t4, Im warp: column 2*t4 + 1) as a complex number, keeps the part it owns and hands the
 //      other part to the partner warp through gs->u.X: every coefficient is read from shared memory once per
 //      matrix, and both warps run the same code (the part only selects operands).
-template <int T>
+template <int T, int NP>      // NP > 0: number of lag pairs known at compile time (z kept in registers, tile-major order)
 __device__ __forceinline__ void mma_assemble(double (&c)[T][T][2], const double* __restrict__ coef, const double2* __restrict__ zf,
                                              const int n_planes, const MmaCtx& x) {
-    double vr[T][T], vi[T][T];
-#pragma unroll
-    for (int ta = 0; ta < T; ++ta)
-#pragma unroll
-        for (int tb = 0; tb < T; ++tb) vr[ta][tb] = vi[ta][tb] = 0.0;
     const double* cbase = coef + x.g4 * kRowD + 4 * x.t4 + 2 * x.part;
-    for (int kp = 0; kp < n_planes; ++kp) {
-        const double2 z0 = zf[2 * kp], z1 = zf[2 * kp + 1];       // shared memory, zero padded to an even number of lags
-        const double* cp = cbase + kp * kPlaneD;
+    const double dg = (x.g4 == 2 * x.t4 + x.part) ? 1.0 : 0.0;      // identity (real part) of the entry this warp assembled
+    double* X = reinterpret_cast<double*>(x.gs->u.X) + x.part * (25 * 32) + x.lane;          // outbox of this warp
+    if constexpr (NP > 0) {
+        double2 z[2 * NP];
+#pragma unroll
+        for (int k = 0; k < 2 * NP; ++k) z[k] = zf[k];       // shared memory, zero padded to an even number of lags
 #pragma unroll
         for (int ta = 0; ta < T; ++ta) {
 #pragma unroll
             for (int tb = 0; tb < T; ++tb) {
-                const double2 q = *reinterpret_cast<const double2*>(cp + ta * 8 * kRowD + tb * 16);
-                vr[ta][tb] = fma(-q.x, z0.x, fma(-q.y, z1.x, vr[ta][tb]));
-                vi[ta][tb] = fma(-q.x, z0.y, fma(-q.y, z1.y, vi[ta][tb]));
+                double vr = (ta == tb) ? dg : 0.0, vi = 0.0;
+#pragma unroll
+                for (int kp = 0; kp < NP; ++kp) {
+                    const double2 q = *reinterpret_cast<const double2*>(cbase + kp * kPlaneD + ta * 8 * kRowD + tb * 16);
+                    vr = fma(-q.x, z[2 * kp].x, fma(-q.y, z[2 * kp + 1].x, vr));
+                    vi = fma(-q.x, z[2 * kp].y, fma(-q.y, z[2 * kp + 1].y, vi));
+                }
+                X[(ta * T + tb) * 32] = x.part ? vr : vi;      // the part the partner owns
+                if (x.part) c[ta][tb][1] = vi;
+                else c[ta][tb][0] = vr;
             }
         }
-    }
-    const double dg = (x.g4 == 2 * x.t4 + x.part) ? 1.0 : 0.0;      // identity (real part) of the entry this warp assembled
-    double* X = reinterpret_cast<double*>(x.gs->u.X) + x.part * (25 * 32) + x.lane;          // outbox of this warp
+    } else {
 #pragma unroll
-    for (int ta = 0; ta < T; ++ta) {
+        for (int ta = 0; ta < T; ++ta)
 #pragma unroll
-        for (int tb = 0; tb < T; ++tb) {
-            if (ta == tb) vr[ta][tb] += dg;
-            X[(ta * T + tb) * 32] = x.part ? vr[ta][tb] : vi[ta][tb];      // the part the partner owns
+            for (int tb = 0; tb < T; ++tb) c[ta][tb][0] = c[ta][tb][1] = 0.0;      // [0]: Re, [1]: Im of the assembled entry, for now
+        for (int kp = 0; kp < n_planes; ++kp) {
+            const double2 z0 = zf[2 * kp], z1 = zf[2 * kp + 1];
+            const double* cp = cbase + kp * kPlaneD;
+#pragma unroll
+            for (int ta = 0; ta < T; ++ta) {
+#pragma unroll
+                for (int tb = 0; tb < T; ++tb) {
+                    const double2 q = *reinterpret_cast<const double2*>(cp + ta * 8 * kRowD + tb * 16);
+                    c[ta][tb][0] = fma(-q.x, z0.x, fma(-q.y, z1.x, c[ta][tb][0]));
+                    c[ta][tb][1] = fma(-q.x, z0.y, fma(-q.y, z1.y, c[ta][tb][1]));
+                }
+            }
+        }
+#pragma unroll
+        for (int ta = 0; ta < T; ++ta) {
+#pragma unroll
+            for (int tb = 0; tb < T; ++tb) {
+                const double vr = c[ta][tb][0] + ((ta == tb) ? dg : 0.0), vi = c[ta][tb][1];
+                X[(ta * T + tb) * 32] = x.part ? vr : vi;
+                if (x.part) c[ta][tb][1] = vi;
+                else c[ta][tb][0] = vr;
+            }
         }
     }
     mma_group_sync(x);
@@ -250,10 +277,9 @@ __device__ __forceinline__ void mma_assemble(double (&c)[T][T][2], const double*
     for (int ta = 0; ta < T; ++ta) {
 #pragma unroll
         for (int tb = 0; tb < T; ++tb) {
-            const double own = x.part ? vi[ta][tb] : vr[ta][tb];
             const double got = Xo[(ta * T + tb) * 32];
-            c[ta][tb][0] = x.part ? got : own;
-            c[ta][tb][1] = x.part ? own : got;
+            if (x.part) c[ta][tb][0] = got;
+            else c[ta][tb][1] = got;
         }
     }
 }
@@ -344,10 +370,20 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
         {   // AR coefficients of window w -> shared, layout [lag pair][row][col][lag & 1]
             const double* Aw = P.A + (size_t)w * m * m * p;
             const int row_len = m * p;
-            for (int i = warp; i < m; i += NG * 2) {       // one warp per row
-                for (int cidx = x.lane; cidx < row_len; cidx += 32) {
-                    const int j = cidx / p, k = cidx - j * p;
-                    coef[(k >> 1) * kPlaneD + i * kRowD + 2 * j + (k & 1)] = Aw[(size_t)i * row_len + cidx];
+            for (int i = warp; i < m; i += NG * 2) {       // one warp per row, 5 independent loads in flight per lane
+                const double* Ar = Aw + (size_t)i * row_len;
+                for (int c0 = x.lane; c0 < row_len; c0 += 5 * 32) {
+                    double v[5];
+#pragma unroll
+                    for (int u = 0; u < 5; ++u) v[u] = (c0 + 32 * u < row_len) ? Ar[c0 + 32 * u] : 0.0;
+#pragma unroll
+                    for (int u = 0; u < 5; ++u) {
+                        const int cidx = c0 + 32 * u;
+                        if (cidx < row_len) {
+                            const int j = cidx / p, k = cidx - j * p;
+                            coef[(k >> 1) * kPlaneD + i * kRowD + 2 * j + (k & 1)] = v[u];
+                        }
+                    }
                 }
             }
             for (int e = l64; e < 2 * kMP; e += 64) (&gs->rs[0][0])[e] = 0.0;
@@ -372,6 +408,12 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
         }
         __syncthreads();
 
+        if (P.flip > 0) {
+            // phase skew between the groups that share an SMSP pair (experiment): all groups run identical work, so after
+            // every CTA barrier they would otherwise hit the FP64 pipe in the same phases
+            const long long until = clock64() + (long long)(gid >> 1) * P.flip;
+            while (clock64() < until) { }
+        }
         for (int f = f_begin + gid; f < f_end; f += NG) {
             double c[T][T][2];
             // ---- v = A(f) u for the check (thread l64 < 40 owns entry l64)
@@ -387,7 +429,8 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
             if (l64 < kMP) gs->vfull[l64] = vacc;
             if (l64 == 0) gs->flag = 0;
             // ---- A(f) = I - sum_k A_k z_k(f)
-            mma_assemble<T>(c, coef, zs + (f - f_begin) * 2 * n_planes, n_planes, x);
+            if (n_planes == 4) mma_assemble<T, 4>(c, coef, zs + (f - f_begin) * 2 * n_planes, n_planes, x);
+            else mma_assemble<T, 0>(c, coef, zs + (f - f_begin) * 2 * n_planes, n_planes, x);
             if (P.Af) mma_store_generic<T, false>(c, P, w, f, x);
             // ---- blocked Gauss-Jordan on the tensor pipe
             mma_gauss_jordan<T>(c, m, x);
@@ -494,11 +537,13 @@ int launch_mma_t(const K5Params& P, int sm_count, cudaStream_t stream) {
 
 }  // namespace
 
-bool transfer_mma_fits(int p, int ng, int seg_len) { return ng == 6 && MmaSmem<5>::total(p, ng, seg_len) <= 227 * 1024; }
+bool transfer_mma_fits(int p, int ng, int seg_len) { return ng >= 4 && ng <= 6 && MmaSmem<5>::total(p, ng, seg_len) <= 227 * 1024; }
 
 // optimistic (unpivoted, verified) pass on the tensor pipe; the caller follows up with the pivoted redo
 int launch_transfer_mma(const K5Params& P, int ng, cudaStream_t stream) {
     const int sm = device_sm_count();
+    if (ng == 4 && (P.m + 7) / 8 == 5) return launch_mma_t<5, 4>(P, sm, stream);      // experiments: fewer matrices in flight per SM
+    if (ng == 5 && (P.m + 7) / 8 == 5) return launch_mma_t<5, 5>(P, sm, stream);
     if (ng != 6) return set_error(HS_ERR_INVALID, "transfer_mma: %d groups per CTA not built", ng);
     switch ((P.m + 7) / 8) {
         case 1: return launch_mma_t<1, 6>(P, sm, stream);

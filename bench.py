@@ -312,6 +312,19 @@ def run_b200(args):
            "api": "mtmvar.FfdtfPlan.run -> hs_plan_mvar_ffdtf_host (chunked H2D/compute/D2H on 3 streams), host wall clock incl. final sync"}
     assert abs(float(out_np[0].sum()) - M) < 1e-6
     plan.close()
+    # PCIe ceiling of this box for the e2e number: one plain device -> pinned-host copy of the result (same buffers)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out_pin.copy_(out_d, non_blocking=True)
+    torch.cuda.synchronize()
+    a.record()
+    out_pin.copy_(out_d, non_blocking=True)
+    b.record()
+    torch.cuda.synchronize()
+    d2h_ms = a.elapsed_time(b)
+    e2e["pcie_d2h_gbs_measured"] = out_np.nbytes / (d2h_ms * 1e-3) * 1e-9
+    e2e["pcie_bound_windows_per_s"] = world * n_win / (d2h_ms * 1e-3)
+    e2e["frac_of_pcie_bound"] = e2e["value"] / e2e["pcie_bound_windows_per_s"]
 
     # ---------------- optional: final result all-gather over NCCL (reported separately)
     allgather = None

@@ -557,15 +557,16 @@ static int run_sweep_d(int d, const IirPass& P, const IirCoef& c, cudaStream_t s
 // memory de-interleaved into its q polyphase components, so that for a fixed tap every thread reads the same component at
 // consecutive positions.  With jj = ntaps-1-j:  y[o] = sum_r sum_u b[ntaps-1-(q u + r)] * S_r[o + u]:  a thread owns 4
 // consecutive outputs and slides a 4-register window along S_r (1 shared load per 4 FMAs).  Positions are skewed by
-// pos + (pos >> 2) so the 32 B-strided window loads of a half-warp hit distinct banks.
+// pos + (pos >> kDecSkewShift) so the 32 B-strided window loads of a half-warp hit distinct banks.
 constexpr int kDecThreads = 256;
-constexpr int kDecPer = 4;
+constexpr int kDecPer = 4;                 // (8 per thread with 128-thread CTAs measured 45 % slower: too few loads in flight)
+constexpr int kDecSkewShift = 2;           // pos + (pos >> 2): lanes 4 positions apart land in distinct banks
 constexpr int kDecOut = kDecThreads * kDecPer;
 
 __host__ __device__ inline int dec_phase_len(int q, int ntaps) { return kDecOut + (ntaps - 1 + q - 1) / q + 1; }
 __host__ __device__ inline int dec_phase_stride(int q, int ntaps) {
     const int pl = dec_phase_len(q, ntaps);
-    int st = pl + (pl >> 2) + 1;
+    int st = pl + (pl >> kDecSkewShift) + 1;
     st += (2 - (st & 15) + 16) & 15;          // = 2 (mod 16) doubles: the q components start 16 B apart modulo 128 B
     return st;
 }
@@ -593,18 +594,18 @@ __global__ void __launch_bounds__(kDecThreads) fir_decimate_kernel(const double*
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int ii = i + k * kDecThreads, r = ii % q, pos = ii / q;
-                S[(size_t)r * pst + pos + (pos >> 2)] = v[k];
+                S[(size_t)r * pst + pos + (pos >> kDecSkewShift)] = v[k];
             }
         }
         for (; i < span; i += kDecThreads) {
             const int r = i % q, pos = i / q;
-            S[(size_t)r * pst + pos + (pos >> 2)] = src[i];
+            S[(size_t)r * pst + pos + (pos >> kDecSkewShift)] = src[i];
         }
     } else {
         for (int i = threadIdx.x; i < span; i += kDecThreads) {
             const long long g = lo + i;
             const int r = i % q, pos = i / q;
-            S[(size_t)r * pst + pos + (pos >> 2)] = (g >= 0 && g < n) ? xs[g] : 0.0;
+            S[(size_t)r * pst + pos + (pos >> kDecSkewShift)] = (g >= 0 && g < n) ? xs[g] : 0.0;
         }
     }
     for (int j = threadIdx.x; j < ntaps; j += kDecThreads) taps[j] = b[ntaps - 1 - j];
@@ -620,13 +621,13 @@ __global__ void __launch_bounds__(kDecThreads) fir_decimate_kernel(const double*
 #pragma unroll
         for (int i = 0; i < kDecPer - 1; ++i) {
             const int pos = o0 + i;
-            w[i + 1] = Sr[pos + (pos >> 2)];
+            w[i + 1] = Sr[pos + (pos >> kDecSkewShift)];
         }
         for (int u = 0; u < nu; ++u) {
 #pragma unroll
             for (int i = 0; i < kDecPer - 1; ++i) w[i] = w[i + 1];
             const int pos = o0 + kDecPer - 1 + u;
-            w[kDecPer - 1] = Sr[pos + (pos >> 2)];
+            w[kDecPer - 1] = Sr[pos + (pos >> kDecSkewShift)];
             const double t = taps[q * u + r];
 #pragma unroll
             for (int i = 0; i < kDecPer; ++i) acc[i] = fma(t, w[i], acc[i]);
@@ -743,20 +744,23 @@ __global__ void __launch_bounds__(kPsdThreads, 1) mt_psd_kernel(const PsdParams 
             buf[e] = y;
         }
         __syncthreads();
-        // ---- step 3: n1 independent in-place radix-2 DIF FFTs of length n2
-        for (int s = P.log2n2 - 1; s >= 0; --s) {
-            const int half = 1 << s;
-            const long long tw_mul = n / (2LL * half);              // W_(2 half)^j = W_n^(j * n / (2 half))
-            for (long long q = tid; q < n / 2; q += kPsdThreads) {
-                const long long sub = q / (n2 / 2);                 // which k1 sub-array
-                const int r = (int)(q - sub * (n2 / 2));
-                const int blk = (r >> s) << (s + 1), j = r & (half - 1);
-                double2* p = buf + sub * n2 + blk + j;
-                const double2 u = p[0], v = p[half];
-                p[0] = make_double2(u.x + v.x, u.y + v.y);
-                p[half] = cmul(make_double2(u.x - v.x, u.y - v.y), P.tw[(long long)j * tw_mul]);
+        // ---- step 3: n1 independent in-place radix-2 DIF FFTs of length n2 (32-bit index arithmetic, shifts only)
+        {
+            const int ni = (int)n, half_n2_log = P.log2n2 - 1;
+            for (int s = P.log2n2 - 1; s >= 0; --s) {
+                const int half = 1 << s;
+                const int tw_mul = ni >> (s + 1);                       // W_(2 half)^j = W_n^(j * n / (2 half))
+                for (int q = tid; q < (ni >> 1); q += kPsdThreads) {
+                    const int sub = q >> half_n2_log;                   // which k1 sub-array
+                    const int r = q & ((n2 >> 1) - 1);
+                    const int blk = (r >> s) << (s + 1), j = r & (half - 1);
+                    double2* p = buf + (size_t)sub * n2 + blk + j;
+                    const double2 u = p[0], v = p[half];
+                    p[0] = make_double2(u.x + v.x, u.y + v.y);
+                    p[half] = cmul(make_double2(u.x - v.x, u.y - v.y), P.tw[j * tw_mul]);
+                }
+                __syncthreads();
             }
-            __syncthreads();
         }
         // ---- power of both tapers at the requested bins; X[k1 + n1 k2] sits at buf[k1 * n2 + bitrev(k2)]
         for (int b = tid; b < P.nb; b += kPsdThreads) {

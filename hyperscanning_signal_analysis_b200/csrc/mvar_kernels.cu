@@ -326,7 +326,7 @@ __global__ void ffdtf_normalize_kernel(double* __restrict__ dtf, const double* _
 // ffdtf[w][i][j][f] = dtf[w][i][j][f] / sum_{j,f} dtf[w][i][j][f]   (mtmvar.py:281-283).
 // One CTA per (window, row i): the F runs of m contiguous doubles are read coalesced, transposed through shared
 // memory in chunks of kFinChunk bins and written as contiguous runs along f.
-constexpr int kFinChunk = 32;
+constexpr int kFinChunk = 64;
 __global__ void __launch_bounds__(256) dtf_finalize_kernel(const double* __restrict__ stage, const double* __restrict__ rowpart,
                                                            const int* __restrict__ bad, int m, int F, int n_seg,
                                                            double* __restrict__ dtf_out, double* __restrict__ ffdtf_out) {

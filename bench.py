@@ -218,7 +218,14 @@ def run_b200(args):
             step()
         e1.record()
         barrier()
-    launches = _lib.launch_count() - launches0
+        launches = _lib.launch_count() - launches0
+        # nvidia-smi answers in ~50-100 ms, the K timed steps take ~9 ms each: keep the identical step loop running
+        # (untimed) so that the clock / throttle samples describe this load and not an idle GPU
+        t_end = time.perf_counter() + 1.5
+        while time.perf_counter() < t_end:
+            for _ in range(4):
+                step()
+            torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -282,7 +289,11 @@ def run_b200(args):
                 "bound": "fp64", "achieved": k5_tflops, "peak": dfma_peak, "unit": "TFLOP/s", "frac": k5_tflops / dfma_peak if dfma_peak else None,
                 "peak_source": "hs_measure_dfma_tflops: register-only DFMA loop on all SMs, measured in this run; DMMA m8n8k4 peaks at the same "
                                "rate (tools/fp64_peak.cu). MEASURED_PEAKS.json has no FP64 figure (its hbm_gbs is %s)" % peaks.get("hbm_gbs"),
-                "flops_per_launch": fl["transfer"] * n_win, "ms_per_launch": k5_ms, "traffic": None,
+                "flops_per_launch": fl["transfer"] * n_win, "ms_per_launch": k5_ms,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, ncu --set full on 296 windows (profiles/r01_k5_mma_ncu_summary.md:
+                # 29.7 MB + 823.1 MB), scaled to this launch's window count; algorithmic bytes: A (m*m*p*8) in, |H|^2 (m*m*F*8) out per window
+                "traffic": (29.743872e6 + 823.112704e6) * n_win / 296.0,
+                "algorithmic_bytes_per_launch": n_win * (M * M * P * 8 + M * M * F * 8),
                 "algorithmic_flops_per_matrix": "4*p*m^2 + 8*m^3 (SURVEY 8d: assembly + complex LU/inverse as the reference computes it)",
                 "matrices_redone_with_pivoting": flagged,
                 "stages_ms": stage_ms,
@@ -355,7 +366,7 @@ def run_b200(args):
                 "config": {"workload": "cfg2: sliding-window ffDTF, 599 windows x (38 ch x 512 samples) of one 600 s task per GPU, p=8, F=256, hop 256",
                            "windows_per_step_per_gpu": n_win, "parallelism": f"one dyad per GPU x{world}, no data-path collective",
                            "l2": "explicit 256 MiB memset before every step, inside the timed region; each step also writes 1.77 GB (> 126 MB L2)"},
-                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
+                "clocks": dict(clk.summary(), window="timed steps + 1.5 s of the same step loop continued untimed"), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
         if cpu:
             line["cpu_baseline"] = cpu
         if allgather:

@@ -8,6 +8,7 @@
 //   dtf_multivariate        src/mtmvar.py:204-234   (|H|^2, un-normalised)
 //   full_freq_dtf           src/mtmvar.py:237-284
 //   multivariate_spectra    src/mtmvar.py:165-201   (H V H^T, plain transpose)
+#include <cstdio>
 #include <cstdlib>
 #include "hs_tile.cuh"
 #include "hs_internal.h"
@@ -727,15 +728,260 @@ __global__ void __launch_bounds__(kK4Groups * 64, 1) lwr_kernel(const K4Params P
     }
 }
 
+// -------------------------------------------------------------------------------------
+// K4, one-group variant (the one that runs): ONE tile group (64 threads) per window and FIVE
+// CTAs per SM.  The recursion of a window is a sequential chain of ~107 small GEMMs and 15
+// SPD inverses; the 4-group kernel above spreads that chain over 256 threads and leaves half of
+// them idle in the inverse / reflection phases, with one window per SM in flight (599 windows on
+// 148 SMs = 5 rounds).  Here every window runs the whole chain on its own 64 threads, five
+// windows share an SM (740 slots >= 599 windows: one round) and hide each other's latencies.
+// Three shared-memory panels with an ODD row stride (41 doubles: row and column fragment reads are
+// both bank-conflict free) rotate through the operand roles, so no transposed copies (D^T, Kf^T,
+// Kb^T) are ever materialised:
+//      phase 1   P0 = A_j, P1 = R(kk-j)            Delta -= A_j Gamma(kk-j)        -> P2 = Delta
+//      phase 3   P1 = Vb^-1:  Kf = Delta Vb^-1 -> P0;   P1 = Vf^-1:  Kb = Delta^T Vf^-1 (regs)
+//                Vf -= Kf Delta^T;   P1 = Kb;   Vb -= Kb Delta
+//      phase 4   P2 = B_{kk-1-j} / A_{kk-1-j}      A_j -= Kf B_{kk-1-j},  B_j -= Kb A_{kk-1-j}
+// -------------------------------------------------------------------------------------
+constexpr int kK4Ld = kPadMax + 1;              // 41
+constexpr int kK4Panel = kPadMax * kK4Ld;       // doubles per panel
+constexpr int kK4PerSM = 5;
+
+// acc[a][b] +=/-= sum_k  L[i = tr+8a][k] * Rt[k][j = tc+8b];  TRA: Pa holds L row-major (else k-major), TRB: Pb holds Rt^T
+template <int T, bool SUB, bool TRA, bool TRB>
+__device__ __forceinline__ void tile_mac_x(double (&acc)[T][T], const double* __restrict__ Pa, const double* __restrict__ Pb,
+                                           const int depth, const Group& g) {
+    const double* pa = TRA ? Pa + g.tr * kK4Ld : Pa + g.tr;
+    const double* pb = TRB ? Pb + g.tc * kK4Ld : Pb + g.tc;
+#pragma unroll 2
+    for (int k = 0; k < depth; ++k) {
+        double av[T], bv[T];
+#pragma unroll
+        for (int a = 0; a < T; ++a) av[a] = TRA ? pa[8 * a * kK4Ld] : pa[8 * a];
+#pragma unroll
+        for (int b = 0; b < T; ++b) bv[b] = TRB ? pb[8 * b * kK4Ld] : pb[8 * b];
+#pragma unroll
+        for (int a = 0; a < T; ++a)
+#pragma unroll
+            for (int b = 0; b < T; ++b) acc[a][b] = fma(SUB ? -av[a] : av[a], bv[b], acc[a][b]);
+        pa += TRA ? 1 : kK4Ld;
+        pb += TRB ? 1 : kK4Ld;
+    }
+}
+
+// dst[r*41 + c] = src[r*m + c], r, c < m: coalesced, 8 loads in flight per thread
+__device__ __forceinline__ void load_rowmajor(double* __restrict__ dst, const double* __restrict__ src, const int m, const int l64) {
+    const int total = m * m;
+    int r = l64 / m, c = l64 - r * m;
+    const int dr = 64 / m, dc = 64 - dr * m;
+    for (int e0 = l64; e0 < total; e0 += 8 * 64) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (e0 + 64 * u < total) ? src[e0 + 64 * u] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (e0 + 64 * u < total) dst[r * kK4Ld + c] = v[u];
+            r += dr;
+            c += dc;
+            if (c >= m) { c -= m; ++r; }
+        }
+    }
+}
+
+// Variants measured and dropped (599 windows): operand panels software-pipelined through registers with V_f / V_b in
+// the scratch (1.68 ms: ptxas sinks the loads to their use under the 168-register cap of 5 CTAs/SM; forcing their issue
+// with 200 registers costs the fifth CTA: 2.2 ms).  This form: 1.43 ms (4-group kernel: 1.71 ms).
+template <int T>
+__global__ void __launch_bounds__(64, kK4PerSM) lwr1_kernel(const K4Params P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* P0 = reinterpret_cast<double*>(smem_raw);
+    double* P1 = P0 + kK4Panel;
+    double* P2 = P1 + kK4Panel;
+    GJScratch* sh = reinterpret_cast<GJScratch*>(P2 + kK4Panel);
+    Group g = make_group();
+    g.gid = 0;
+    g.bar = 1;
+    const int m = P.m, p = P.p;
+    const int mmi = m * m;
+    const size_t mm = (size_t)mmi;
+    double* ws = P.ws + (size_t)blockIdx.x * 4 * p * mm;               // [par][A|B][p][mm]
+    auto stA = [&](int par, int j) { return ws + ((size_t)(par * 2 + 0) * p + j) * mm; };   // j = 0-based index of A_{j+1}
+    auto stB = [&](int par, int j) { return ws + ((size_t)(par * 2 + 1) * p + j) * mm; };
+
+    for (int e = threadIdx.x; e < 3 * kK4Panel; e += 64) P0[e] = 0.0;      // padding rows / columns stay zero for good
+
+    for (int w = blockIdx.x; w < P.n_win; w += gridDim.x) {
+        const double* Rw = P.R + (size_t)w * (p + 1) * mm;
+        double Vf[T][T], Vb[T][T], dummy[T][T];
+#pragma unroll
+        for (int a = 0; a < T; ++a)
+#pragma unroll
+            for (int b = 0; b < T; ++b) {
+                const int i = g.tr + 8 * a, j = g.tc + 8 * b;
+                Vf[a][b] = Vb[a][b] = (i < m && j < m) ? Rw[(size_t)j * m + i] : 0.0;      // Gamma(0) = R(0)^T
+            }
+        for (int kk = 0; kk < p; ++kk) {
+            const int cur = kk & 1, nxt = cur ^ 1;
+            const bool last = (kk == p - 1);
+            // ---- phase 1: Delta = Gamma(kk+1) - sum_j A_{j+1} Gamma(kk-j)
+            {
+                double acc[T][T];
+#pragma unroll
+                for (int a = 0; a < T; ++a)
+#pragma unroll
+                    for (int b = 0; b < T; ++b) {
+                        const int i = g.tr + 8 * a, j = g.tc + 8 * b;
+                        acc[a][b] = (i < m && j < m) ? Rw[((size_t)(kk + 1) * m + j) * m + i] : 0.0;
+                    }
+                for (int j = 0; j < kk; ++j) {
+                    __syncthreads();
+                    load_rowmajor(P0, stA(cur, j), m, g.l64);                          // A_{j+1}[i][q]
+                    load_rowmajor(P1, Rw + (size_t)(kk - j) * mm, m, g.l64);           // R(l)[c][q] = Gamma(l)[q][c]
+                    __syncthreads();
+                    tile_mac_x<T, true, true, true>(acc, P0, P1, m, g);
+                }
+                __syncthreads();
+                store_tile<T>(P2, kK4Ld, acc, m, g);                                    // Delta, row-major
+            }
+            // ---- phases 2+3: Kf = Delta Vb^-1, Kb = Delta^T Vf^-1, residual covariances
+            {
+                double iv[T][T];
+                bool finite = true;
+#pragma unroll
+                for (int a = 0; a < T; ++a)
+#pragma unroll
+                    for (int b = 0; b < T; ++b) {
+                        const int i = g.tr + 8 * a, j = g.tc + 8 * b;
+                        iv[a][b] = (i < m && j < m) ? Vb[a][b] : ((i == j) ? 1.0 : 0.0);
+                    }
+                // residual covariances are symmetric positive definite: unpivoted elimination is stable
+                gj_inverse_static<T, false>(iv, dummy, m, g, sh);
+#pragma unroll
+                for (int a = 0; a < T; ++a)
+#pragma unroll
+                    for (int b = 0; b < T; ++b) {
+                        const int i = g.tr + 8 * a, j = g.tc + 8 * b;
+                        if (i < m && j < m) {
+                            P1[i * kK4Ld + j] = iv[a][b];
+                            finite = finite && (fabs(iv[a][b]) <= 1.79e308);
+                        }
+                    }
+                __syncthreads();
+#pragma unroll
+                for (int a = 0; a < T; ++a)
+#pragma unroll
+                    for (int b = 0; b < T; ++b) iv[a][b] = 0.0;
+                tile_mac_x<T, false, true, false>(iv, P2, P1, m, g);                    // Kf = sum_q Delta[i][q] Vbinv[q][j]
+                store_tile<T>(P0, kK4Ld, iv, m, g);                                     // (phase 1 is done with P0)
+                store_tile<T>(stA(nxt, kk), m, iv, m, g);
+                if (!last) {
+#pragma unroll
+                    for (int a = 0; a < T; ++a)
+#pragma unroll
+                        for (int b = 0; b < T; ++b) {
+                            const int i = g.tr + 8 * a, j = g.tc + 8 * b;
+                            iv[a][b] = (i < m && j < m) ? Vf[a][b] : ((i == j) ? 1.0 : 0.0);
+                        }
+                    gj_inverse_static<T, false>(iv, dummy, m, g, sh);
+                    __syncthreads();                                                     // every thread is done reading Vb^-1
+#pragma unroll
+                    for (int a = 0; a < T; ++a)
+#pragma unroll
+                        for (int b = 0; b < T; ++b) {
+                            const int i = g.tr + 8 * a, j = g.tc + 8 * b;
+                            if (i < m && j < m) {
+                                P1[i * kK4Ld + j] = iv[a][b];
+                                finite = finite && (fabs(iv[a][b]) <= 1.79e308);
+                            }
+                        }
+                    __syncthreads();
+#pragma unroll
+                    for (int a = 0; a < T; ++a)
+#pragma unroll
+                        for (int b = 0; b < T; ++b) iv[a][b] = 0.0;
+                    tile_mac_x<T, false, false, false>(iv, P2, P1, m, g);               // Kb = sum_q Delta[q][i] Vfinv[q][j]
+                    store_tile<T>(stB(nxt, kk), m, iv, m, g);
+                    tile_mac_x<T, true, true, true>(Vf, P0, P2, m, g);                  // Vf -= Kf Delta^T   (P0 written before the barriers above)
+                    __syncthreads();                                                     // every thread is done reading Vf^-1
+                    store_tile<T>(P1, kK4Ld, iv, m, g);
+                    __syncthreads();
+                    tile_mac_x<T, true, true, false>(Vb, P1, P2, m, g);                 // Vb -= Kb Delta
+                } else {
+                    __syncthreads();
+                    tile_mac_x<T, true, true, true>(Vf, P0, P2, m, g);
+                }
+                if (!finite) atomicOr(&P.status[w], 2);      // singular (or not positive definite) residual covariance
+                if (P.Vall) store_tile<T>(P.Vall + ((size_t)w * p + kk) * mm, m, Vf, m, g);
+            }
+            // ---- phase 4: order update  A_j -= Kf B_{kk-1-j}  (and  B_j -= Kb A_{kk-1-j}  unless this is the last order)
+            for (int it = 0; it < (last ? kk : 2 * kk); ++it) {
+                const bool isA = it < kk;
+                const int j = isA ? it : it - kk;
+                const double* own = isA ? stA(cur, j) : stB(cur, j);
+                const double* other = isA ? stB(cur, kk - 1 - j) : stA(cur, kk - 1 - j);
+                double acc[T][T];
+                __syncthreads();                                                         // P2 (Delta / previous operand) is free
+                load_tile<T>(acc, own, m, m, g);
+                load_rowmajor(P2, other, m, g.l64);
+                __syncthreads();
+                if (isA) tile_mac_x<T, true, true, false>(acc, P0, P2, m, g);
+                else tile_mac_x<T, true, true, false>(acc, P1, P2, m, g);
+                store_tile<T>(isA ? stA(nxt, j) : stB(nxt, j), m, acc, m, g);
+            }
+            __syncthreads();
+        }
+        // ---- outputs: A[w][i][j][k] = A_{k+1}[i][j]
+        {
+            const int fin = p & 1;
+            double* Aw = P.A + (size_t)w * mm * p;
+            const int total = mmi * p;
+            for (int e0 = threadIdx.x; e0 < total; e0 += 8 * 64) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = e0 + 64 * u;
+                    const int ij = e / p, k = e - ij * p;
+                    v[u] = (e < total) ? stA(fin, k)[ij] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (e0 + 64 * u < total) Aw[e0 + 64 * u] = v[u];
+            }
+            store_tile<T>(P.V + (size_t)w * mm, m, Vf, m, g);
+        }
+        __syncthreads();
+    }
+}
+
+static bool k4_legacy() {
+    static const bool v = [] { const char* e = getenv("HS_K4_LEGACY"); return e && e[0] == '1'; }();
+    return v;
+}
+
 size_t lwr_ws_doubles(int grid, int m, int p) { return (size_t)grid * 4 * p * m * m; }
-int lwr_grid(int n_win) { const int sm = device_sm_count(); return n_win < sm ? n_win : sm; }
+int lwr_grid(int n_win) { const int slots = device_sm_count() * kK4PerSM; return n_win < slots ? n_win : slots; }
 
 int launch_lwr(const K4Params& P, int grid, cudaStream_t stream) {
-    const size_t smem = (size_t)(kK4Groups * 2 + 4) * kPanel * sizeof(double) + kK4Groups * sizeof(GJScratch);
-    cudaError_t e = cudaFuncSetAttribute(lwr_kernel<kTileMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (k4_legacy()) {
+        const int sm = device_sm_count();
+        const size_t smem = (size_t)(kK4Groups * 2 + 4) * kPanel * sizeof(double) + kK4Groups * sizeof(GJScratch);
+        cudaError_t e = cudaFuncSetAttribute(lwr_kernel<kTileMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "lwr: %s", cudaGetErrorString(e));
+        lwr_kernel<kTileMax><<<grid < sm ? grid : sm, kK4Groups * 64, smem, stream>>>(P);
+        return check_launch("lwr_kernel");
+    }
+    const size_t smem = (size_t)3 * kK4Panel * sizeof(double) + sizeof(GJScratch);
+    cudaError_t e = cudaFuncSetAttribute(lwr1_kernel<kTileMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "lwr: %s", cudaGetErrorString(e));
-    lwr_kernel<kTileMax><<<grid, kK4Groups * 64, smem, stream>>>(P);
-    return check_launch("lwr_kernel");
+    // five 41 KB CTAs per SM need the large shared-memory carve-out (the default split may leave room for two only)
+    cudaFuncSetAttribute(lwr1_kernel<kTileMax>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (getenv("HS_DEBUG")) {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lwr1_kernel<kTileMax>, 64, smem);
+        fprintf(stderr, "[hs] lwr1_kernel: %d CTAs/SM, smem %zu, grid %d\n", nb, smem, grid);
+    }
+    lwr1_kernel<kTileMax><<<grid, 64, smem, stream>>>(P);
+    return check_launch("lwr1_kernel");
 }
 
 

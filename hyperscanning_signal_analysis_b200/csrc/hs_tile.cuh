@@ -79,7 +79,7 @@ struct __align__(16) GJScratch {
 // ---------------------------------------------------------------------------------
 template <int T, bool CPLX, bool PIVOT = true>
 __device__ __forceinline__ void gj_inverse(double (&ar)[T][T], double (&ai)[T][T], const int m,
-                                           const Group& g, GJScratch* sh) {
+                                           const Group& g, GJScratch* sh, double2* pinv_prod = nullptr) {
     constexpr int kNone = 1 << 20;
     unsigned used = 0;
     int step = 0;
@@ -156,6 +156,10 @@ __device__ __forceinline__ void gj_inverse(double (&ar)[T][T], double (&ai)[T][T
             const int rl = r & 7, ra = r >> 3;
             const bool row_owner = (g.tr == rl);
             const double2 iv = sh->inv[par];
+            if (pinv_prod) {      // product of the pivot reciprocals: 1 / (det * sign of the row permutation)
+                const double2 q = *pinv_prod;
+                *pinv_prod = make_double2(fma(q.x, iv.x, -q.y * iv.y), fma(q.x, iv.y, q.y * iv.x));
+            }
             if (row_owner) used |= 1u << ra;
             double rr[T], ri[T];
 #define HS_GJ_ROW_CASE(A)                                                                         \

@@ -1082,6 +1082,138 @@ __global__ void spectra_kernel(const double2* __restrict__ H, const double* __re
     }
 }
 
+// Partial coherence from the spectral matrix (partial_coherence, mtmvar.py:287-338) and dDTF = ffDTF * |kappa|
+// (direct_dtf, :341-385).  The reference takes the determinant of every (m-1) x (m-1) minor of S(f) -- m^2 LU
+// factorisations per bin; the minors are the entries of the adjugate:
+//      minor_ij = (-1)^(i+j) det(S) (S^-1)[j][i]
+// so ONE pivoted Gauss-Jordan inverse per bin (which also yields det S as the product of the pivots) gives all of them;
+//      kappa_ij = minor_ij / sqrt(minor_ii minor_jj)   (principal complex square root, 0 where the denominator is 0),
+//      kappa_ii = 1.
+// One tile group (64 threads) per (window, bin), four groups per CTA; S is (n_win, m, m, F) complex128.
+struct PcohScratch {
+    GJScratch gj;
+    double2 diag[kPadMax];
+};
+
+__device__ __forceinline__ double2 cmul2(const double2 a, const double2 b) {
+    return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+// principal square root, as numpy / C99 csqrt
+__device__ __forceinline__ double2 csqrt2(const double2 z) {
+    if (z.x == 0.0 && z.y == 0.0) return make_double2(0.0, z.y);
+    const double r = hypot(z.x, z.y);
+    if (z.x >= 0.0) {
+        const double t = sqrt(0.5 * (r + z.x));
+        return make_double2(t, z.y / (2.0 * t));
+    }
+    const double t = sqrt(0.5 * (r - z.x));
+    return make_double2(fabs(z.y) / (2.0 * t), copysign(t, z.y));
+}
+// a / b, Smith's algorithm (what C / numpy complex division does)
+__device__ __forceinline__ double2 cdiv2(const double2 a, const double2 b) {
+    if (fabs(b.x) >= fabs(b.y)) {
+        const double r = b.y / b.x, d = 1.0 / (b.x + b.y * r);
+        return make_double2((a.x + a.y * r) * d, (a.y - a.x * r) * d);
+    }
+    const double r = b.x / b.y, d = 1.0 / (b.x * r + b.y);
+    return make_double2((a.x * r + a.y) * d, (a.y * r - a.x) * d);
+}
+
+template <int T>
+__global__ void __launch_bounds__(256) pcoh_kernel(const double2* __restrict__ S, const int n_mat, const int m, const int F,
+                                                   double2* __restrict__ kappa, const double* __restrict__ ffdtf,
+                                                   double* __restrict__ ddtf, int* __restrict__ status) {
+    __shared__ PcohScratch scr[4];
+    const Group g = make_group();
+    PcohScratch* sc = scr + g.gid;
+    const int q = blockIdx.x * 4 + g.gid;
+    const bool active = q < n_mat;
+    const int w = active ? q / F : 0, f = active ? q - w * F : 0;
+    const size_t sF = (size_t)F;
+    const double2* Sw = S + (size_t)w * m * m * sF + f;
+    double ar[T][T], ai[T][T];
+#pragma unroll
+    for (int a = 0; a < T; ++a)
+#pragma unroll
+        for (int b = 0; b < T; ++b) {
+            const int i = g.tr + 8 * a, j = g.tc + 8 * b;
+            double2 v = make_double2((i == j) ? 1.0 : 0.0, 0.0);
+            if (active && i < m && j < m) v = Sw[((size_t)i * m + j) * sF];
+            ar[a][b] = v.x;
+            ai[a][b] = v.y;
+        }
+    double2 pprod = make_double2(1.0, 0.0);
+    gj_inverse<T, true, true>(ar, ai, m, g, &sc->gj, &pprod);
+    // sign of the row permutation k -> colmap[k] (every thread walks the cycles: m <= 40 steps)
+    double sign = 1.0;
+    {
+        unsigned long long seen = 0ull;
+        for (int k = 0; k < m; ++k) {
+            if ((seen >> k) & 1ull) continue;
+            int len = 0, c = k;
+            while (!((seen >> c) & 1ull)) {
+                seen |= 1ull << c;
+                c = sc->gj.colmap[c];
+                ++len;
+            }
+            if (!(len & 1)) sign = -sign;
+        }
+    }
+    const double2 det = cdiv2(make_double2(sign, 0.0), pprod);
+    if (active && g.l64 == 0 && sc->gj.singular) atomicOr(&status[w], 4);
+    // minors: storage entry (i', j') holds inverse[r][c], r = rowmap[i'], c = colmap[j']  ->  minor[c][r]
+    int rr[T], cc[T];
+#pragma unroll
+    for (int a = 0; a < T; ++a) rr[a] = (g.tr + 8 * a < m) ? sc->gj.rowmap[g.tr + 8 * a] : -1;
+#pragma unroll
+    for (int b = 0; b < T; ++b) cc[b] = (g.tc + 8 * b < m) ? sc->gj.colmap[g.tc + 8 * b] : -2;
+#pragma unroll
+    for (int a = 0; a < T; ++a)
+#pragma unroll
+        for (int b = 0; b < T; ++b) {
+            double2 v = cmul2(det, make_double2(ar[a][b], ai[a][b]));
+            if ((rr[a] + cc[b]) & 1) v = make_double2(-v.x, -v.y);
+            ar[a][b] = v.x;
+            ai[a][b] = v.y;
+            if (rr[a] == cc[b] && rr[a] >= 0) sc->diag[rr[a]] = v;
+        }
+    group_sync(g);
+    if (!active) return;
+#pragma unroll
+    for (int a = 0; a < T; ++a)
+#pragma unroll
+        for (int b = 0; b < T; ++b) {
+            const int r = rr[a], c = cc[b];
+            if (r < 0 || c < 0) continue;
+            double2 k;
+            if (r == c) {
+                k = make_double2(1.0, 0.0);
+            } else {
+                const double2 den = csqrt2(cmul2(sc->diag[c], sc->diag[r]));
+                k = (den.x != 0.0 || den.y != 0.0) ? cdiv2(make_double2(ar[a][b], ai[a][b]), den) : make_double2(0.0, 0.0);
+            }
+            const size_t o = (((size_t)w * m + c) * m + r) * sF + f;
+            if (kappa) kappa[o] = k;
+            if (ddtf) ddtf[o] = ffdtf[o] * hypot(k.x, k.y);
+        }
+}
+
+int launch_pcoh(const void* S, int n_win, int m, int F, void* kappa, const double* ffdtf, double* ddtf, int* status, cudaStream_t stream) {
+    const long long n_mat = (long long)n_win * F;
+    const int grid = (int)((n_mat + 3) / 4);
+    const double2* Sp = reinterpret_cast<const double2*>(S);
+    double2* kp = reinterpret_cast<double2*>(kappa);
+    switch ((m + 7) / 8) {
+        case 1: pcoh_kernel<1><<<grid, 256, 0, stream>>>(Sp, (int)n_mat, m, F, kp, ffdtf, ddtf, status); break;
+        case 2: pcoh_kernel<2><<<grid, 256, 0, stream>>>(Sp, (int)n_mat, m, F, kp, ffdtf, ddtf, status); break;
+        case 3: pcoh_kernel<3><<<grid, 256, 0, stream>>>(Sp, (int)n_mat, m, F, kp, ffdtf, ddtf, status); break;
+        case 4: pcoh_kernel<4><<<grid, 256, 0, stream>>>(Sp, (int)n_mat, m, F, kp, ffdtf, ddtf, status); break;
+        case 5: pcoh_kernel<5><<<grid, 256, 0, stream>>>(Sp, (int)n_mat, m, F, kp, ffdtf, ddtf, status); break;
+        default: return set_error(HS_ERR_UNSUPPORTED, "partial coherence: m = %d > %d not built", m, kPadMax);
+    }
+    return check_launch("pcoh_kernel");
+}
+
 int launch_spectra(const void* H, const double* V, int n_win, int m, int F, void* S, cudaStream_t stream) {
     const size_t smem = (size_t)2 * m * m * sizeof(double2);
     if (smem > 200 * 1024) return set_error(HS_ERR_UNSUPPORTED, "spectra: m=%d too large", m);

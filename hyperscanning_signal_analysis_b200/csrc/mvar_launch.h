@@ -61,6 +61,7 @@ size_t lwr_generic_ws_doubles(int n_win, int m, int p);
 int launch_lwr_generic(const K4Params& P, cudaStream_t stream);
 size_t transfer_generic_scratch_bytes(int m);
 int launch_transfer_generic(const K5Params& P, void* scratch, cudaStream_t stream);
+int launch_pcoh(const void* S, int n_win, int m, int F, void* kappa, const double* ffdtf, double* ddtf, int* status, cudaStream_t stream);
 int launch_spectra(const void* H, const double* V, int n_win, int m, int F, void* S, cudaStream_t stream);
 
 }  // namespace hs

@@ -22,8 +22,8 @@ from . import _lib
 
 __all__ = [
     "count_corr", "ar_coeff", "mvar_transfer_function", "multivariate_spectra", "dtf_multivariate",
-    "full_freq_dtf", "mvar_criterion", "gen_partial_directed_coherence",
-    "batched_lagcov", "batched_ar_coeff", "batched_transfer", "windowed_ffdtf", "FfdtfPlan",
+    "full_freq_dtf", "mvar_criterion", "gen_partial_directed_coherence", "partial_coherence", "direct_dtf",
+    "batched_partial_coherence", "batched_lagcov", "batched_ar_coeff", "batched_transfer", "windowed_ffdtf", "FfdtfPlan",
 ]
 
 
@@ -343,3 +343,67 @@ def gen_partial_directed_coherence(signals, freqs, fs, max_model_order=20, optim
     num = absA / torch.sqrt(s2)[:, None, None]
     g = torch.where(denom[None] != 0, num / denom[None], torch.zeros_like(num))
     return g.cpu().numpy()
+
+
+def batched_partial_coherence(S, ffdtf=None, want_kappa=True):
+    """S (n_win, m, m, F) complex128 on the device -> (kappa or None, ddtf or None, status).
+
+    One pivoted complex inverse per (window, bin) replaces the m^2 minor determinants of the reference
+    (mtmvar.py:300-321): minor_ij = (-1)^(i+j) det(S) (S^-1)_ji.  With ``ffdtf`` (n_win, m, m, F) float64 the
+    kernel also returns dDTF = ffDTF * |kappa| (mtmvar.py:383)."""
+    torch = _torch()
+    lib = _lib.load()
+    S = S.contiguous()
+    n_win, m, _, F = S.shape
+    kappa = torch.empty_like(S) if want_kappa else None
+    ddtf = None
+    if ffdtf is not None:
+        ffdtf = ffdtf.contiguous()
+        ddtf = torch.empty_like(ffdtf)
+    status = torch.zeros((n_win,), dtype=torch.int32, device="cuda")
+    _lib.check(lib.hs_partial_coherence_f64(S.data_ptr(), n_win, m, F, kappa.data_ptr() if want_kappa else None,
+                                            ffdtf.data_ptr() if ffdtf is not None else None,
+                                            ddtf.data_ptr() if ddtf is not None else None, status.data_ptr(), _stream()),
+               "hs_partial_coherence_f64")
+    return kappa, ddtf, status
+
+
+def partial_coherence(spectra):
+    """Reference ``partial_coherence`` (mtmvar.py:287-338): (m, m, F) complex128 in and out, diagonal = 1."""
+    torch = _torch()
+    sp = np.ascontiguousarray(np.asarray(spectra, dtype=np.complex128))
+    n_chan, _, n_f = sp.shape
+    if n_chan == 1:          # mtmvar.py:320-321: the minor of a 1 x 1 matrix is 1; the diagonal is 1
+        return np.ones((1, 1, n_f), dtype=np.complex128)
+    S = torch.from_numpy(sp).cuda()[None]
+    kappa, _, status = batched_partial_coherence(S)
+    _raise_if_singular(status, "partial_coherence")
+    return kappa[0].cpu().numpy()
+
+
+def direct_dtf(signals, freqs, fs, max_model_order=20, optimal_model_order=None, crit_type='AIC'):
+    """Reference ``direct_dtf`` (mtmvar.py:341-385): dDTF = ffDTF * |partial coherence|.
+
+    The reference fits the model twice (``multivariate_spectra`` and ``full_freq_dtf`` each refit and each print);
+    here one fit feeds both, the prints are kept."""
+    torch = _torch()
+    lib = _lib.load()
+    # the two nested calls of the reference each resolve the order and print (mtmvar.py:186-191 and :262-267)
+    if optimal_model_order is None:
+        _, _, optimal_model_order_ = mvar_criterion(signals, max_model_order, crit_type, True)
+        print('Optimal model order for all channels: p = ', str(optimal_model_order_))
+        print(f'Optimal model order for all channels: p = {optimal_model_order_}')
+    else:
+        optimal_model_order_ = optimal_model_order
+        print('Using provided model order: p = ', str(optimal_model_order))
+        print(f'Using provided model order: p = {optimal_model_order}')
+    A, V, _ = _fit(signals, optimal_model_order_)
+    res = batched_transfer(A, freqs, fs, want=("H", "ffdtf"))
+    _raise_if_singular(res["status"], "direct_dtf")
+    H = res["H"]
+    S = torch.empty_like(H)
+    _, m, _, F = H.shape
+    _lib.check(lib.hs_spectra_f64(H.data_ptr(), V.data_ptr(), 1, m, F, S.data_ptr(), _stream()), "hs_spectra_f64")
+    _, ddtf, status = batched_partial_coherence(S, res["ffdtf"], want_kappa=False)
+    _raise_if_singular(status, "direct_dtf")
+    return ddtf[0].cpu().numpy()

@@ -101,6 +101,15 @@ int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double 
 /* S(f) = H(f) V H(f)^T with a plain transpose, src/mtmvar.py:197-199.  d_S (n_win, m, m, F) complex128. */
 int hs_spectra_f64(const void* d_H, const double* d_V, int n_win, int m, int F, void* d_S, void* stream);
 
+/* Partial coherence of a spectral matrix and the direct DTF.
+ * Replaces partial_coherence (src/mtmvar.py:287-338: determinant of every minor of S(f)) by one pivoted complex
+ * inverse per bin (minor_ij = (-1)^(i+j) det S (S^-1)_ji), and the product of direct_dtf (:379-383).
+ *   d_S (n_win, m, m, F) complex128 in;  d_kappa (n_win, m, m, F) complex128 out or NULL;
+ *   d_ffdtf in / d_ddtf out (n_win, m, m, F) float64, both or neither:  ddtf = ffdtf * |kappa|.
+ * d_status[w] |= 4 when S(f) of window w is singular for some bin.  m <= 40.                     */
+int hs_partial_coherence_f64(const void* d_S, int n_win, int m, int F, void* d_kappa, const double* d_ffdtf,
+                             double* d_ddtf, int32_t* d_status, void* stream);
+
 /* Fused windows -> ffDTF (the metric path): K3 -> K4 -> K5 on one stream.
  * Equivalent to calling full_freq_dtf(window, freqs, fs, optimal_model_order=p)
  * (src/mtmvar.py:237) for every window of EEG_IBI_FFDTF_Pipeline.run_pipeline's loop

@@ -69,7 +69,31 @@ def quiet(fn, *a, **k):
         return fn(*a, **k)
 
 
+def gen_pcoh():
+    """Partial coherence / dDTF from the reference (mtmvar.py:287-385): the m=4 AR(1) example and two cfg-2 windows
+    (m=38, production band) on a 12-bin grid -- the reference takes 38*38*12 determinants of 37x37 minors per window."""
+    sys.path.insert(0, ROOT)
+    import scipy
+    mtmvar = import_reference()[0]
+    versions = f"numpy {np.__version__} scipy {scipy.__version__}"
+    g4 = np.load(os.path.join(OUT, "mvar_m4.npz"))
+    x4, p4, fs4, fr4 = g4["x"], int(g4["p"]), float(g4["fs"]), g4["freqs"]
+    S4 = quiet(mtmvar.multivariate_spectra, x4, fr4, fs4, optimal_model_order=p4)
+    rec = dict(versions=versions, m4_S=S4, m4_kappa=mtmvar.partial_coherence(S4),
+               m4_ddtf=quiet(mtmvar.direct_dtf, x4, fr4, fs4, optimal_model_order=p4))
+    g = np.load(os.path.join(OUT, "mvar_cfg2_windows.npz"))
+    f12 = np.linspace(0, 128, 12, endpoint=False)
+    w0 = g["windows"][0]
+    S = quiet(mtmvar.multivariate_spectra, w0, f12, 256.0, optimal_model_order=8)
+    rec.update(freqs=f12, w0_S=S, w0_kappa=mtmvar.partial_coherence(S),
+               w0_ddtf=quiet(mtmvar.direct_dtf, w0, f12, 256.0, optimal_model_order=8))
+    np.savez_compressed(os.path.join(OUT, "mvar_pcoh.npz"), **rec)
+    print("mvar_pcoh.npz", os.path.getsize(os.path.join(OUT, "mvar_pcoh.npz")))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "pcoh":
+        return gen_pcoh()
     sys.path.insert(0, ROOT)
     from hyperscanning_signal_analysis_b200 import synth
     from scipy import signal
@@ -239,6 +263,7 @@ def main():
             rec[f"T{T}_n{nw}_w{ws}"] = np.array([int(w[0, 0]) for w in wl] + [wl[0].shape[1]])
         np.savez_compressed(os.path.join(OUT, "window_starts.npz"), versions=versions, **rec)
 
+    gen_pcoh()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -183,6 +183,38 @@ def gen_partial_directed_coherence(signals, freqs, fs, max_model_order=20, optim
     return g
 
 
+def partial_coherence(spectra):
+    """Partial coherence from the minors of S(f), reference mtmvar.py:287-338 (det of every minor, as the reference)."""
+    n_chan, _, n_f = spectra.shape
+    minors = np.zeros((n_chan, n_chan, n_f), dtype=np.complex128)
+    idx = np.arange(n_chan)
+    for i in range(n_chan):
+        for j in range(n_chan):
+            if n_chan > 1:
+                sub = spectra[np.ix_(idx != i, idx != j)]                   # (m-1, m-1, F)
+                minors[i, j, :] = np.linalg.det(np.moveaxis(sub, 2, 0))     # mtmvar.py:318
+            else:
+                minors[i, j, :] = 1.0
+    kappa = np.zeros((n_chan, n_chan, n_f), dtype=np.complex128)
+    for i in range(n_chan):
+        for j in range(n_chan):
+            if i != j:
+                den = np.sqrt(minors[i, i, :] * minors[j, j, :])
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    kappa[i, j, :] = np.where(den != 0, minors[i, j, :] / den, 0)
+            else:
+                kappa[i, j, :] = 1.0
+    return kappa
+
+
+def direct_dtf(signals, freqs, fs, max_model_order=20, optimal_model_order=None, crit_type="AIC"):
+    """dDTF = ffDTF * |partial coherence|, reference mtmvar.py:341-385."""
+    S = multivariate_spectra(signals, freqs, fs, max_model_order, optimal_model_order, crit_type)
+    kappa = partial_coherence(S)
+    ff = full_freq_dtf(signals, freqs, fs, max_model_order, optimal_model_order, crit_type)
+    return ff * np.abs(kappa)
+
+
 # ---------------------------------------------------------------- windows
 def window_starts(T, n_windows=3, window_size=None):
     """Start samples of ``EEG_IBI_FFDTF_Pipeline._create_windows``

@@ -273,3 +273,30 @@ def test_optimistic_elimination_falls_back_to_pivoting(mv):
     ff_r = dtf_r / dtf_r.sum(axis=(1, 2), keepdims=True)
     assert relerr(res["dtf"][0].cpu().numpy(), dtf_r) < TOL_MODEL
     assert relerr(res["ffdtf"][0].cpu().numpy(), ff_r) < TOL_MODEL
+
+
+def test_partial_coherence_and_ddtf_against_reference_golden(mv, capsys):
+    """partial_coherence / direct_dtf (mtmvar.py:287-385): one pivoted inverse per bin instead of m^2 minor determinants."""
+    g = golden("mvar_pcoh.npz")
+    k4 = mv.partial_coherence(g["m4_S"])
+    assert k4.dtype == np.complex128 and k4.shape == g["m4_kappa"].shape
+    assert relerr(k4, g["m4_kappa"]) < TOL_MODEL
+    assert np.all(k4[np.arange(4), np.arange(4), :] == 1.0)
+    k38 = mv.partial_coherence(g["w0_S"])
+    assert relerr(k38, g["w0_kappa"]) < TOL_MODEL
+    assert np.max(np.abs(k38 - g["w0_kappa"])) < TOL_MODEL          # |kappa| <= ~1: absolute = element-wise here
+    m4 = golden("mvar_m4.npz")
+    capsys.readouterr()
+    dd = mv.direct_dtf(m4["x"], m4["freqs"], float(m4["fs"]), optimal_model_order=int(m4["p"]))
+    out = capsys.readouterr().out
+    assert out.count("Using provided model order") == 2            # both nested reference calls print (mtmvar.py:191, :266)
+    assert relerr(dd, g["m4_ddtf"]) < TOL_MODEL
+    w = golden("mvar_cfg2_windows.npz")["windows"][0]
+    dd38 = quiet(mv.direct_dtf, w, g["freqs"], 256.0, optimal_model_order=8)
+    assert dd38.shape == (38, 38, 12) and dd38.dtype == np.float64
+    assert relerr(dd38, g["w0_ddtf"]) < TOL_MODEL
+    # 1 x 1 input: the minor is defined as 1 (mtmvar.py:320-321)
+    assert np.all(mv.partial_coherence(np.full((1, 1, 3), 2.0 + 1j)) == 1.0)
+    # singular spectrum -> LinAlgError, like np.linalg.det/inv based code would misbehave; the kernel flags it
+    with pytest.raises(np.linalg.LinAlgError):
+        mv.partial_coherence(np.zeros((3, 3, 2), dtype=complex))

@@ -6,13 +6,96 @@
 * ``compute_ffdtf_windows``: the serial window loop of ``run_pipeline`` (:741-755) calling ``_compute_ffDTF``
   (:521-634: ``freqs = np.arange(fmin, fmax + step, step)`` :584, ``full_freq_dtf`` :592,
   ``multivariate_spectra`` :599), as ONE batched GPU call; results stacked ``(n_win, m, m, F)`` as at :651-652.
-The file discovery, NetCDF loading, Hilbert/FAA, resampling and plotting around it stay in the reference.
+* ``alpha_bandpass_filter`` / ``compute_asymmetry`` / ``downsample_signal`` / ``crop_signal`` / ``zscore_rows`` /
+  ``preprocess_dyad``: the pre-window stage of ``run_pipeline`` (:693-719) -- SOS zero-phase alpha band-pass (:271-311),
+  Hilbert-envelope frontal alpha asymmetry (:314-365), anti-aliased integer down-sampling (:368-406), crop (:409-448),
+  channel-wise z-score (:719) -- same signatures minus ``self``, same ValueErrors, the arithmetic on the GPU.
+The file discovery, NetCDF loading and plotting around it stay in the reference.
 """
 from __future__ import annotations
 
 import numpy as np
 
-from . import _lib, mtmvar
+from . import _lib, mtmvar, frontend
+
+
+# --------------------------------------------------------------------------- pre-window stage (src/eeg_alpha_ibi_ffdtf.py:271-448, :693-719)
+def alpha_bandpass_filter(data, fs, lowcut=8, highcut=12, order=4, axis=-1):
+    """``_alpha_bandpass_filter`` (:271-311): butter(order, [low, high], 'band', output='sos') + ``sosfiltfilt``."""
+    from scipy.signal import butter
+    nyq = 0.5 * fs
+    sos = butter(order, [lowcut / nyq, highcut / nyq], btype='band', output='sos')      # design stays host-side SciPy
+    return frontend.sosfiltfilt(sos, data, axis=axis)
+
+
+def compute_asymmetry(filtered_eeg, channel_names, left_chan="F3", right_chan="F4", metric='amp'):
+    """``_compute_asymmetry`` (:314-365): FAA = log(env_right + 1e-12) - log(env_left + 1e-12), env = |hilbert| with
+    ``N = next_fast_len(n)``.  ``left_chan`` / ``right_chan`` are the pipeline's ``self.left_chan`` / ``self.right_chan``."""
+    torch = _lib.require_cuda()
+    try:
+        left_idx = channel_names.index(left_chan)
+        right_idx = channel_names.index(right_chan)
+    except ValueError as e:
+        raise ValueError(f"Channels {left_chan} or {right_chan} not found: {e}")
+    filtered_eeg = np.asarray(filtered_eeg, dtype=np.float64)
+    pair = np.ascontiguousarray(np.stack([filtered_eeg[left_idx, :], filtered_eeg[right_idx, :]]))
+    orig_len = pair.shape[1]
+    env = frontend.hilbert_envelope_dev(torch.from_numpy(pair).cuda(), N=frontend.next_fast_len(orig_len))
+    if metric == 'power':
+        env = env ** 2
+    elif metric != 'amp':
+        raise ValueError("metric must be 'power' or 'amp'")
+    faa = torch.log(env[1] + 1e-12) - torch.log(env[0] + 1e-12)
+    return faa.cpu().numpy()
+
+
+def downsample_signal(signal, fs=128, fs_new=8):
+    """``_downsample_signal`` (:368-406): ``resample_poly(signal, up=1, down=fs/fs_new)`` for a 1-D signal."""
+    torch = _lib.require_cuda()
+    if fs_new >= fs:
+        raise ValueError("fs_new must be lower than fs")
+    ratio = fs / fs_new
+    if not np.isclose(ratio, round(ratio)):
+        raise ValueError("fs must be divisible by fs_new")
+    down = int(round(ratio))
+    x = np.ascontiguousarray(np.asarray(signal, dtype=np.float64))
+    y = frontend.downsample_dev(torch.from_numpy(np.atleast_2d(x)).cuda(), down).cpu().numpy()
+    return y[0] if x.ndim == 1 else y
+
+
+def crop_signal(signal, fs, drop_front_sec=10, keep_duration_sec=60):
+    """``_crop_signal`` (:409-448): drop the first seconds, keep the next ``keep_duration_sec`` (a view, like the reference)."""
+    required_sec = drop_front_sec + keep_duration_sec
+    total_samples = signal.shape[-1]
+    total_sec = total_samples / fs
+    if total_sec >= required_sec:
+        return signal[..., int(drop_front_sec * fs):int(required_sec * fs)]
+    raise ValueError(
+        f"Cropping failed: The signal is too short. "
+        f"It needs to be at least {required_sec} seconds long, "
+        f"but the provided signal is only {total_sec:.2f} seconds.")
+
+
+def zscore_rows(signals):
+    """Channel-wise z-score of run_pipeline (:719): (x - mean) / std along axis 1 (population std, ddof = 0)."""
+    signals = np.asarray(signals, dtype=np.float64)
+    return (signals - np.mean(signals, axis=1, keepdims=True)) / np.std(signals, axis=1, keepdims=True)
+
+
+def preprocess_dyad(eeg_ch, eeg_cg, channel_names, ibi_ch, ibi_cg, fs_eeg, fs_ibi, fs_ds=8.0, left_chan="F3", right_chan="F4",
+                    drop_front_sec=10, keep_duration_sec=60):
+    """run_pipeline's pre-window stage (:693-719) for one dyad/film: alpha band-pass of both EEG arrays (n_ch, n), FAA of each
+    participant, down-sampling of FAA and IBI to ``fs_ds``, crop, stack [faa_ch, ibi_ch, faa_cg, ibi_cg], z-score.
+    Returns the (4, keep_duration_sec * fs_ds) array that ``_create_windows`` / ``compute_ffdtf_windows`` take."""
+    rows = []
+    for eeg, ibi in ((eeg_ch, ibi_ch), (eeg_cg, ibi_cg)):
+        filt = alpha_bandpass_filter(eeg, fs_eeg)
+        faa = compute_asymmetry(filt, list(channel_names), left_chan, right_chan, metric="amp")
+        faa_ds = downsample_signal(faa, fs_eeg, fs_ds)
+        ibi_ds = downsample_signal(np.asarray(ibi).squeeze(), fs_ibi, fs_ds)
+        rows.append(crop_signal(faa_ds, fs_ds, drop_front_sec, keep_duration_sec))
+        rows.append(crop_signal(ibi_ds, fs_ds, drop_front_sec, keep_duration_sec))
+    return zscore_rows(np.vstack(rows))
 
 
 def window_starts(T, n_windows=3, window_size=None):

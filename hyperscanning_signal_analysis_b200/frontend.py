@@ -153,3 +153,106 @@ def decimate(x, q):
     t = torch.from_numpy(np.ascontiguousarray(np.atleast_2d(x))).cuda()
     y = decimate_dev(t, q).cpu().numpy()
     return y[0] if one_d else y
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Pre-window stage of EEG_IBI_FFDTF_Pipeline (src/eeg_alpha_ibi_ffdtf.py:271-448): SOS zero-phase band-pass,
+# anti-aliased integer down-sampling, Hilbert envelope.
+# ------------------------------------------------------------------------------------------------------------------
+def sosfiltfilt_dev(x_dev, sos):
+    """``scipy.signal.sosfiltfilt(sos, x, axis=-1)`` (defaults: odd extension, padlen 3 * effective taps, ``sosfilt_zi``)
+    on a (n_sig, n) CUDA float64 tensor; returns a new tensor.  Replaces eeg_alpha_ibi_ffdtf.py:307-309.
+
+    Each sweep runs the sections in cascade with the scan kernels of K1 (``hs_iir_lfilter_f64``, zero state); the initial
+    state ``zi * x0`` SciPy starts every section from enters by superposition: its zero-input response ``x0 * g_s[t]`` is
+    signal independent up to the scalar ``x0``, so ``g_s`` is tabulated once per section (host, O(n), SciPy's own
+    recursion) and added on the device."""
+    from scipy import signal as _sig
+    torch = _torch()
+    lib = _lib.load()
+    assert x_dev.is_cuda and x_dev.dtype == torch.float64 and x_dev.dim() == 2 and x_dev.is_contiguous()
+    sos = np.atleast_2d(np.asarray(sos, dtype=np.float64))
+    if sos.ndim != 2 or sos.shape[1] != 6:
+        raise ValueError("sos array must be shape (n_sections, 6)")
+    n_sections = sos.shape[0]
+    ntaps = 2 * n_sections + 1
+    ntaps -= min(int((sos[:, 2] == 0).sum()), int((sos[:, 5] == 0).sum()))
+    edge = ntaps * 3
+    n_sig, n = x_dev.shape
+    if n <= edge:       # scipy.signal._validate_pad
+        raise ValueError("The length of the input vector x must be greater than padlen, which is %d." % edge)
+    left = 2.0 * x_dev[:, :1] - x_dev[:, 1:edge + 1].flip(1)
+    right = 2.0 * x_dev[:, -1:] - x_dev[:, -edge - 1:-1].flip(1)
+    ext = torch.cat([left, x_dev, right], dim=1).contiguous()
+    n_ext = ext.shape[1]
+    zi = _sig.sosfilt_zi(sos)
+    g = np.stack([_sig.lfilter(sos[s, :3], sos[s, 3:], np.zeros(n_ext), zi=zi[s])[0] for s in range(n_sections)])
+    g_dev = torch.from_numpy(g).cuda()
+    ws = torch.empty(max(int(lib.hs_filtfilt_ws_bytes(n_sig, n_ext)), 16), dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    coef = [(np.ascontiguousarray(sos[s, :3] / sos[s, 3]), np.ascontiguousarray(sos[s, 3:] / sos[s, 3])) for s in range(n_sections)]
+
+    def sweep(u):
+        x0 = u[:, :1].clone()
+        for s in range(n_sections):
+            y = torch.empty_like(u)
+            _lib.check(lib.hs_iir_lfilter_f64(u.data_ptr(), n_sig, n_ext, n_ext, coef[s][0].ctypes.data, coef[s][1].ctypes.data, 3, 0,
+                                              y.data_ptr(), n_ext, ws.data_ptr(), stream), "hs_iir_lfilter_f64")
+            y.addcmul_(x0, g_dev[s][None, :])
+            u = y
+        return u
+
+    fwd = sweep(ext)
+    bwd = sweep(fwd.flip(1).contiguous())
+    return bwd.flip(1)[:, edge:n_ext - edge].contiguous()
+
+
+def sosfiltfilt(sos, x, axis=-1):
+    """NumPy wrapper of :func:`sosfiltfilt_dev` (1-D or 2-D input, filtering along ``axis``)."""
+    torch = _torch()
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 1:
+        return sosfiltfilt_dev(torch.from_numpy(np.ascontiguousarray(x[None])).cuda(), sos)[0].cpu().numpy()
+    if x.ndim != 2:
+        raise ValueError("sosfiltfilt: 1-D or 2-D input")
+    if axis in (-1, 1):
+        return sosfiltfilt_dev(torch.from_numpy(np.ascontiguousarray(x)).cuda(), sos).cpu().numpy()
+    return np.ascontiguousarray(sosfiltfilt_dev(torch.from_numpy(np.ascontiguousarray(x.T)).cuda(), sos).cpu().numpy().T)
+
+
+def resample_poly_taps(down):
+    """Anti-alias FIR of ``scipy.signal.resample_poly(x, 1, down)``: firwin(20 down + 1, 1/down, window=('kaiser', 5.0))."""
+    from scipy.signal import firwin
+    return firwin(2 * 10 * down + 1, 1.0 / down, window=("kaiser", 5.0))
+
+
+def downsample_dev(x_dev, down):
+    """``scipy.signal.resample_poly(x, up=1, down=down)`` (eeg_alpha_ibi_ffdtf.py:403): same polyphase kernel as
+    ``decimate`` (K2), Kaiser-5 taps instead of Hamming; y[k] = sum_j h[j] x[down k + 10 down - j], zero outside."""
+    return decimate_dev(x_dev, int(down), taps=resample_poly_taps(int(down)))
+
+
+def next_fast_len(n):
+    """``scipy.fft.next_fast_len(n)`` (complex transforms: 2-3-5-7-11 smooth), as eeg_alpha_ibi_ffdtf.py:350 calls it."""
+    from scipy.fft import next_fast_len as _nfl
+    return int(_nfl(int(n)))
+
+
+def hilbert_envelope_dev(x_dev, N=None):
+    """``np.abs(scipy.signal.hilbert(x, N=N)[..., :n])`` along the last axis of a (n_sig, n) CUDA float64 tensor
+    (eeg_alpha_ibi_ffdtf.py:352-356); ``N`` defaults to ``n`` like SciPy.  Hand-written mixed-radix FFT (K7)."""
+    torch = _torch()
+    lib = _lib.load()
+    assert x_dev.is_cuda and x_dev.dtype == torch.float64 and x_dev.dim() == 2 and x_dev.is_contiguous()
+    n_sig, n = x_dev.shape
+    N = n if N is None else int(N)
+    if N <= 0:
+        raise ValueError("N must be positive.")
+    n_out = min(n, N)
+    env = torch.empty((n_sig, n_out), dtype=torch.float64, device="cuda")
+    if n_sig == 0:
+        return env
+    ws = torch.empty(int(lib.hs_hilbert_ws_bytes(n_sig, N)), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.hs_hilbert_f64(x_dev.data_ptr(), n_sig, n, n, N, env.data_ptr(), n_out, None, ws.data_ptr(),
+                                  torch.cuda.current_stream().cuda_stream), "hs_hilbert_f64")
+    return env

@@ -159,6 +159,16 @@ int hs_iir_lfilter_f64(const double* d_x, int n_sig, int64_t n, int64_t sig_stri
 int hs_fir_filter_f64(const double* d_x, int n_sig, int64_t n, int64_t sig_stride, int q, int64_t off, const double* d_b,
                       int ntaps, double* d_y, int64_t n_out, int64_t y_stride, void* stream);
 
+/* Hilbert envelope: np.abs(scipy.signal.hilbert(x, N=N)[:n]) of EEG_IBI_FFDTF_Pipeline._compute_asymmetry,
+ * src/eeg_alpha_ibi_ffdtf.py:352-356 (N = scipy.fft.next_fast_len(n)).  Hand-written mixed-radix Stockham FFT
+ * (radices 2..31), forward transform, one-sided mask, inverse transform.
+ *   d_x (n_sig rows, row stride sig_stride, n samples each; zero padded / truncated to N like fft(x, N))
+ *   d_env (n_sig, min(n, N)) float64 with row stride env_stride, or NULL;  d_analytic (n_sig, min(n, N)) complex128
+ *   contiguous, or NULL;  d_ws: hs_hilbert_ws_bytes(n_sig, N) bytes.                                                 */
+size_t hs_hilbert_ws_bytes(int n_sig, int64_t N);
+int hs_hilbert_f64(const double* d_x, int n_sig, int64_t n, int64_t sig_stride, int64_t N, double* d_env, int64_t env_stride,
+                   void* d_analytic, void* d_ws, void* stream);
+
 /* scipy.signal.decimate(x, q, ftype='fir', zero_phase=True), src/data_structures.py:792:
  * y[k] = sum_j b[j] x[q k + half - j], half = (ntaps-1)/2, zero outside.  d_y (n_sig, ceil(n/q)). */
 int hs_fir_decimate_f64(const double* d_x, int n_sig, int64_t n, int64_t sig_stride, int q, const double* d_b,

@@ -212,3 +212,66 @@ def average_psd_across_conditions(psd_dict):
     if not psd_dict:
         raise ValueError("psd_dict is empty; no conditions to average PSD over.")
     return np.mean(np.stack(list(psd_dict.values()), axis=0), axis=0)
+
+
+# ------------------------------------------------------------------ pre-window stage of EEG_IBI_FFDTF_Pipeline
+def alpha_bandpass(data, fs, lowcut=8, highcut=12, order=4, axis=-1):
+    """``_alpha_bandpass_filter`` (/root/reference src/eeg_alpha_ibi_ffdtf.py:303-309): SciPy's own calls."""
+    nyq = 0.5 * fs
+    sos = signal.butter(order, [lowcut / nyq, highcut / nyq], btype="band", output="sos")
+    return signal.sosfiltfilt(sos, data, axis=axis)
+
+
+def sosfiltfilt_explicit(sos, x):
+    """Restatement of ``scipy.signal.sosfiltfilt`` defaults along the last axis (odd extension by
+    3 * (2 n_sections + 1 - min(#b2 == 0, #a2 == 0)), ``sosfilt_zi`` scaled by the first sample of each sweep)."""
+    sos = np.atleast_2d(sos)
+    ns = sos.shape[0]
+    ntaps = 2 * ns + 1 - min(int((sos[:, 2] == 0).sum()), int((sos[:, 5] == 0).sum()))
+    edge = 3 * ntaps
+    x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+    ext = np.concatenate([2 * x[:, :1] - x[:, edge:0:-1], x, 2 * x[:, -1:] - x[:, -2:-edge - 2:-1]], axis=1)
+    zi = signal.sosfilt_zi(sos)[:, None, :]
+    f, _ = signal.sosfilt(sos, ext, axis=1, zi=zi * ext[:, :1][None])
+    r = f[:, ::-1]
+    b, _ = signal.sosfilt(sos, r, axis=1, zi=zi * r[:, :1][None])
+    return b[:, ::-1][:, edge:-edge]
+
+
+def hilbert_envelope(x, N=None):
+    """|scipy.signal.hilbert(x, N)[..., :n]| written out (eeg_alpha_ibi_ffdtf.py:352-356): one-sided spectrum doubling."""
+    x = np.asarray(x, dtype=np.float64)
+    n = x.shape[-1]
+    N = n if N is None else int(N)
+    X = np.fft.fft(x, N, axis=-1)
+    h = np.zeros(N)
+    if N % 2 == 0:
+        h[0] = h[N // 2] = 1
+        h[1:N // 2] = 2
+    else:
+        h[0] = 1
+        h[1:(N + 1) // 2] = 2
+    return np.abs(np.fft.ifft(X * h, axis=-1)[..., :n])
+
+
+def frontal_alpha_asymmetry(filtered_eeg, left_idx, right_idx, metric="amp"):
+    """``_compute_asymmetry`` (eeg_alpha_ibi_ffdtf.py:343-365)."""
+    from scipy.fft import next_fast_len
+    n = filtered_eeg.shape[1]
+    N = next_fast_len(n)
+    left = hilbert_envelope(filtered_eeg[left_idx], N)
+    right = hilbert_envelope(filtered_eeg[right_idx], N)
+    if metric == "power":
+        left, right = left ** 2, right ** 2
+    return np.log(right + 1e-12) - np.log(left + 1e-12)
+
+
+def downsample(x, down):
+    """``resample_poly(x, 1, down)`` in closed form (eeg_alpha_ibi_ffdtf.py:403): Kaiser-5 firwin(20 down + 1, 1/down),
+    y[k] = sum_j h[j] x[down k + 10 down - j], zero outside."""
+    x = np.asarray(x, dtype=np.float64)
+    h = signal.firwin(20 * down + 1, 1.0 / down, window=("kaiser", 5.0))
+    full = np.convolve(x, h)
+    n_out = -(-len(x) // down)
+    idx = down * np.arange(n_out) + 10 * down
+    return full[idx]

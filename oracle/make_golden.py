@@ -91,9 +91,52 @@ def gen_pcoh():
     print("mvar_pcoh.npz", os.path.getsize(os.path.join(OUT, "mvar_pcoh.npz")))
 
 
+def gen_prewindow():
+    """Pre-window stage of EEG_IBI_FFDTF_Pipeline, run through the REFERENCE's own methods (eeg_alpha_ibi_ffdtf.py:271-448,
+    :693-719) on a synthetic dyad: 19 ch x 75 s @ 128 Hz per participant + IBI series at 128 Hz."""
+    sys.path.insert(0, ROOT)
+    import scipy
+    from hyperscanning_signal_analysis_b200 import synth
+    ffd = import_reference()[3]
+    versions = f"numpy {np.__version__} scipy {scipy.__version__}"
+    pipe = ffd.EEG_IBI_FFDTF_Pipeline.__new__(ffd.EEG_IBI_FFDTF_Pipeline)
+    pipe.left_chan, pipe.right_chan, pipe.fs_ds = "F3", "F4", 8.0
+    names = ["Fp1", "Fp2", "F7", "F3", "Fz", "F4", "F8", "T3", "C3", "Cz", "C4", "T4", "T5", "P3", "Pz", "P4", "T6", "O1", "O2"]
+    fs = 128.0
+    n = int(75 * fs) + 37                     # 9637 samples: next_fast_len -> 9680 = 2^4 5 11^2 (radix-11 passes)
+    x = synth.dyad_eeg(seed=77, m=38, fs=fs, n_samples=n, line_amp=0.0)
+    rng = np.random.default_rng(78)
+    t = np.arange(n) / fs
+    ibi = np.stack([0.8 + 0.05 * np.sin(2 * np.pi * 0.1 * t + ph) + 0.01 * rng.standard_normal(n) for ph in (0.0, 1.0)])
+    rec = dict(versions=versions, fs=fs, names=np.array(names), n=n, eeg_sum=float(np.sum(x)), ibi=ibi)      # eeg: synth.dyad_eeg(seed=77, ...)
+    rows = []
+    for who, sl in (("ch", slice(0, 19)), ("cg", slice(19, 38))):
+        eeg = x[sl]
+        filt = pipe._alpha_bandpass_filter(eeg, fs)
+        faa = pipe._compute_asymmetry(filt, names, metric="amp")
+        faa_p = pipe._compute_asymmetry(filt, names, metric="power")
+        faa_ds = pipe._downsample_signal(faa, fs, 8.0)
+        ibi_ds = pipe._downsample_signal(ibi[0 if who == "ch" else 1], fs, 8.0)
+        rows += [pipe._crop_signal(faa_ds, 8.0, 10, 60), pipe._crop_signal(ibi_ds, 8.0, 10, 60)]
+        rec.update({f"filt_{who}": filt[[3, 5, 18]], f"faa_{who}": faa, f"faa_power_{who}": faa_p, f"faa_ds_{who}": faa_ds,
+                    f"ibi_ds_{who}": ibi_ds})
+    sig = np.vstack(rows)
+    sig = (sig - np.mean(sig, axis=1, keepdims=True)) / np.std(sig, axis=1, keepdims=True)      # eeg_alpha_ibi_ffdtf.py:719
+    rec["signals_to_ffDTF"] = sig
+    # short odd-length case: N = next_fast_len(1001) = 1008 = 2^4 3^2 7; hilbert with default N (prime factor 13: 1001 = 7 11 13)
+    from scipy.signal import hilbert
+    xs = x[:3, :1001]
+    rec["short_env_fast"] = np.abs(hilbert(xs, N=1008, axis=-1)[:, :1001])
+    rec["short_env_n"] = np.abs(hilbert(xs, axis=-1))
+    np.savez_compressed(os.path.join(OUT, "prewindow.npz"), **rec)
+    print("prewindow.npz", os.path.getsize(os.path.join(OUT, "prewindow.npz")))
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "pcoh":
         return gen_pcoh()
+    if len(sys.argv) > 1 and sys.argv[1] == "prewindow":
+        return gen_prewindow()
     sys.path.insert(0, ROOT)
     from hyperscanning_signal_analysis_b200 import synth
     from scipy import signal
@@ -264,6 +307,7 @@ def main():
         np.savez_compressed(os.path.join(OUT, "window_starts.npz"), versions=versions, **rec)
 
     gen_pcoh()
+    gen_prewindow()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

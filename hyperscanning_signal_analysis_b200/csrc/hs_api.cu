@@ -369,7 +369,7 @@ struct hs_plan {
     int64_t* h_offsets = nullptr;     // pinned
     cudaStream_t s_compute[2] = {nullptr, nullptr};
     cudaStream_t s_copy = nullptr;
-    cudaEvent_t ev_in = nullptr, ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    cudaEvent_t ev_in = nullptr, ev_in0 = nullptr, ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     size_t ws_bytes = 0;
 };
 
@@ -413,6 +413,7 @@ int hs_plan_create(hs_plan** plan, int max_windows, int m, int n, int p, int F, 
     }
     PLAN_CUDA(cudaStreamCreateWithFlags(&pl->s_copy, cudaStreamNonBlocking));
     PLAN_CUDA(cudaEventCreateWithFlags(&pl->ev_in, cudaEventDisableTiming));
+    PLAN_CUDA(cudaEventCreateWithFlags(&pl->ev_in0, cudaEventDisableTiming));
     return HS_OK;
 }
 
@@ -433,6 +434,7 @@ void hs_plan_destroy(hs_plan* pl) {
     }
     if (pl->s_copy) cudaStreamDestroy(pl->s_copy);
     if (pl->ev_in) cudaEventDestroy(pl->ev_in);
+    if (pl->ev_in0) cudaEventDestroy(pl->ev_in0);
     delete pl;
 }
 
@@ -449,34 +451,66 @@ int hs_plan_mvar_ffdtf_host(hs_plan* pl, const double* h_x, int64_t t_total, con
     }
     if (n_win == 0) return HS_OK;
     const int m = pl->m, F = pl->F;
-    // inputs
-    PLAN_CUDA(cudaMemcpyAsync(pl->d_x, h_x, (size_t)m * t_total * sizeof(double), cudaMemcpyHostToDevice, pl->s_copy));
+    // Chunk schedule: a short first chunk (and a medium second one) so that the device-to-host stream, which bounds the whole
+    // call (2.96 MB per window over PCIe), starts after ~1 ms instead of after a full chunk; HS_PLAN_RAMP=0 disables it.
+    static int ramp = -1;
+    if (ramp < 0) { const char* e = getenv("HS_PLAN_RAMP"); ramp = (e && atoi(e) == 0) ? 0 : 1; }
+    // 16, 32, 64, then full chunks: chunk k's compute (~0.5 ms + 15 us/window) fits inside chunk k-1's copy (52 us/window)
+    auto chunk_at = [&](int idx) { const int c = ramp ? (16 << (idx < 3 ? idx : 3)) : pl->chunk; return c < pl->chunk ? c : pl->chunk; };
+    const int c0 = chunk_at(0);
+    // inputs: the samples the first chunk needs go first (columns [0, t_split) of every channel row), the rest follows
+    int64_t t_split = 0;
+    for (int w = 0; w < n_win && w < c0; ++w)
+        if (h_starts[w] + pl->n > t_split) t_split = h_starts[w] + pl->n;
+    if (!ramp || t_split > t_total / 2) t_split = t_total;
+    const size_t pitch = (size_t)t_total * sizeof(double);
     PLAN_CUDA(cudaMemcpyAsync(pl->d_offsets, pl->h_offsets, (size_t)n_win * sizeof(int64_t), cudaMemcpyHostToDevice, pl->s_copy));
     PLAN_CUDA(cudaMemcpyAsync(pl->d_freqs, h_freqs, (size_t)F * sizeof(double), cudaMemcpyHostToDevice, pl->s_copy));
     PLAN_CUDA(cudaMemsetAsync(pl->d_status, 0, (size_t)n_win * sizeof(int32_t), pl->s_copy));
+    PLAN_CUDA(cudaMemcpy2DAsync(pl->d_x, pitch, h_x, pitch, (size_t)t_split * sizeof(double), m, cudaMemcpyHostToDevice, pl->s_copy));
+    PLAN_CUDA(cudaEventRecord(pl->ev_in0, pl->s_copy));
+    if (t_split < t_total)
+        PLAN_CUDA(cudaMemcpy2DAsync(pl->d_x + t_split, pitch, h_x + t_split, pitch, (size_t)(t_total - t_split) * sizeof(double), m,
+                                    cudaMemcpyHostToDevice, pl->s_copy));
     PLAN_CUDA(cudaEventRecord(pl->ev_in, pl->s_copy));
     const size_t per_win = (size_t)m * m * F;
     int slot = 0;
     bool used[2] = {false, false};
-    for (int w0 = 0; w0 < n_win; w0 += pl->chunk, slot ^= 1) {
-        const int nw = (n_win - w0 < pl->chunk) ? (n_win - w0) : pl->chunk;
+    int idx = 0;
+    static int dbg = -1;
+    if (dbg < 0) dbg = getenv("HS_DEBUG") ? 1 : 0;
+    cudaEvent_t tev[64];
+    int ntev = 0;
+    if (dbg) { cudaEventCreate(&tev[0]); cudaEventRecord(tev[0], pl->s_copy); ntev = 1; }
+    for (int w0 = 0; w0 < n_win; slot ^= 1, ++idx) {
+        const int want = chunk_at(idx);
+        const int nw = (n_win - w0 < want) ? (n_win - w0) : want;
         cudaStream_t sc = pl->s_compute[slot];
-        PLAN_CUDA(cudaStreamWaitEvent(sc, pl->ev_in, 0));
+        PLAN_CUDA(cudaStreamWaitEvent(sc, idx == 0 ? pl->ev_in0 : pl->ev_in, 0));
         if (used[slot]) PLAN_CUDA(cudaStreamWaitEvent(sc, pl->ev_free[slot], 0));    // previous D2H of this slot finished
         int rc = hs_mvar_ffdtf_f64(pl->d_x, pl->d_offsets + w0, t_total, nw, m, pl->n, pl->p, pl->d_freqs, F, fs, pl->d_out[slot],
                                    nullptr, nullptr, pl->d_status + w0, pl->d_ws[slot], sc);
         if (rc) return rc;
         PLAN_CUDA(cudaEventRecord(pl->ev_done[slot], sc));
         PLAN_CUDA(cudaStreamWaitEvent(pl->s_copy, pl->ev_done[slot], 0));
+        if (dbg && ntev < 62) { cudaEventCreate(&tev[ntev]); cudaEventRecord(tev[ntev++], pl->s_copy); }
         PLAN_CUDA(cudaMemcpyAsync(h_ffdtf + (size_t)w0 * per_win, pl->d_out[slot], (size_t)nw * per_win * sizeof(double),
                                   cudaMemcpyDeviceToHost, pl->s_copy));
         PLAN_CUDA(cudaEventRecord(pl->ev_free[slot], pl->s_copy));
+        if (dbg && ntev < 62) { cudaEventCreate(&tev[ntev]); cudaEventRecord(tev[ntev++], pl->s_copy); }
         used[slot] = true;
+        w0 += nw;
     }
     PLAN_CUDA(cudaMemcpyAsync(h_status, pl->d_status, (size_t)n_win * sizeof(int32_t), cudaMemcpyDeviceToHost, pl->s_copy));
     PLAN_CUDA(cudaStreamSynchronize(pl->s_copy));
     PLAN_CUDA(cudaStreamSynchronize(pl->s_compute[0]));
     PLAN_CUDA(cudaStreamSynchronize(pl->s_compute[1]));
+    if (dbg) {
+        fprintf(stderr, "[hs] plan timeline (ms since first copy): ");
+        for (int i = 1; i < ntev; ++i) { float ms = 0; cudaEventElapsedTime(&ms, tev[0], tev[i]); fprintf(stderr, "%s%.2f", (i & 1) ? " [" : "-", ms); if (!(i & 1)) fprintf(stderr, "]"); }
+        fprintf(stderr, "\n");
+        for (int i = 0; i < ntev; ++i) cudaEventDestroy(tev[i]);
+    }
     return HS_OK;
 }
 

@@ -816,22 +816,24 @@ __device__ __forceinline__ void tile_mac_x(double (&acc)[T][T], const double* __
     }
 }
 
-// dst[r*41 + c] = src[r*m + c], r, c < m: coalesced, 8 loads in flight per thread
-__device__ __forceinline__ void load_rowmajor(double* __restrict__ dst, const double* __restrict__ src, const int m, const int l64) {
+// A row-major m x m matrix in global memory -> registers (coalesced: element e = l64 + 64 u, all kK4Pre loads in flight at
+// once) -> shared panel dst[r*41 + c].  Fetch and commit are separate so that the loads of BOTH operands of a product are
+// issued before the first one is waited for.
+constexpr int kK4Pre = (kPadMax * kPadMax + 63) / 64;      // 25
+__device__ __forceinline__ void fetch_rowmajor(double (&v)[kK4Pre], const double* __restrict__ src, const int total, const int l64) {
+#pragma unroll
+    for (int u = 0; u < kK4Pre; ++u) v[u] = (l64 + 64 * u < total) ? src[l64 + 64 * u] : 0.0;
+}
+__device__ __forceinline__ void commit_rowmajor(double* __restrict__ dst, const double (&v)[kK4Pre], const int m, const int l64) {
     const int total = m * m;
     int r = l64 / m, c = l64 - r * m;
     const int dr = 64 / m, dc = 64 - dr * m;
-    for (int e0 = l64; e0 < total; e0 += 8 * 64) {
-        double v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = (e0 + 64 * u < total) ? src[e0 + 64 * u] : 0.0;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            if (e0 + 64 * u < total) dst[r * kK4Ld + c] = v[u];
-            r += dr;
-            c += dc;
-            if (c >= m) { c -= m; ++r; }
-        }
+    for (int u = 0; u < kK4Pre; ++u) {
+        if (l64 + 64 * u < total) dst[r * kK4Ld + c] = v[u];
+        r += dr;
+        c += dc;
+        if (c >= m) { c -= m; ++r; }
     }
 }
 
@@ -851,22 +853,31 @@ __global__ void __launch_bounds__(64, kK4PerSM) lwr1_kernel(const K4Params P) {
     const int m = P.m, p = P.p;
     const int mmi = m * m;
     const size_t mm = (size_t)mmi;
-    double* ws = P.ws + (size_t)blockIdx.x * 4 * p * mm;               // [par][A|B][p][mm]
+    double* ws = P.ws + (size_t)blockIdx.x * (4 * p + 2) * mm;         // [par][A|B][p][mm], Vf, Vb
     auto stA = [&](int par, int j) { return ws + ((size_t)(par * 2 + 0) * p + j) * mm; };   // j = 0-based index of A_{j+1}
     auto stB = [&](int par, int j) { return ws + ((size_t)(par * 2 + 1) * p + j) * mm; };
+    // The residual covariances live in the scratch between the orders (2 tile loads + 2 stores per order): keeping them
+    // in registers would pin 100 of the 168 registers through phases 1 and 4, where they buy 50 loads in flight instead.
+    double* gVf = ws + (size_t)4 * p * mm;
+    double* gVb = gVf + mm;
 
     for (int e = threadIdx.x; e < 3 * kK4Panel; e += 64) P0[e] = 0.0;      // padding rows / columns stay zero for good
 
     for (int w = blockIdx.x; w < P.n_win; w += gridDim.x) {
         const double* Rw = P.R + (size_t)w * (p + 1) * mm;
-        double Vf[T][T], Vb[T][T], dummy[T][T];
+        double dummy[T][T];
+        {
+            double v0[T][T];
 #pragma unroll
-        for (int a = 0; a < T; ++a)
+            for (int a = 0; a < T; ++a)
 #pragma unroll
-            for (int b = 0; b < T; ++b) {
-                const int i = g.tr + 8 * a, j = g.tc + 8 * b;
-                Vf[a][b] = Vb[a][b] = (i < m && j < m) ? Rw[(size_t)j * m + i] : 0.0;      // Gamma(0) = R(0)^T
-            }
+                for (int b = 0; b < T; ++b) {
+                    const int i = g.tr + 8 * a, j = g.tc + 8 * b;
+                    v0[a][b] = (i < m && j < m) ? Rw[(size_t)j * m + i] : 0.0;      // Gamma(0) = R(0)^T
+                }
+            store_tile<T>(gVf, m, v0, m, g);
+            store_tile<T>(gVb, m, v0, m, g);
+        }
         for (int kk = 0; kk < p; ++kk) {
             const int cur = kk & 1, nxt = cur ^ 1;
             const bool last = (kk == p - 1);
@@ -881,9 +892,12 @@ __global__ void __launch_bounds__(64, kK4PerSM) lwr1_kernel(const K4Params P) {
                         acc[a][b] = (i < m && j < m) ? Rw[((size_t)(kk + 1) * m + j) * m + i] : 0.0;
                     }
                 for (int j = 0; j < kk; ++j) {
-                    __syncthreads();
-                    load_rowmajor(P0, stA(cur, j), m, g.l64);                          // A_{j+1}[i][q]
-                    load_rowmajor(P1, Rw + (size_t)(kk - j) * mm, m, g.l64);           // R(l)[c][q] = Gamma(l)[q][c]
+                    double va[kK4Pre], vr[kK4Pre];
+                    fetch_rowmajor(va, stA(cur, j), mmi, g.l64);                       // A_{j+1}[i][q]
+                    fetch_rowmajor(vr, Rw + (size_t)(kk - j) * mm, mmi, g.l64);        // R(l)[c][q] = Gamma(l)[q][c]
+                    __syncthreads();                                                    // the previous product is done with P0 / P1
+                    commit_rowmajor(P0, va, m, g.l64);
+                    commit_rowmajor(P1, vr, m, g.l64);
                     __syncthreads();
                     tile_mac_x<T, true, true, true>(acc, P0, P1, m, g);
                 }
@@ -894,12 +908,13 @@ __global__ void __launch_bounds__(64, kK4PerSM) lwr1_kernel(const K4Params P) {
             {
                 double iv[T][T];
                 bool finite = true;
+                load_tile<T>(iv, gVb, m, m, g);
 #pragma unroll
                 for (int a = 0; a < T; ++a)
 #pragma unroll
                     for (int b = 0; b < T; ++b) {
                         const int i = g.tr + 8 * a, j = g.tc + 8 * b;
-                        iv[a][b] = (i < m && j < m) ? Vb[a][b] : ((i == j) ? 1.0 : 0.0);
+                        if (!(i < m && j < m)) iv[a][b] = (i == j) ? 1.0 : 0.0;
                     }
                 // residual covariances are symmetric positive definite: unpivoted elimination is stable
                 gj_inverse_static<T, false>(iv, dummy, m, g, sh);
@@ -922,12 +937,13 @@ __global__ void __launch_bounds__(64, kK4PerSM) lwr1_kernel(const K4Params P) {
                 store_tile<T>(P0, kK4Ld, iv, m, g);                                     // (phase 1 is done with P0)
                 store_tile<T>(stA(nxt, kk), m, iv, m, g);
                 if (!last) {
+                    load_tile<T>(iv, gVf, m, m, g);
 #pragma unroll
                     for (int a = 0; a < T; ++a)
 #pragma unroll
                         for (int b = 0; b < T; ++b) {
                             const int i = g.tr + 8 * a, j = g.tc + 8 * b;
-                            iv[a][b] = (i < m && j < m) ? Vf[a][b] : ((i == j) ? 1.0 : 0.0);
+                            if (!(i < m && j < m)) iv[a][b] = (i == j) ? 1.0 : 0.0;
                         }
                     gj_inverse_static<T, false>(iv, dummy, m, g, sh);
                     __syncthreads();                                                     // every thread is done reading Vb^-1
@@ -948,17 +964,21 @@ __global__ void __launch_bounds__(64, kK4PerSM) lwr1_kernel(const K4Params P) {
                         for (int b = 0; b < T; ++b) iv[a][b] = 0.0;
                     tile_mac_x<T, false, false, false>(iv, P2, P1, m, g);               // Kb = sum_q Delta[q][i] Vfinv[q][j]
                     store_tile<T>(stB(nxt, kk), m, iv, m, g);
-                    tile_mac_x<T, true, true, true>(Vf, P0, P2, m, g);                  // Vf -= Kf Delta^T   (P0 written before the barriers above)
                     __syncthreads();                                                     // every thread is done reading Vf^-1
                     store_tile<T>(P1, kK4Ld, iv, m, g);
+                    load_tile<T>(iv, gVb, m, m, g);
                     __syncthreads();
-                    tile_mac_x<T, true, true, false>(Vb, P1, P2, m, g);                 // Vb -= Kb Delta
+                    tile_mac_x<T, true, true, false>(iv, P1, P2, m, g);                 // Vb -= Kb Delta
+                    store_tile<T>(gVb, m, iv, m, g);
                 } else {
                     __syncthreads();
-                    tile_mac_x<T, true, true, true>(Vf, P0, P2, m, g);
                 }
+                load_tile<T>(iv, gVf, m, m, g);
+                tile_mac_x<T, true, true, true>(iv, P0, P2, m, g);                      // Vf -= Kf Delta^T   (P0 written before the barriers above)
+                store_tile<T>(gVf, m, iv, m, g);
                 if (!finite) atomicOr(&P.status[w], 2);      // singular (or not positive definite) residual covariance
-                if (P.Vall) store_tile<T>(P.Vall + ((size_t)w * p + kk) * mm, m, Vf, m, g);
+                if (P.Vall) store_tile<T>(P.Vall + ((size_t)w * p + kk) * mm, m, iv, m, g);
+                if (last) store_tile<T>(P.V + (size_t)w * mm, m, iv, m, g);
             }
             // ---- phase 4: order update  A_j -= Kf B_{kk-1-j}  (and  B_j -= Kb A_{kk-1-j}  unless this is the last order)
             for (int it = 0; it < (last ? kk : 2 * kk); ++it) {
@@ -967,9 +987,11 @@ __global__ void __launch_bounds__(64, kK4PerSM) lwr1_kernel(const K4Params P) {
                 const double* own = isA ? stA(cur, j) : stB(cur, j);
                 const double* other = isA ? stB(cur, kk - 1 - j) : stA(cur, kk - 1 - j);
                 double acc[T][T];
-                __syncthreads();                                                         // P2 (Delta / previous operand) is free
+                double vo[kK4Pre];
+                fetch_rowmajor(vo, other, mmi, g.l64);
                 load_tile<T>(acc, own, m, m, g);
-                load_rowmajor(P2, other, m, g.l64);
+                __syncthreads();                                                         // P2 (Delta / previous operand) is free
+                commit_rowmajor(P2, vo, m, g.l64);
                 __syncthreads();
                 if (isA) tile_mac_x<T, true, true, false>(acc, P0, P2, m, g);
                 else tile_mac_x<T, true, true, false>(acc, P1, P2, m, g);
@@ -994,7 +1016,6 @@ __global__ void __launch_bounds__(64, kK4PerSM) lwr1_kernel(const K4Params P) {
                 for (int u = 0; u < 8; ++u)
                     if (e0 + 64 * u < total) Aw[e0 + 64 * u] = v[u];
             }
-            store_tile<T>(P.V + (size_t)w * mm, m, Vf, m, g);
         }
         __syncthreads();
     }
@@ -1005,7 +1026,7 @@ static bool k4_legacy() {
     return v;
 }
 
-size_t lwr_ws_doubles(int grid, int m, int p) { return (size_t)grid * 4 * p * m * m; }
+size_t lwr_ws_doubles(int grid, int m, int p) { return (size_t)grid * (4 * p + 2) * m * m; }
 int lwr_grid(int n_win) { const int slots = device_sm_count() * kK4PerSM; return n_win < slots ? n_win : slots; }
 
 int launch_lwr(const K4Params& P, int grid, cudaStream_t stream) {

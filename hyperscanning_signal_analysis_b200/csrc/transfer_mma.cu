@@ -29,6 +29,7 @@
 // Stability is that of elimination without pivoting across blocks; the kernel verifies every matrix
 // (|| H (A u) - u || on a probe vector) and flags failures for the pivoted register-tile kernel
 // (transfer_dtf_kernel MODE 2).
+#include <cstdlib>
 #include "hs_tile.cuh"
 #include "hs_internal.h"
 #include "mvar_launch.h"
@@ -136,8 +137,52 @@ __device__ __forceinline__ void mma_inverse4(const MmaCtx& x, const int K0, cons
     __syncwarp();
 }
 
+// ---- P = D^-1 by cofactors: lane (i, j) (all 32 lanes, 16..31 mirror 0..15) takes the 3 x 3 minor that deletes row j and column i
+//      straight from the panel in shared memory (9 complex loads, any lane pattern inside one 128-byte block is conflict free),
+//      the determinant follows from one round of shuffles (det = sum_c D[0][c] adj[c][0]), then ONE reciprocal.
+//      Dependent depth ~20 FP64 instructions and 1 shuffle round, against 4 x (shuffle round + reciprocal chain) for the
+//      in-place elimination above; no pivot order inside the block, so small leading minors of D are harmless.
+__device__ __forceinline__ void mma_inverse4_adj(const MmaCtx& x, const int K0, const int buf) {
+    MmaGroupSmem* gs = x.gs;
+    const int i = (x.lane >> 2) & 3, j = x.lane & 3;
+    const double* Dr = gs->u.p.Craw[buf][0] + K0 * 4;
+    const double* Di = gs->u.p.Craw[buf][1] + K0 * 4;
+    const int r0 = (0 >= j) ? 1 : 0, r1 = (1 >= j) ? 2 : 1, r2 = (2 >= j) ? 3 : 2;
+    const int c0 = (0 >= i) ? 1 : 0, c1 = (1 >= i) ? 2 : 1, c2 = (2 >= i) ? 3 : 2;
+#define HS_LD(R, C, vr, vi) const double vr = Dr[(R) * 4 + (C)], vi = Di[(R) * 4 + (C)]
+    HS_LD(r0, c0, a00r, a00i); HS_LD(r0, c1, a01r, a01i); HS_LD(r0, c2, a02r, a02i);
+    HS_LD(r1, c0, a10r, a10i); HS_LD(r1, c1, a11r, a11i); HS_LD(r1, c2, a12r, a12i);
+    HS_LD(r2, c0, a20r, a20i); HS_LD(r2, c1, a21r, a21i); HS_LD(r2, c2, a22r, a22i);
+    HS_LD(0, 0, d0r, d0i); HS_LD(0, 1, d1r, d1i); HS_LD(0, 2, d2r, d2i); HS_LD(0, 3, d3r, d3i);
+#undef HS_LD
+    // 2 x 2 minors of rows r1, r2:  m0 = a11 a22 - a12 a21,  m1 = a10 a22 - a12 a20,  m2 = a10 a21 - a11 a20
+#define HS_DET2(pr, pi, qr, qi, sr, si, tr, ti, outr, outi)                                        \
+    const double outr = fma(pr, qr, -pi * qi) - fma(sr, tr, -si * ti);                              \
+    const double outi = fma(pr, qi, pi * qr) - fma(sr, ti, si * tr)
+    HS_DET2(a11r, a11i, a22r, a22i, a12r, a12i, a21r, a21i, m0r, m0i);
+    HS_DET2(a10r, a10i, a22r, a22i, a12r, a12i, a20r, a20i, m1r, m1i);
+    HS_DET2(a10r, a10i, a21r, a21i, a11r, a11i, a20r, a20i, m2r, m2i);
+#undef HS_DET2
+    // cofactor = a00 m0 - a01 m1 + a02 m2, signed
+    double cr = fma(a00r, m0r, -a00i * m0i) - fma(a01r, m1r, -a01i * m1i) + fma(a02r, m2r, -a02i * m2i);
+    double ci = fma(a00r, m0i, a00i * m0r) - fma(a01r, m1i, a01i * m1r) + fma(a02r, m2i, a02i * m2r);
+    if ((i + j) & 1) { cr = -cr; ci = -ci; }
+    // det = sum_c D[0][c] adj[c][0];  adj[c][0] lives in lane 4c
+    const double b0r = __shfl_sync(0xffffffffu, cr, 0, 16), b0i = __shfl_sync(0xffffffffu, ci, 0, 16);
+    const double b1r = __shfl_sync(0xffffffffu, cr, 4, 16), b1i = __shfl_sync(0xffffffffu, ci, 4, 16);
+    const double b2r = __shfl_sync(0xffffffffu, cr, 8, 16), b2i = __shfl_sync(0xffffffffu, ci, 8, 16);
+    const double b3r = __shfl_sync(0xffffffffu, cr, 12, 16), b3i = __shfl_sync(0xffffffffu, ci, 12, 16);
+    const double detr = (fma(d0r, b0r, -d0i * b0i) + fma(d1r, b1r, -d1i * b1i)) + (fma(d2r, b2r, -d2i * b2i) + fma(d3r, b3r, -d3i * b3i));
+    const double deti = (fma(d0r, b0i, d0i * b0r) + fma(d1r, b1i, d1i * b1r)) + (fma(d2r, b2i, d2i * b2r) + fma(d3r, b3i, d3i * b3r));
+    const double y = rcp_newton2(fma(detr, detr, deti * deti));
+    const double ivr = detr * y, ivi = -deti * y;                      // 1 / det
+    const double pr = fma(cr, ivr, -ci * ivi), pi = fma(cr, ivi, ci * ivr);
+    if (x.lane < 16) gs->u.p.P[x.part][x.lane] = make_double2(pr, pi);
+    __syncwarp();
+}
+
 // ---- the two block steps of tile t (h = 0, 1): hand-over of the panel, 4 x 4 inverse, L panel by DMMA, rank-4 update
-template <int T, int t>
+template <int T, int t, bool ADJ>
 __device__ __forceinline__ void mma_tile_steps(double (&c)[T][T][2], const int m, const MmaCtx& x) {
     MmaGroupSmem* gs = x.gs;
     const int fo = x.g4 * 4 + x.t4;           // A-fragment offset inside a tile row
@@ -148,7 +193,8 @@ __device__ __forceinline__ void mma_tile_steps(double (&c)[T][T][2], const int m
         if (K0 >= m) break;
         mma_extract<T, t>(c, h, x);
         mma_group_sync(x);
-        mma_inverse4(x, K0, h);
+        if (ADJ) mma_inverse4_adj(x, K0, h);
+        else mma_inverse4(x, K0, h);
         // B fragments of -P with Re/Im interleaved by output column:  n = 2j -> Re, n = 2j+1 -> Im
         double a0[T], a1[T];
         {
@@ -196,19 +242,19 @@ __device__ __forceinline__ void mma_tile_steps(double (&c)[T][T][2], const int m
     }
 }
 
-template <int T, int t>
+template <int T, int t, bool ADJ>
 __device__ __forceinline__ void mma_all_tiles(double (&c)[T][T][2], const int m, const MmaCtx& x) {
     if constexpr (t < T) {
-        mma_tile_steps<T, t>(c, m, x);
-        mma_all_tiles<T, t + 1>(c, m, x);
+        mma_tile_steps<T, t, ADJ>(c, m, x);
+        mma_all_tiles<T, t + 1, ADJ>(c, m, x);
     }
 }
 
 // in-place inverse of the matrix held by the two warps of the group
-template <int T>
+template <int T, bool ADJ>
 __device__ __forceinline__ void mma_gauss_jordan(double (&c)[T][T][2], const int m, const MmaCtx& x) {
     mma_group_sync(x);                 // previous users of the panel buffers (assembly exchange) are done
-    mma_all_tiles<T, 0>(c, m, x);
+    mma_all_tiles<T, 0, ADJ>(c, m, x);
 }
 
 
@@ -338,7 +384,7 @@ struct MmaSmem {
     }
 };
 
-template <int T, int NG>
+template <int T, int NG, bool ADJ>
 __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int m = P.m, p = P.p, F = P.F;
@@ -441,7 +487,7 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
             else mma_assemble<T, 0>(c, coef, zs + (f - f_begin) * 2 * n_planes, n_planes, x);
             if (P.Af) mma_store_generic<T, false>(c, P, w, f, x);
             // ---- blocked Gauss-Jordan on the tensor pipe
-            mma_gauss_jordan<T>(c, m, x);
+            mma_gauss_jordan<T, ADJ>(c, m, x);
             // ---- a-posteriori check:  S v == u ?   (v = A(f) u)
             {
                 double sr[T], si[T];
@@ -536,11 +582,13 @@ template <int T, int NG>
 int launch_mma_t(const K5Params& P, int sm_count, cudaStream_t stream) {
     const size_t smem = MmaSmem<T>::total(P.p, NG, P.seg_len);
     if (smem > 227 * 1024) return set_error(HS_ERR_UNSUPPORTED, "transfer_mma: model order %d needs %zu B shared memory", P.p, smem);
-    cudaError_t e = cudaFuncSetAttribute(transfer_mma_kernel<T, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static const bool adj = [] { const char* e = getenv("HS_K5_ADJ"); return !(e && e[0] == '0'); }();      // 4 x 4 pivot-block inverse by cofactors
+    auto kern = (adj && T == 5 && NG == 6) ? transfer_mma_kernel<T, NG, (T == 5 && NG == 6)> : transfer_mma_kernel<T, NG, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "transfer_mma: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
     const int n_units = P.n_win * P.n_seg;
     const int grid = n_units < sm_count ? n_units : sm_count;
-    transfer_mma_kernel<T, NG><<<grid, NG * 64, smem, stream>>>(P);
+    kern<<<grid, NG * 64, smem, stream>>>(P);
     return check_launch("transfer_mma_kernel");
 }
 

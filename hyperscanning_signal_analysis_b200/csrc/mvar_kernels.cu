@@ -800,7 +800,7 @@ __device__ __forceinline__ void tile_mac_x(double (&acc)[T][T], const double* __
                                            const int depth, const Group& g) {
     const double* pa = TRA ? Pa + g.tr * kK4Ld : Pa + g.tr;
     const double* pb = TRB ? Pb + g.tc * kK4Ld : Pb + g.tc;
-#pragma unroll 2
+#pragma unroll 4
     for (int k = 0; k < depth; ++k) {
         double av[T], bv[T];
 #pragma unroll

@@ -15,6 +15,8 @@ all-gather over NCCL that north_star describes is timed separately and reported 
 from __future__ import annotations
 
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -384,10 +386,28 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    # stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 on their own (NCCL prints its version
+    # banner there when NCCL_DEBUG=VERSION is set in the environment) are sent to stderr for the duration of the run.
+    sys.stdout.flush()
+    real_out = os.dup(1)
+    os.dup2(2, 1)
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            if args.impl == "reference":
+                run_reference(args)
+            else:
+                run_b200(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_out, 1)
+        os.close(real_out)
+    lines = [ln for ln in buf.getvalue().splitlines() if ln.strip()]
+    for ln in lines[:-1]:
+        print(ln, file=sys.stderr)
+    if lines:
+        print(lines[-1])
+        sys.stdout.flush()
 
 
 if __name__ == "__main__":

@@ -300,3 +300,40 @@ def test_partial_coherence_and_ddtf_against_reference_golden(mv, capsys):
     # singular spectrum -> LinAlgError, like np.linalg.det/inv based code would misbehave; the kernel flags it
     with pytest.raises(np.linalg.LinAlgError):
         mv.partial_coherence(np.zeros((3, 3, 2), dtype=complex))
+
+
+def test_cfg2_full_size_properties(mv):
+    """BASELINE cfg2 at full size (599 windows x 38 ch x 512 samples, p = 8, 256 bins: 153 344 complex inversions) through
+    size-independent properties, plus the oracle on a handful of windows."""
+    import torch
+    import bench
+    y, starts, freqs = bench.make_task(20260101)
+    assert len(starts) == 599 and freqs.size == 256 and y.shape == (38, 153600)
+    ff, A, V = mv.windowed_ffdtf(y, starts, 512, freqs, 256.0, 8, return_model=True)
+    assert ff.shape == (599, 38, 38, 256)
+    # (ii) every row of every window sums to 1 over (j, f)  (mtmvar.py:281-283)
+    rows = ff.sum(dim=(2, 3))
+    assert float((rows - 1.0).abs().max()) < 1e-12
+    assert bool(torch.isfinite(ff).all()) and float(ff.min()) >= 0.0
+    # run-to-run determinism at full size (fixed summation order, no atomics on the data path)
+    ff2 = mv.windowed_ffdtf(y, starts, 512, freqs, 256.0, 8)
+    assert torch.equal(ff, ff2)
+    del ff2
+    # scale invariance: x * 2^k scales every covariance by exactly 4^k, so A, H and the ffDTF are unchanged to the last bit
+    ff3, A3, V3 = mv.windowed_ffdtf(y * 8.0, starts, 512, freqs, 256.0, 8, return_model=True)
+    assert torch.equal(A, A3) and torch.equal(V * 64.0, V3) and torch.equal(ff, ff3)
+    del ff3
+    # (iii) H(f) A(f) = I on a slice of windows (complex outputs of the same kernels)
+    sel = torch.tensor([0, 123, 300, 598], device="cuda")
+    res = mv.batched_transfer(A[sel].contiguous(), freqs, 256.0, want=("H", "Af", "dtf"))
+    H, Af = res["H"].permute(0, 3, 1, 2), res["Af"].permute(0, 3, 1, 2)         # (w, f, m, m)
+    eye = torch.eye(38, dtype=torch.complex128, device="cuda")
+    assert float((H @ Af - eye).abs().max()) < 1e-9
+    assert float((res["dtf"] - res["H"].abs() ** 2).abs().max() / res["dtf"].max()) < 1e-12
+    # overlapping windows share samples: window w+1 starts 256 samples after window w (hop = W/2)
+    assert np.all(np.diff(starts) == 256)
+    # ... and the oracle on a few windows
+    ffh = ff[sel].cpu().numpy()
+    for k, w in enumerate(sel.tolist()):
+        seg = y[:, starts[w]:starts[w] + 512]
+        assert relerr(ffh[k], mo.full_freq_dtf(seg, freqs, 256.0, optimal_model_order=8)) < TOL_MODEL

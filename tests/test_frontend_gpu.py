@@ -194,3 +194,48 @@ def test_long_signals_take_the_tiled_path(n, fs):
     for q in (2, 8, 5):
         d_ref = signal.decimate(ref, q, ftype="fir", zero_phase=True, axis=1)
         assert relerr(frontend.decimate(got, q), d_ref) < TOL_SIGNAL
+
+
+def test_cfg4_full_size_properties():
+    """BASELINE cfg4 at full size (2 x 19 ch x 1 h at 1024 Hz = 1.12 GB of float64): filtfilt cascade + decimate by 8 on the
+    GPU; two channels against SciPy over the full hour, the rest through size-independent properties."""
+    import torch
+    from hyperscanning_signal_analysis_b200 import frontend, synth
+    fs, n_ch, n = 1024.0, 38, 3600 * 1024
+    x = synth.dyad_eeg(seed=4, m=n_ch, fs=fs, n_samples=n, drift=True)
+    filt = fo.design_eeg_filters(fs, 1.0, 64.0)
+    f3 = list(filt[:3])
+    xd = torch.from_numpy(x).cuda()
+    yd = xd.clone()
+    frontend.filtfilt_cascade_(yd, f3, remove_dc=True)
+    assert bool(torch.isfinite(yd).all())
+    chk = [0, 37]
+    ref = fo.apply_filters_iir(x[chk], filt)
+    assert relerr(yd[chk].cpu().numpy(), ref) < TOL_SIGNAL
+    dd = frontend.decimate_dev(yd, 8)
+    assert dd.shape == (n_ch, n // 8)
+    assert relerr(dd[chk].cpu().numpy(), signal.decimate(ref, 8, ftype="fir", zero_phase=True, axis=1)) < TOL_SIGNAL
+    # run-to-run determinism
+    y2 = xd.clone()
+    frontend.filtfilt_cascade_(y2, f3, remove_dc=True)
+    assert torch.equal(yd, y2)
+    # linearity of the whole cascade: F(a x_i + b x_j) = a F(x_i) + b F(x_j)   (DC removal is linear too)
+    mix = (0.75 * xd[3] - 1.5 * xd[21])[None].contiguous()
+    frontend.filtfilt_cascade_(mix, f3, remove_dc=True)
+    lin = 0.75 * yd[3] - 1.5 * yd[21]
+    assert float((mix[0] - lin).abs().max() / lin.abs().max()) < TOL_SIGNAL
+    # zero phase: away from the two ends (where forward-then-backward and backward-then-forward start-up transients differ; the
+    # slowest pole, |z| = 0.9957, has decayed below 1e-9 after ~5000 samples) filtering the time-reversed signal gives the
+    # time-reversed result
+    rev = xd[5:6].flip(1).contiguous()
+    frontend.filtfilt_cascade_(rev, f3, remove_dc=True)
+    mid = slice(50000, n - 50000)
+    assert float((rev.flip(1)[0, mid] - yd[5, mid]).abs().max() / yd[5].abs().max()) < TOL_SIGNAL
+    # a constant is removed by the DC step and stays zero; a pure 50 Hz line is notched away in the interior
+    c = torch.full((1, 100000), 7.25, dtype=torch.float64, device="cuda")
+    frontend.filtfilt_cascade_(c, f3, remove_dc=True)
+    assert float(c.abs().max()) < 1e-9
+    t = torch.arange(200000, dtype=torch.float64, device="cuda") / fs
+    line = (5.0 * torch.sin(2 * np.pi * 50.0 * t))[None].contiguous()
+    frontend.filtfilt_cascade_(line, f3, remove_dc=True)
+    assert float(line[0, 50000:150000].abs().max()) < 1e-6

@@ -60,6 +60,13 @@ static int k5_groups() {
     return ng;
 }
 
+// doubles reserved for the per-piece row sums: the segment layout of the DFMA kernels (n_win * n_seg * m) or the balanced
+// partition of the tensor-pipe kernel (n_win * slots <= CTAs + 2 * n_win, CTAs <= 1024), whichever is larger
+static size_t k5_rowpart_bytes(int n_win, int n_seg, int m) {
+    size_t a = (size_t)n_win * n_seg, b = (size_t)1024 + 2 * (size_t)n_win;
+    return ((a > b ? a : b) * m * sizeof(double) + 255) / 256 * 256;
+}
+
 static void k5_segments(int F, int ng, int* n_seg, int* seg_len) {
     int target = 8 * ng;
     const char* e = getenv("HS_K5_SEG");
@@ -205,7 +212,7 @@ size_t hs_transfer_ws_bytes(int n_win, int m, int p, int F) {
     if (m > kPadMaxHost)      // generic path: one partial row sum per bin + per-CTA scratch matrices
         return align_up((size_t)p * F * 16) + align_up((size_t)n_win * F * m * sizeof(double)) + align_up(transfer_generic_scratch_bytes(m)) + 256;
     // z table, row sums of the optimistic pass, per-matrix flags, list of flagged matrices, counter, |H|^2 staging (n_win, F, m, m)
-    return align_up((size_t)p * F * 16) + align_up((size_t)n_win * ns * m * sizeof(double)) + 2 * align_up((size_t)n_win * F * sizeof(int)) + 512 +
+    return align_up((size_t)p * F * 16) + k5_rowpart_bytes(n_win, ns, m) + 2 * align_up((size_t)n_win * F * sizeof(int)) + 512 +
            align_up((size_t)n_win * F * m * m * sizeof(double));
 }
 
@@ -213,7 +220,7 @@ size_t hs_transfer_ws_flag_offset(int n_win, int m, int p, int F) {
     if (m > kPadMaxHost) return (size_t)-1;
     int ns, sl;
     k5_segments(F, k5_groups(), &ns, &sl);
-    return align_up((size_t)p * F * 16) + align_up((size_t)n_win * ns * m * sizeof(double)) + 2 * align_up((size_t)n_win * F * sizeof(int));
+    return align_up((size_t)p * F * 16) + k5_rowpart_bytes(n_win, ns, m) + 2 * align_up((size_t)n_win * F * sizeof(int));
 }
 
 int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double fs, int n_win, int m, int p, void* d_H,
@@ -236,7 +243,7 @@ int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double 
     if (k5_mode < 0) { const char* e = getenv("HS_K5_PIVOT_ONLY"); k5_mode = (e && atoi(e)) ? 0 : 1; }
     int* bad_list = nullptr;
     if (m <= kPadMaxHost) {
-        const size_t rp = align_up((size_t)n_win * ns * m * sizeof(double));
+        const size_t rp = k5_rowpart_bytes(n_win, ns, m);
         const size_t fl = align_up((size_t)n_win * F * sizeof(int));
         unsigned char* q = ws + align_up((size_t)p * F * 16) + rp;
         bad = reinterpret_cast<int*>(q);
@@ -263,6 +270,7 @@ int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double 
     P.F = F;
     P.n_seg = ns;
     P.seg_len = sl;
+    P.per_cta = 0;
     { const char* e = getenv("HS_K5_FLIP"); P.flip = e ? atoi(e) : 0; }
     P.rowpart2 = nullptr;
     P.bad = bad;
@@ -289,7 +297,16 @@ int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double 
                 return set_error(HS_ERR_CUDA, "hs_transfer_dtf_f64: cannot create timing events");
             cudaEventRecord(g_ev[0], st);
         }
-        rc = (use_mma && transfer_mma_fits(p, ng, sl)) ? launch_transfer_mma(P, ng, st) : launch_transfer_dtf(P, ng, 1, st);
+        if (use_mma && transfer_mma_fits(p, ng, sl)) {
+            // balanced partition: a window may be covered by fewer CTAs than it has row-sum slots -> the slots start at zero
+            transfer_mma_partition(n_win, F, &P.per_cta, &P.n_seg);
+            ns = P.n_seg;
+            if (P.rowpart && cudaMemsetAsync(P.rowpart, 0, (size_t)n_win * ns * m * sizeof(double), st) != cudaSuccess)
+                return set_error(HS_ERR_CUDA, "hs_transfer_dtf_f64: memset failed");
+            rc = launch_transfer_mma(P, ng, st);
+        } else {
+            rc = launch_transfer_dtf(P, ng, 1, st);
+        }
         if (g_timing) {
             cudaEventRecord(g_ev[1], st);
             g_ev_valid = true;

@@ -40,6 +40,8 @@ struct K5Params {
     int* bad_count;         // number of flagged matrices
     int* bad_list;          // (n_win * F) compact list of flagged matrices (w * F + f), filled by the optimistic pass
     double verify_tol2;     // squared relative tolerance of the a-posteriori check
+    int per_cta;            // tensor-pipe kernel: matrices (w * F + f, contiguous range) per CTA; rowpart is then (n_win, n_seg, m)
+                            //    with slot = CTA index - first CTA of the window, n_seg = ceil(F / per_cta) + 1
     int dtf_fij;            // 1: P.dtf is a staging buffer laid out (n_win, F, m, m) -- one contiguous matrix per bin --
                             //    that launch_dtf_finalize transposes to the reference's (n_win, m, m, F)
 };
@@ -51,7 +53,8 @@ int lwr_grid(int n_win);
 int launch_lwr(const K4Params& P, int grid, cudaStream_t stream);
 int launch_ztable(const double* freqs, int F, int p, double fs, void* z, cudaStream_t stream);
 int launch_transfer_dtf(const K5Params& P, int ng, int mode, cudaStream_t stream);
-bool transfer_mma_fits(int p, int ng, int seg_len);       // shared memory for the coefficient planes of order p fits next to ng groups
+bool transfer_mma_fits(int p, int ng, int seg_len);
+void transfer_mma_partition(int n_win, int F, int* per_cta, int* slots);      // balanced split of the n_win * F matrices over the SMs       // shared memory for the coefficient planes of order p fits next to ng groups
 int launch_transfer_mma(const K5Params& P, int ng, cudaStream_t stream);      // optimistic pass on the FP64 tensor pipe (transfer_mma.cu)
 int launch_dtf_finalize(const double* stage, const double* rowpart, const int* bad, int n_win, int m, int F, int n_seg,
                         double* dtf_out, double* ffdtf_out, cudaStream_t stream);

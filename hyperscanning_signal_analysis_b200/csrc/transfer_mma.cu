@@ -403,15 +403,21 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
     x.gs = groups + gid;
     MmaGroupSmem* gs = x.gs;
     const int l64 = x.part * 32 + x.lane;
-    const int n_units = P.n_win * P.n_seg;
     const int n_planes = MmaSmem<T>::planes(p);
 
     // zero the coefficient planes once: padding rows / columns / the odd lag stay zero for every unit
     for (int e = threadIdx.x; e < n_planes * kPlaneD; e += NG * 64) coef[e] = 0.0;
 
-    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        const int w = unit / P.n_seg, seg = unit % P.n_seg;
-        const int f_begin = seg * P.seg_len, f_end = min(F, f_begin + P.seg_len);
+    // Balanced static partition: CTA c owns the matrices q = w * F + f in [c * per_cta, (c + 1) * per_cta): every CTA gets the
+    // same count (+-1 round of NG), and a window's coefficients are loaded once per PIECE (= the part of a window inside the range).
+    const long long q_total = (long long)P.n_win * F;
+    long long q = (long long)blockIdx.x * P.per_cta;
+    const long long q_end = min(q_total, q + (long long)P.per_cta);
+    while (q < q_end) {
+        const int w = (int)(q / F);
+        const int f_begin = (int)(q - (long long)w * F);
+        const int f_end = (int)min((long long)F, f_begin + (q_end - q));
+        q += f_end - f_begin;
         __syncthreads();
         {   // AR coefficients of window w -> shared, layout [lag pair][row][col][lag & 1]
             const double* Aw = P.A + (size_t)w * m * m * p;
@@ -433,10 +439,6 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
                 }
             }
             for (int e = l64; e < 2 * kMP; e += 64) (&gs->rs[0][0])[e] = 0.0;
-            for (int e = threadIdx.x; e < (f_end - f_begin) * 2 * n_planes; e += NG * 64) {
-                const int fi = e / (2 * n_planes), k = e - fi * (2 * n_planes);
-                zs[e] = (k < p) ? P.z[(size_t)k * F + f_begin + fi] : make_double2(0.0, 0.0);
-            }
         }
         __syncthreads();
         // probe[i][k] = sum_j A_k[i][j] u_j : the window-dependent part of v = A(f) u = u - sum_k z_k(f) probe[.][k]
@@ -460,18 +462,28 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
             const long long until = clock64() + (long long)(gid >> 1) * (P.flip & 0xfffff);
             while (clock64() < until) { }
         }
+        // z_k(f) of the group's current bin: a private 2 * n_planes slot in shared memory, filled from the (L2-resident) table by the
+        // lanes l64 < 2 * n_planes, which fetch the NEXT bin's values one matrix ahead
+        double2* zg = zs + gid * 2 * n_planes;
+        auto z_fetch = [&](const int f) {
+            return (l64 < p && f < f_end) ? P.z[(size_t)l64 * F + f] : make_double2(0.0, 0.0);
+        };
+        double2 z_next = z_fetch(f_begin + gid);
         for (int f = f_begin + gid; f < f_end; f += NG) {
             double c[T][T][2];
+            mma_group_sync(x);                      // previous matrix' check / epilogue is done with zg, vfull, wpart, X
+            if (l64 < 2 * n_planes) zg[l64] = z_next;
+            z_next = z_fetch(f + NG);
+            mma_group_sync(x);
             // ---- v = A(f) u for the check (thread l64 < 40 owns entry l64)
             const int vi = min(l64, kMP - 1);
             double2 vacc = (l64 < m) ? probe_u2(l64) : make_double2(0.0, 0.0);
             for (int k = 0; k < p; ++k) {
-                const double2 zz = zs[(f - f_begin) * 2 * n_planes + k];
+                const double2 zz = zg[k];
                 const double2 q0 = probe[vi * p + k];
                 vacc.x = fma(-q0.x, zz.x, fma(q0.y, zz.y, vacc.x));
                 vacc.y = fma(-q0.x, zz.y, fma(-q0.y, zz.x, vacc.y));
             }
-            mma_group_sync(x);                      // previous matrix' check / epilogue is done with vfull, wpart, X
             if (l64 < kMP) gs->vfull[l64] = vacc;
             if (l64 == 0) gs->flag = 0;
             // ---- A(f) = I - sum_k A_k z_k(f)
@@ -483,8 +495,8 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
                         c[ta][tb][0] = ((ta == tb && x.g4 == 2 * x.t4 && x.part == 0) ? 4.0 : 0.0) + 1e-3 * (x.lane + ta - tb + f);
                         c[ta][tb][1] = ((ta == tb && x.g4 == 2 * x.t4 + 1 && x.part == 0) ? 4.0 : 0.0) + 1e-3 * (x.lane - ta + tb);
                     }
-            } else if (n_planes == 4) mma_assemble<T, 4>(c, coef, zs + (f - f_begin) * 2 * n_planes, n_planes, x);
-            else mma_assemble<T, 0>(c, coef, zs + (f - f_begin) * 2 * n_planes, n_planes, x);
+            } else if (n_planes == 4) mma_assemble<T, 4>(c, coef, zg, n_planes, x);
+            else mma_assemble<T, 0>(c, coef, zg, n_planes, x);
             if (P.Af) mma_store_generic<T, false>(c, P, w, f, x);
             // ---- blocked Gauss-Jordan on the tensor pipe
             mma_gauss_jordan<T, ADJ>(c, m, x);
@@ -568,12 +580,13 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
                 }
             }
         }
-        // ---- per-unit row sums (fixed summation order -> deterministic)
+        // ---- row sums of the piece (fixed summation order -> deterministic); slot = CTA index - first CTA of the window
         __syncthreads();
         if (P.rowpart && threadIdx.x < m) {
             double acc = 0.0;
-            for (int q = 0; q < NG; ++q) acc += groups[q].rs[0][threadIdx.x] + groups[q].rs[1][threadIdx.x];
-            P.rowpart[((size_t)w * P.n_seg + seg) * m + threadIdx.x] = acc;
+            for (int g2 = 0; g2 < NG; ++g2) acc += groups[g2].rs[0][threadIdx.x] + groups[g2].rs[1][threadIdx.x];
+            const int slot = (int)blockIdx.x - (int)(((long long)w * F) / P.per_cta);
+            P.rowpart[((size_t)w * P.n_seg + slot) * m + threadIdx.x] = acc;
         }
     }
 }
@@ -586,13 +599,24 @@ int launch_mma_t(const K5Params& P, int sm_count, cudaStream_t stream) {
     auto kern = (adj && T == 5 && NG == 6) ? transfer_mma_kernel<T, NG, (T == 5 && NG == 6)> : transfer_mma_kernel<T, NG, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "transfer_mma: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
-    const int n_units = P.n_win * P.n_seg;
-    const int grid = n_units < sm_count ? n_units : sm_count;
+    const long long q_total = (long long)P.n_win * P.F;
+    const int grid = (int)((q_total + P.per_cta - 1) / P.per_cta);
     kern<<<grid, NG * 64, smem, stream>>>(P);
     return check_launch("transfer_mma_kernel");
 }
 
 }  // namespace
+
+void transfer_mma_partition(int n_win, int F, int* per_cta, int* slots) {
+    const long long total = (long long)n_win * F;
+    int sm = device_sm_count();
+    if (sm < 1) sm = 148;
+    long long per = (total + sm - 1) / sm;
+    per = (per + 5) / 6 * 6;                     // whole rounds of the 6 groups
+    if (per < 6) per = 6;
+    *per_cta = (int)per;
+    *slots = (int)((F + per - 1) / per) + 1;
+}
 
 bool transfer_mma_fits(int p, int ng, int seg_len) { return ng >= 4 && ng <= 6 && MmaSmem<5>::total(p, ng, seg_len) <= 227 * 1024; }
 

@@ -299,7 +299,7 @@ int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double 
         }
         if (use_mma && transfer_mma_fits(p, ng, sl)) {
             // balanced partition: a window may be covered by fewer CTAs than it has row-sum slots -> the slots start at zero
-            transfer_mma_partition(n_win, F, &P.per_cta, &P.n_seg);
+            transfer_mma_partition(n_win, F, &P.per_cta, &P.n_seg, ng);
             ns = P.n_seg;
             if (P.rowpart && cudaMemsetAsync(P.rowpart, 0, (size_t)n_win * ns * m * sizeof(double), st) != cudaSuccess)
                 return set_error(HS_ERR_CUDA, "hs_transfer_dtf_f64: memset failed");

@@ -607,13 +607,13 @@ int launch_mma_t(const K5Params& P, int sm_count, cudaStream_t stream) {
 
 }  // namespace
 
-void transfer_mma_partition(int n_win, int F, int* per_cta, int* slots) {
+void transfer_mma_partition(int n_win, int F, int* per_cta, int* slots, int ng) {
     const long long total = (long long)n_win * F;
     int sm = device_sm_count();
     if (sm < 1) sm = 148;
     long long per = (total + sm - 1) / sm;
-    per = (per + 5) / 6 * 6;                     // whole rounds of the 6 groups
-    if (per < 6) per = 6;
+    per = (per + ng - 1) / ng * ng;              // whole rounds of the ng groups
+    if (per < ng) per = ng;
     *per_cta = (int)per;
     *slots = (int)((F + per - 1) / per) + 1;
 }

@@ -556,7 +556,132 @@ __global__ void __launch_bounds__(576, 1) lagcov_kernel(const K3Params P) {
         }
 }
 
+// -------------------------------------------------------------------------------------
+// K3 on the FP64 tensor pipe (m <= 40, 5 (p+1) <= 96 output column tiles, window fits in shared memory).
+//   R(L)[i][j] = scale * sum_t x_i(t) x_j(t + L)  is, for all lags at once, the product  X (40 x n) . [X_0 | X_1 | ... | X_p]^T
+//   where X_L is X shifted by L samples: one channel-major copy of the window in shared memory (zero padded by p + 3
+//   samples, so the upper summation limit n - 1 - L needs no test) serves every operand.
+//   mma.m8n8k4:  A fragment = x[8 ta + g4][t0 + t4],  B fragment = x[8 tb + g4][t0 + t4 + L]  -- both plain 8-byte loads, conflict
+//   free because the row stride is = 4 (mod 16) doubles.  One warp owns three of the 5 (p+1) column tiles (lag, tb) for all
+//   row tiles: 8 fragment loads per 15 DMMAs.  The DFMA kernel above issues 25 three-operand DFMAs (2.47 cycles each) + 10 LDS
+//   per k step and lag; this form needs 1/8 of the issue slots and leaves the pipe to the DMMAs.
+// -------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void dmma884_k3(double& c0, double& c1, const double a, const double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int KC>      // column tiles per warp: 3 (up to 48 column tiles with 16 warps), 6 (up to 96)
+__global__ void __launch_bounds__(512, 1) lagcov_mma_kernel(const K3Params P, const int ld) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* xs = reinterpret_cast<double*>(smem_raw);                 // [40][ld], channel-major, zero padded
+    const int m = P.m, n = P.n, p = P.p;
+    const int w = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int g4 = lane >> 2, t4 = lane & 3;
+    const int TA = (m + 7) >> 3;                                        // row / column tiles actually populated
+    const int n_cols = TA * (p + 1);
+    const double scale = 1.0 / ((double)n * (double)P.trials);
+    // zero the padding once: columns n .. ld-1 of every row, and rows m .. 8 TA - 1 completely
+    for (int e = threadIdx.x; e < kPadMax * ld; e += blockDim.x) {
+        const int r = e / ld, c = e - r * ld;
+        if (r >= m || c >= n) xs[e] = 0.0;
+    }
+    // this warp's column tiles
+    int lag[KC], tb[KC];
+    bool okc[KC];
+#pragma unroll
+    for (int u = 0; u < KC; ++u) {
+        const int c = warp * KC + u;
+        okc[u] = c < n_cols;
+        lag[u] = okc[u] ? c / TA : 0;
+        tb[u] = okc[u] ? c - lag[u] * TA : 0;
+    }
+    double acc[kTileMax][KC][2];
+#pragma unroll
+    for (int ta = 0; ta < kTileMax; ++ta)
+#pragma unroll
+        for (int u = 0; u < KC; ++u) acc[ta][u][0] = acc[ta][u][1] = 0.0;
+
+    for (int tr = 0; tr < P.trials; ++tr) {
+        const double* xu = P.x + P.offsets[(size_t)w * P.trials + tr];
+        __syncthreads();                                               // previous trial's products are done with xs
+        for (int r = warp; r < m; r += nwarps) {                       // one warp per channel row: coalesced
+            const double* src = xu + (size_t)r * P.ch_stride;
+            double* dst = xs + (size_t)r * ld;
+            for (int t0 = lane; t0 < n; t0 += 8 * 32) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = (t0 + 32 * u < n) ? src[t0 + 32 * u] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (t0 + 32 * u < n) dst[t0 + 32 * u] = v[u];
+            }
+        }
+        __syncthreads();
+        if (okc[0]) {
+            const double* pa = xs + (size_t)g4 * ld + t4;
+            int ob[KC];                                               // element offsets of the B fragments (invalid tiles read tile 0: harmless)
+#pragma unroll
+            for (int u = 0; u < KC; ++u) ob[u] = (8 * tb[u] + g4) * ld + t4 + lag[u];
+            const int row8 = 8 * ld;
+#pragma unroll(KC == 3 ? 4 : 1)
+            for (int t0 = 0; t0 < n; t0 += 4) {
+                double a[kTileMax];
+#pragma unroll
+                for (int ta = 0; ta < kTileMax; ++ta) a[ta] = (ta < TA) ? pa[ta * row8 + t0] : 0.0;
+                double b[KC];
+#pragma unroll
+                for (int u = 0; u < KC; ++u) b[u] = xs[ob[u] + t0];
+#pragma unroll
+                for (int ta = 0; ta < kTileMax; ++ta) {
+                    if (ta < TA) {
+#pragma unroll
+                        for (int u = 0; u < KC; ++u) dmma884_k3(acc[ta][u][0], acc[ta][u][1], a[ta], b[u]);
+                    }
+                }
+            }
+        }
+    }
+    // R[w][lag][i][j],  i = 8 ta + g4,  j = 8 tb + 2 t4 + {0, 1}
+#pragma unroll
+    for (int u = 0; u < KC; ++u) {
+        if (!okc[u]) continue;
+        double* Rl = P.R + ((size_t)w * (p + 1) + lag[u]) * m * m;
+        const int j = 8 * tb[u] + 2 * t4;
+#pragma unroll
+        for (int ta = 0; ta < kTileMax; ++ta) {
+            const int i = 8 * ta + g4;
+            if (ta < TA && i < m) {
+                if (j < m) Rl[(size_t)i * m + j] = acc[ta][u][0] * scale;
+                if (j + 1 < m) Rl[(size_t)i * m + j + 1] = acc[ta][u][1] * scale;
+            }
+        }
+    }
+}
+
+static int lagcov_mma_ld(int n, int p) {
+    int ld = n + p + 4;                        // fragments read up to column (n - 4) + 3 + p
+    ld += (4 - ld % 16 + 16) % 16;             // = 4 (mod 16) doubles: the 32 lanes of a fragment load hit 32 distinct banks
+    return ld;
+}
+
 int launch_lagcov(const K3Params& P, cudaStream_t stream) {
+    static const bool legacy = [] { const char* e = getenv("HS_K3_LEGACY"); return e && e[0] == '1'; }();
+    if (!legacy && P.m <= kPadMax) {
+        const int ld = lagcov_mma_ld(P.n, P.p);
+        const size_t smem_mma = (size_t)kPadMax * ld * sizeof(double);
+        const int n_cols = ((P.m + 7) / 8) * (P.p + 1);
+        if (smem_mma <= 220 * 1024 && n_cols <= 96) {
+            const int kc = n_cols <= 48 ? 3 : 6;
+            const int nwarps = (n_cols + kc - 1) / kc;
+            auto kern = kc == 3 ? lagcov_mma_kernel<3> : lagcov_mma_kernel<6>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
+            if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "lagcov: %s", cudaGetErrorString(e));
+            kern<<<P.n_win, nwarps * 32, smem_mma, stream>>>(P, ld);
+            return check_launch("lagcov_mma_kernel");
+        }
+    }
     int ng = P.p + 1;
     if (ng > 9) ng = 9;
     const size_t smem = ((size_t)(kK3Chunk + P.p) + kK3Chunk) * kK3Ld * sizeof(double);

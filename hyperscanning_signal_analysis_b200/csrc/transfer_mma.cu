@@ -76,7 +76,7 @@ struct __align__(16) MmaGroupSmem {
 };
 
 struct MmaCtx {
-    int part, lane, g4, t4, bar;
+    int part, lane, g4, t4, bar, dbg;
     MmaGroupSmem* gs;
 };
 
@@ -142,7 +142,8 @@ __device__ __forceinline__ void mma_inverse4(const MmaCtx& x, const int K0, cons
 //      the determinant follows from one round of shuffles (det = sum_c D[0][c] adj[c][0]), then ONE reciprocal.
 //      Dependent depth ~20 FP64 instructions and 1 shuffle round, against 4 x (shuffle round + reciprocal chain) for the
 //      in-place elimination above; no pivot order inside the block, so small leading minors of D are harmless.
-__device__ __forceinline__ void mma_inverse4_adj(const MmaCtx& x, const int K0, const int buf) {
+template <bool SCALED>      // SCALED: P = adj / det in shared memory;  otherwise P = adj and the caller applies 1 / det (returned in det)
+__device__ __forceinline__ void mma_inverse4_adj(const MmaCtx& x, const int K0, const int buf, double2& det) {
     MmaGroupSmem* gs = x.gs;
     const int i = (x.lane >> 2) & 3, j = x.lane & 3;
     const double* Dr = gs->u.p.Craw[buf][0] + K0 * 4;
@@ -174,15 +175,20 @@ __device__ __forceinline__ void mma_inverse4_adj(const MmaCtx& x, const int K0, 
     const double b3r = __shfl_sync(0xffffffffu, cr, 12, 16), b3i = __shfl_sync(0xffffffffu, ci, 12, 16);
     const double detr = (fma(d0r, b0r, -d0i * b0i) + fma(d1r, b1r, -d1i * b1i)) + (fma(d2r, b2r, -d2i * b2i) + fma(d3r, b3r, -d3i * b3i));
     const double deti = (fma(d0r, b0i, d0i * b0r) + fma(d1r, b1i, d1i * b1r)) + (fma(d2r, b2i, d2i * b2r) + fma(d3r, b3i, d3i * b3r));
-    const double y = rcp_newton2(fma(detr, detr, deti * deti));
-    const double ivr = detr * y, ivi = -deti * y;                      // 1 / det
-    const double pr = fma(cr, ivr, -ci * ivi), pi = fma(cr, ivi, ci * ivr);
-    if (x.lane < 16) gs->u.p.P[x.part][x.lane] = make_double2(pr, pi);
+    det = make_double2(detr, deti);
+    if (SCALED) {
+        const double y = rcp_newton2(fma(detr, detr, deti * deti));
+        const double ivr = detr * y, ivi = -deti * y;                      // 1 / det
+        const double pr = fma(cr, ivr, -ci * ivi), pi = fma(cr, ivi, ci * ivr);
+        if (x.lane < 16) gs->u.p.P[x.part][x.lane] = make_double2(pr, pi);
+    } else {
+        if (x.lane < 16) gs->u.p.P[x.part][x.lane] = make_double2(cr, ci);
+    }
     __syncwarp();
 }
 
 // ---- the two block steps of tile t (h = 0, 1): hand-over of the panel, 4 x 4 inverse, L panel by DMMA, rank-4 update
-template <int T, int t, bool ADJ>
+template <int T, int t, int ADJ>
 __device__ __forceinline__ void mma_tile_steps(double (&c)[T][T][2], const int m, const MmaCtx& x) {
     MmaGroupSmem* gs = x.gs;
     const int fo = x.g4 * 4 + x.t4;           // A-fragment offset inside a tile row
@@ -193,7 +199,12 @@ __device__ __forceinline__ void mma_tile_steps(double (&c)[T][T][2], const int m
         if (K0 >= m) break;
         mma_extract<T, t>(c, h, x);
         mma_group_sync(x);
-        if (ADJ) mma_inverse4_adj(x, K0, h);
+        double2 det = make_double2(1.0, 0.0);      // ADJ == 2: P holds adj(D), L comes out multiplied by det and U is divided by it below
+        if (x.dbg & 1) {      // experiment: no 4 x 4 inverse (timing only, results are wrong)
+            if (x.lane < 16) gs->u.p.P[x.part][x.lane] = make_double2((x.lane % 5 == 0) ? 1.0 : 0.0, 0.0);
+            __syncwarp();
+        } else if (ADJ == 2) mma_inverse4_adj<false>(x, K0, h, det);
+        else if (ADJ == 1) mma_inverse4_adj<true>(x, K0, h, det);
         else mma_inverse4(x, K0, h);
         // B fragments of -P with Re/Im interleaved by output column:  n = 2j -> Re, n = 2j+1 -> Im
         double a0[T], a1[T];
@@ -215,8 +226,9 @@ __device__ __forceinline__ void mma_tile_steps(double (&c)[T][T][2], const int m
             // rows K of the panel: -L = P - I
             const double2 pk = gs->u.p.P[x.part][(x.g4 & 3) * 4 + x.t4];
             if ((x.g4 >> 2) == h) {
-                a0[t] = pk.x - (((x.g4 & 3) == x.t4) ? 1.0 : 0.0);
-                a1[t] = pk.y;
+                const bool dg = (x.g4 & 3) == x.t4;
+                a0[t] = pk.x - (dg ? (ADJ == 2 ? det.x : 1.0) : 0.0);
+                a1[t] = pk.y - ((ADJ == 2 && dg) ? det.y : 0.0);
             }
 #pragma unroll
             for (int ta = 0; ta < T; ++ta) a1[ta] = flip_sign(a1[ta], sgn);
@@ -230,6 +242,19 @@ __device__ __forceinline__ void mma_tile_steps(double (&c)[T][T][2], const int m
                 b0[tb] = Ua[8 * tb];
                 b1[tb] = Ub[8 * tb];
             }
+            if (ADJ == 2) {
+                // U / det: the reciprocal chain runs next to the L-panel DMMAs above instead of in front of them.
+                // (b0, b1) = (Re U, Im U) in the Re warp and (Im U, Re U) in the Im warp.
+                const double y = rcp_newton2(fma(det.x, det.x, det.y * det.y));
+                const double yr = det.x * y, yi = -det.y * y;
+#pragma unroll
+                for (int tb = 0; tb < T; ++tb) {
+                    const double ur = x.part ? b1[tb] : b0[tb], ui = x.part ? b0[tb] : b1[tb];
+                    const double sr = fma(ur, yr, -ui * yi), si = fma(ur, yi, ui * yr);
+                    b0[tb] = x.part ? si : sr;
+                    b1[tb] = x.part ? sr : si;
+                }
+            }
 #pragma unroll
             for (int ta = 0; ta < T; ++ta) {
 #pragma unroll
@@ -242,7 +267,7 @@ __device__ __forceinline__ void mma_tile_steps(double (&c)[T][T][2], const int m
     }
 }
 
-template <int T, int t, bool ADJ>
+template <int T, int t, int ADJ>
 __device__ __forceinline__ void mma_all_tiles(double (&c)[T][T][2], const int m, const MmaCtx& x) {
     if constexpr (t < T) {
         mma_tile_steps<T, t, ADJ>(c, m, x);
@@ -251,7 +276,7 @@ __device__ __forceinline__ void mma_all_tiles(double (&c)[T][T][2], const int m,
 }
 
 // in-place inverse of the matrix held by the two warps of the group
-template <int T, bool ADJ>
+template <int T, int ADJ>
 __device__ __forceinline__ void mma_gauss_jordan(double (&c)[T][T][2], const int m, const MmaCtx& x) {
     mma_group_sync(x);                 // previous users of the panel buffers (assembly exchange) are done
     mma_all_tiles<T, 0, ADJ>(c, m, x);
@@ -384,7 +409,7 @@ struct MmaSmem {
     }
 };
 
-template <int T, int NG, bool ADJ>
+template <int T, int NG, int ADJ>
 __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int m = P.m, p = P.p, F = P.F;
@@ -400,6 +425,7 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
     x.t4 = x.lane & 3;
     const int gid = warp >> 1;
     x.bar = 1 + gid;
+    x.dbg = (P.flip >> 27) & 1;
     x.gs = groups + gid;
     MmaGroupSmem* gs = x.gs;
     const int l64 = x.part * 32 + x.lane;
@@ -595,8 +621,12 @@ template <int T, int NG>
 int launch_mma_t(const K5Params& P, int sm_count, cudaStream_t stream) {
     const size_t smem = MmaSmem<T>::total(P.p, NG, P.seg_len);
     if (smem > 227 * 1024) return set_error(HS_ERR_UNSUPPORTED, "transfer_mma: model order %d needs %zu B shared memory", P.p, smem);
-    static const bool adj = [] { const char* e = getenv("HS_K5_ADJ"); return !(e && e[0] == '0'); }();      // 4 x 4 pivot-block inverse by cofactors
-    auto kern = (adj && T == 5 && NG == 6) ? transfer_mma_kernel<T, NG, (T == 5 && NG == 6)> : transfer_mma_kernel<T, NG, false>;
+    // 4 x 4 pivot-block inverse: 1 (default) cofactors; 2 cofactors with the division by det deferred to the U panel (measured
+    // slower: 5.49 vs 5.24 ms, the 20 extra FP64 instructions per lane and step sit in front of the 50 update DMMAs); 0 in-place elimination
+    static const int adj = [] { const char* e = getenv("HS_K5_ADJ"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1; }();
+    constexpr bool kMain = (T == 5 && NG == 6);
+    auto kern = (adj == 2 && kMain) ? transfer_mma_kernel<T, NG, kMain ? 2 : 0>
+              : (adj == 1 && kMain) ? transfer_mma_kernel<T, NG, kMain ? 1 : 0> : transfer_mma_kernel<T, NG, 0>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "transfer_mma: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
     const long long q_total = (long long)P.n_win * P.F;

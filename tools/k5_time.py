@@ -26,6 +26,9 @@ sp = torch.cuda.current_stream().cuda_stream
 _lib.check(lib.hs_lagcov_f64(x_d.data_ptr(), st_d.data_ptr(), T, n_win, 1, M, WIN, P, R.data_ptr(), sp), "lagcov")
 _lib.check(lib.hs_yw_solve_f64(R.data_ptr(), n_win, M, P, A.data_ptr(), V.data_ptr(), None, status.data_ptr(), yw_ws.data_ptr(), sp), "yw")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+import ctypes as C
+lib.hs_timing_enable(1)
+ks = []
 ts = []
 for i in range(reps + 2):
     flush.zero_()
@@ -34,9 +37,12 @@ for i in range(reps + 2):
     _lib.check(lib.hs_transfer_dtf_f64(A.data_ptr(), fr_d.data_ptr(), F, FS, n_win, M, P, None, None, out.data_ptr(), None,
                                        status.data_ptr(), tr_ws.data_ptr(), sp), "transfer")
     b.record(); torch.cuda.synchronize()
-    if i >= 2: ts.append(a.elapsed_time(b))
+    if i >= 2:
+        ts.append(a.elapsed_time(b))
+        kms = C.c_double(0.0)
+        if lib.hs_timing_last_k5_ms(C.byref(kms)) == 0: ks.append(kms.value)
 off = lib.hs_transfer_ws_flag_offset(n_win, M, P, F)
 bad = int(tr_ws[off:off + 4].view(torch.int32).item())
 fl = bench.flops_per_window()["transfer"] * n_win
-print({"n_win": n_win, "ms": float(np.mean(ts)), "min_ms": float(np.min(ts)), "tflops": fl / (np.min(ts) * 1e-3) * 1e-12,
+print({"k5_kernel_ms": float(np.min(ks)) if ks else None, "n_win": n_win, "ms": float(np.mean(ts)), "min_ms": float(np.min(ts)), "tflops": fl / (np.min(ts) * 1e-3) * 1e-12,
        "flagged": bad, "status_max": int(status.max())})

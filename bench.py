@@ -292,9 +292,9 @@ def run_b200(args):
                 "peak_source": "hs_measure_dfma_tflops: register-only DFMA loop on all SMs, measured in this run; DMMA m8n8k4 peaks at the same "
                                "rate (tools/fp64_peak.cu). MEASURED_PEAKS.json has no FP64 figure (its hbm_gbs is %s)" % peaks.get("hbm_gbs"),
                 "flops_per_launch": fl["transfer"] * n_win, "ms_per_launch": k5_ms,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, ncu --set full on 296 windows (profiles/r01_k5_mma_ncu_summary.md:
-                # 29.7 MB + 823.1 MB), scaled to this launch's window count; algorithmic bytes: A (m*m*p*8) in, |H|^2 (m*m*F*8) out per window
-                "traffic": (29.743872e6 + 823.112704e6) * n_win / 296.0,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, ncu --set full on 599 windows (profiles/r01_k5_mma_ncu.txt:
+                # 72.6 MB + 1718.4 MB), scaled to this launch's window count; algorithmic bytes: A (m*m*p*8) in, |H|^2 (m*m*F*8) out per window
+                "traffic": (72.581888e6 + 1718.427e6) * n_win / 599.0,
                 "algorithmic_bytes_per_launch": n_win * (M * M * P * 8 + M * M * F * 8),
                 "algorithmic_flops_per_matrix": "4*p*m^2 + 8*m^3 (SURVEY 8d: assembly + complex LU/inverse as the reference computes it)",
                 "matrices_redone_with_pivoting": flagged,

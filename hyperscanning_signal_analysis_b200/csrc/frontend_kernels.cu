@@ -655,11 +655,19 @@ __global__ void __launch_bounds__(kDecThreads) fir_decimate_kernel(const double*
 constexpr size_t kPsdSmemMax = 200 * 1024;
 constexpr int kPsdThreads = 512;
 
+// Taper-pair groups per signal: CTAs = n_sig * groups run one per SM (the FFT buffer fills the shared memory), so the group
+// count is chosen to fill whole waves of 148 CTAs (342 segments: 1 group = 2.3 waves -> 3 rounds, 3 groups = 6.93 -> 7 rounds).
 static int psd_groups(int n_sig, int pairs) {
-    int g = (2 * 148 + n_sig - 1) / n_sig;      // aim for >= 2 CTAs per SM
-    if (g > pairs) g = pairs;
-    if (g < 1) g = 1;
-    return g;
+    const int sm = 148;            // sizing only (also used by the GPU-less workspace query); any SM count gives a valid split
+    int best = 1;
+    double best_eff = 0.0;
+    for (int g = 1; g <= 8 && g <= pairs; ++g) {
+        const double waves = (double)n_sig * g / sm;
+        const double rounds = (double)((long long)((n_sig * (long long)g + sm - 1) / sm));
+        const double eff = waves / rounds - 0.004 * g;      // small penalty: every CTA recomputes the mean and reloads the twiddles
+        if (eff > best_eff) { best_eff = eff; best = g; }
+    }
+    return best;
 }
 
 __global__ void twiddle_kernel(double2* w, long long n) {
@@ -685,6 +693,7 @@ struct PsdParams {
     long long n;
     int n1, n2, log2n2;      // n = n1 * n2, n2 = 2^log2n2
     int K, groups, k_lo, nb, n_sig;
+    int tw_in_smem;          // 1: the half twiddle table sits behind the FFT buffer in shared memory
 };
 
 __global__ void __launch_bounds__(kPsdThreads, 1) mt_psd_kernel(const PsdParams P) {
@@ -695,6 +704,9 @@ __global__ void __launch_bounds__(kPsdThreads, 1) mt_psd_kernel(const PsdParams 
     double* acc = reinterpret_cast<double*>(smem_raw);                       // [nb]
     double2* buf = P.gbuf ? (P.gbuf + (size_t)blockIdx.x * n)
                           : reinterpret_cast<double2*>(smem_raw + (((size_t)P.nb * sizeof(double) + 15) / 16) * 16);
+    double2* tws = P.tw_in_smem ? buf + n : nullptr;                         // W_n^j, j < n/2 (only with the shared-memory FFT buffer)
+    if (tws)
+        for (int e = threadIdx.x; e < (int)(n >> 1); e += kPsdThreads) tws[e] = P.tw[e];
     __shared__ double red[kPsdThreads];
     const double* xs = P.x + (size_t)sig * n;
     const int tid = threadIdx.x;
@@ -744,20 +756,44 @@ __global__ void __launch_bounds__(kPsdThreads, 1) mt_psd_kernel(const PsdParams 
             buf[e] = y;
         }
         __syncthreads();
-        // ---- step 3: n1 independent in-place radix-2 DIF FFTs of length n2 (32-bit index arithmetic, shifts only)
+        // ---- step 3: n1 independent in-place DIF FFTs of length n2 (32-bit index arithmetic, shifts only).  Two radix-2 stages
+        //      are fused into one radix-4 pass (same data placement as the two stages, so the bit-reversed read-out below is
+        //      unchanged): half the passes through shared memory and half the barriers; a single radix-2 stage is left over
+        //      when log2(n2) is odd.  Twiddles come from the shared-memory half table when it fits (tws), else from L2.
         {
-            const int ni = (int)n, half_n2_log = P.log2n2 - 1;
-            for (int s = P.log2n2 - 1; s >= 0; --s) {
-                const int half = 1 << s;
-                const int tw_mul = ni >> (s + 1);                       // W_(2 half)^j = W_n^(j * n / (2 half))
-                for (int q = tid; q < (ni >> 1); q += kPsdThreads) {
-                    const int sub = q >> half_n2_log;                   // which k1 sub-array
-                    const int r = q & ((n2 >> 1) - 1);
-                    const int blk = (r >> s) << (s + 1), j = r & (half - 1);
-                    double2* p = buf + (size_t)sub * n2 + blk + j;
-                    const double2 u = p[0], v = p[half];
+            const int ni = (int)n;
+            auto twid = [&](const int idx) -> double2 {
+                if (tws) {
+                    const int h = ni >> 1;
+                    const double2 v = tws[idx >= h ? idx - h : idx];
+                    return idx >= h ? make_double2(-v.x, -v.y) : v;             // W^(k + n/2) = -W^k
+                }
+                return P.tw[idx];
+            };
+            int s = P.log2n2 - 1;
+            for (; s >= 1; s -= 2) {
+                const int q4 = 1 << (s - 1);                                    // quarter of the block length L = 2^(s+1)
+                const int tw_mul = ni >> (s + 1);                               // W_L^j = W_n^(j * n / L)
+                for (int r = tid; r < (ni >> 2); r += kPsdThreads) {
+                    const int j = r & (q4 - 1);
+                    double2* p = buf + (((r >> (s - 1)) << (s + 1)) + j);
+                    const double2 a = p[0], b = p[q4], c = p[2 * q4], d = p[3 * q4];
+                    const double2 w1 = twid(j * tw_mul), w2 = twid(2 * j * tw_mul), w3 = twid(3 * j * tw_mul);
+                    const double2 apc = make_double2(a.x + c.x, a.y + c.y), amc = make_double2(a.x - c.x, a.y - c.y);
+                    const double2 bpd = make_double2(b.x + d.x, b.y + d.y), bmd = make_double2(b.x - d.x, b.y - d.y);
+                    p[0] = make_double2(apc.x + bpd.x, apc.y + bpd.y);
+                    p[q4] = cmul(make_double2(apc.x - bpd.x, apc.y - bpd.y), w2);
+                    p[2 * q4] = cmul(make_double2(amc.x + bmd.y, amc.y - bmd.x), w1);      // (a - c) - i (b - d)
+                    p[3 * q4] = cmul(make_double2(amc.x - bmd.y, amc.y + bmd.x), w3);      // (a - c) + i (b - d)
+                }
+                __syncthreads();
+            }
+            if (s == 0) {                                                       // last radix-2 stage: blocks of 2, twiddle 1
+                for (int r = tid; r < (ni >> 1); r += kPsdThreads) {
+                    double2* p = buf + 2 * r;
+                    const double2 u = p[0], v = p[1];
                     p[0] = make_double2(u.x + v.x, u.y + v.y);
-                    p[half] = cmul(make_double2(u.x - v.x, u.y - v.y), P.tw[j * tw_mul]);
+                    p[1] = make_double2(u.x - v.x, u.y - v.y);
                 }
                 __syncthreads();
             }
@@ -822,7 +858,12 @@ static int launch_mt_psd(const double* x, int n_sig, long long n, const double* 
     const size_t accb = (((size_t)P.nb * sizeof(double) + 15) / 16) * 16;
     size_t smem = accb + (size_t)n * 16;
     P.gbuf = nullptr;
-    if (smem > kPsdSmemMax) {
+    P.tw_in_smem = 0;
+    if (smem + (size_t)(n / 2) * 16 <= 220 * 1024 && (n & 1) == 0) {
+        smem += (size_t)(n / 2) * 16;
+        P.tw_in_smem = 1;
+    }
+    if (smem > kPsdSmemMax && !P.tw_in_smem) {
         P.gbuf = reinterpret_cast<double2*>(ws);
         smem = accb;
         if (smem > 200 * 1024) return set_error(HS_ERR_UNSUPPORTED, "hs_mt_psd_f64: too many bins requested");

@@ -181,6 +181,10 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
+    numa_cpus = None
+    if world > 1 and os.environ.get("HS_BENCH_NUMA", "1") != "0":
+        from hyperscanning_signal_analysis_b200 import sharding
+        numa_cpus = sharding.bind_to_gpu_numa(local)      # pinned e2e buffers of every rank on its GPU's NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
@@ -322,7 +326,8 @@ def run_b200(args):
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e = {"value": world * n_win * e2e_steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(y.nbytes + starts.nbytes + freqs.nbytes),
            "d2h_bytes_per_step": int(out_np.nbytes + 4 * n_win), "steps": e2e_steps,
-           "api": "mtmvar.FfdtfPlan.run -> hs_plan_mvar_ffdtf_host (chunked H2D/compute/D2H on 3 streams), host wall clock incl. final sync"}
+           "api": "mtmvar.FfdtfPlan.run -> hs_plan_mvar_ffdtf_host (chunked H2D/compute/D2H on 3 streams), host wall clock incl. final sync",
+           "host_numa_binding": ("rank bound to %d GPU-local CPUs" % len(numa_cpus)) if numa_cpus else "none"}
     assert abs(float(out_np[0].sum()) - M) < 1e-6
     plan.close()
     # PCIe ceiling of this box for the e2e number: one plain device -> pinned-host copy of the result (same buffers)

@@ -52,3 +52,31 @@ def all_gather_windows(local, counts: Sequence[int]):
 def unit_table(n_dyads: int, tasks: Sequence[str]) -> List[Tuple[int, str]]:
     """(dyad, task) units in the order run_pipeline visits them."""
     return [(d, t) for d in range(n_dyads) for t in tasks]
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin the calling process to the CPUs local to GPU ``device_index`` (sysfs ``local_cpulist`` of its PCI function), so that
+    pinned host buffers allocated afterwards (first touch) sit on the GPU's own NUMA node and the result stream of every rank
+    crosses its own root complex instead of the socket interconnect -- what ``numactl --cpunodebind`` does per rank in a
+    deployment.  Best effort: returns the CPU set, or None when the topology cannot be read (nothing is changed then)."""
+    import os
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device_index)
+        addr = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{addr}/local_cpulist") as fh:
+            text = fh.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None

@@ -363,10 +363,10 @@ int hs_spectra_f64(const void* d_H, const double* d_V, int n_win, int m, int F, 
 
 int hs_partial_coherence_f64(const void* d_S, int n_win, int m, int F, void* d_kappa, const double* d_ffdtf, double* d_ddtf,
                              int32_t* d_status, void* stream) {
+    if (n_win <= 0) return HS_OK;               // empty batch: nothing to do (and no buffers to point at)
     if (!d_S || !d_status || (!d_kappa && !d_ddtf)) return set_error(HS_ERR_INVALID, "hs_partial_coherence_f64: null pointer");
     if (d_ddtf && !d_ffdtf) return set_error(HS_ERR_INVALID, "hs_partial_coherence_f64: dDTF needs the ffDTF input");
     if (m < 1 || F < 1) return set_error(HS_ERR_INVALID, "hs_partial_coherence_f64: bad shape m=%d F=%d", m, F);
-    if (n_win <= 0) return HS_OK;
     return launch_pcoh(d_S, n_win, m, F, d_kappa, d_ffdtf, d_ddtf, d_status, (cudaStream_t)stream);
 }
 

@@ -337,3 +337,23 @@ def test_cfg2_full_size_properties(mv):
     for k, w in enumerate(sel.tolist()):
         seg = y[:, starts[w]:starts[w] + 512]
         assert relerr(ffh[k], mo.full_freq_dtf(seg, freqs, 256.0, optimal_model_order=8)) < TOL_MODEL
+
+
+def test_partial_coherence_batch_and_edges(mv):
+    import torch
+    rng = np.random.default_rng(3)
+    # batched call == per-matrix calls; F = 1; m = 2 .. 9 (every tile count below the dyad's)
+    for m in (2, 3, 8, 9):
+        H = rng.standard_normal((m, m, 5)) + 1j * rng.standard_normal((m, m, 5))
+        S = np.einsum("ikf,jkf->ijf", H, H) + np.eye(m)[:, :, None] * 0.1          # H H^T: complex symmetric like the reference's spectra
+        ref = mo.partial_coherence(S)
+        assert relerr(mv.partial_coherence(S), ref) < TOL_MODEL
+        assert relerr(mv.partial_coherence(S[:, :, :1]), ref[:, :, :1]) < TOL_MODEL
+    S2 = torch.from_numpy(np.stack([S, 2.0 * S])).cuda()
+    k, dd, st = mv.batched_partial_coherence(S2, ffdtf=torch.ones((2, 9, 9, 5), dtype=torch.float64, device="cuda"))
+    assert int(st.max()) == 0
+    assert relerr(k[0].cpu().numpy(), ref) < TOL_MODEL and relerr(k[1].cpu().numpy(), ref) < TOL_MODEL      # scale invariant
+    assert relerr(dd[0].cpu().numpy(), np.abs(ref)) < TOL_MODEL                                              # ffDTF = 1 -> dDTF = |kappa|
+    # empty batch
+    k0, _, st0 = mv.batched_partial_coherence(torch.empty((0, 4, 4, 3), dtype=torch.complex128, device="cuda"))
+    assert k0.shape == (0, 4, 4, 3) and st0.numel() == 0

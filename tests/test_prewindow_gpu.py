@@ -102,3 +102,36 @@ def test_downsample_crop_zscore_and_whole_stage(pl):
     from oracle import mvar_oracle as mo
     ref = mo.full_freq_dtf(g["signals_to_ffDTF"][:, :160], res["freqs"], 8.0, optimal_model_order=5)
     assert relerr(res["ff_dtf_windowed"][0], ref) < 1e-6
+
+
+def test_prewindow_edge_cases(pl, fe):
+    import torch
+    rng = np.random.default_rng(11)
+    fs = 128.0
+    # shortest signal sosfiltfilt accepts: padlen + 1 = 28 samples (four sections)
+    x = rng.standard_normal((2, 28))
+    assert relerr(pl.alpha_bandpass_filter(x, fs), fo.alpha_bandpass(x, fs)) < TOL_SIGNAL
+    # a single section and a section with a zero a2 / b2 (padlen shrinks by one tap: scipy's ntaps correction)
+    sos1 = signal.butter(1, 0.3, output="sos")
+    y = rng.standard_normal((3, 50))
+    assert relerr(fe.sosfiltfilt(sos1, y), signal.sosfiltfilt(sos1, y, axis=-1)) < TOL_SIGNAL
+    # Hilbert: n = 1, n = 2, odd n, a prime length (generic radix) and an all-zero signal
+    for n in (1, 2, 3, 31, 97 * 2):
+        xs = rng.standard_normal((2, n))
+        if n == 97 * 2:
+            with pytest.raises(Exception):          # 97 > 31: no radix for it, the library says so instead of guessing
+                fe.hilbert_envelope_dev(torch.from_numpy(xs).cuda())
+            continue
+        got = fe.hilbert_envelope_dev(torch.from_numpy(xs).cuda()).cpu().numpy()
+        assert relerr(got, np.abs(signal.hilbert(xs, axis=-1))) < TOL_SIGNAL
+    z = fe.hilbert_envelope_dev(torch.zeros((1, 64), dtype=torch.float64, device="cuda"))
+    assert float(z.abs().max()) == 0.0
+    assert fe.hilbert_envelope_dev(torch.zeros((0, 64), dtype=torch.float64, device="cuda")).shape == (0, 64)
+    # resample_poly: length not a multiple of the factor, factor larger than the signal
+    for n, down in ((1001, 16), (10, 16), (17, 2)):
+        v = rng.standard_normal(n)
+        assert relerr(pl.downsample_signal(v, float(down), 1.0), signal.resample_poly(v, 1, down)) < TOL_SIGNAL
+    # z-score of a constant row is NaN, like NumPy's 0 / 0 in the reference (:719)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        zc = pl.zscore_rows(np.vstack([np.ones(8), np.arange(8.0)]))
+    assert np.isnan(zc[0]).all() and abs(zc[1].std() - 1.0) < 1e-12

@@ -558,7 +558,7 @@ static int run_sweep_d(int d, const IirPass& P, const IirCoef& c, cudaStream_t s
 // consecutive positions.  With jj = ntaps-1-j:  y[o] = sum_r sum_u b[ntaps-1-(q u + r)] * S_r[o + u]:  a thread owns 4
 // consecutive outputs and slides a 4-register window along S_r (1 shared load per 4 FMAs).  Positions are skewed by
 // pos + (pos >> kDecSkewShift) so the 32 B-strided window loads of a half-warp hit distinct banks.
-constexpr int kDecThreads = 256;
+constexpr int kDecThreads = 128;           // 512 outputs per CTA: 42 KB of staged input (q = 8), 5 CTAs/SM (256 threads: 2 CTAs/SM, 0.118 vs 0.107 ms)
 constexpr int kDecPer = 4;                 // (8 per thread with 128-thread CTAs measured 45 % slower: too few loads in flight)
 constexpr int kDecSkewShift = 2;           // pos + (pos >> 2): lanes 4 positions apart land in distinct banks
 constexpr int kDecOut = kDecThreads * kDecPer;

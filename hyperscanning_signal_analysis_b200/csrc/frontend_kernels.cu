@@ -694,6 +694,7 @@ struct PsdParams {
     int n1, n2, log2n2;      // n = n1 * n2, n2 = 2^log2n2
     int K, groups, k_lo, nb, n_sig;
     int tw_in_smem;          // 1: the half twiddle table sits behind the FFT buffer in shared memory
+    int skew;                // 1: FFT buffer in shared memory with the i + (i >> 3) layout
 };
 
 __global__ void __launch_bounds__(kPsdThreads, 1) mt_psd_kernel(const PsdParams P) {
@@ -704,7 +705,12 @@ __global__ void __launch_bounds__(kPsdThreads, 1) mt_psd_kernel(const PsdParams 
     double* acc = reinterpret_cast<double*>(smem_raw);                       // [nb]
     double2* buf = P.gbuf ? (P.gbuf + (size_t)blockIdx.x * n)
                           : reinterpret_cast<double2*>(smem_raw + (((size_t)P.nb * sizeof(double) + 15) / 16) * 16);
-    double2* tws = P.tw_in_smem ? buf + n : nullptr;                         // W_n^j, j < n/2 (only with the shared-memory FFT buffer)
+    // Shared-memory layout of the FFT buffer: element i sits at i + (i >> 3) (one 16-byte pad per 128-byte row), so the strided
+    // accesses of the late stages (stride 4, 16, ... elements) and the bit-reversed read-out spread over the banks
+    // (61 % of the wavefronts were bank-conflict replays without it).  No skew for the global-memory fallback.
+    const int skew = P.skew;
+    auto sk = [skew](const long long i) -> long long { return skew ? i + (i >> 3) : i; };
+    double2* tws = P.tw_in_smem ? buf + (n + (n >> 3) + 1) : nullptr;        // W_n^j, j < n/2 (only with the shared-memory FFT buffer)
     if (tws)
         for (int e = threadIdx.x; e < (int)(n >> 1); e += kPsdThreads) tws[e] = P.tw[e];
     __shared__ double red[kPsdThreads];
@@ -753,7 +759,7 @@ __global__ void __launch_bounds__(kPsdThreads, 1) mt_psd_kernel(const PsdParams 
                 }
                 y = cmul(make_double2(yr, yi), P.tw[((long long)t2 * k1) % n]);
             }
-            buf[e] = y;
+            buf[sk(e)] = y;
         }
         __syncthreads();
         // ---- step 3: n1 independent in-place DIF FFTs of length n2 (32-bit index arithmetic, shifts only).  Two radix-2 stages
@@ -776,21 +782,25 @@ __global__ void __launch_bounds__(kPsdThreads, 1) mt_psd_kernel(const PsdParams 
                 const int tw_mul = ni >> (s + 1);                               // W_L^j = W_n^(j * n / L)
                 for (int r = tid; r < (ni >> 2); r += kPsdThreads) {
                     const int j = r & (q4 - 1);
-                    double2* p = buf + (((r >> (s - 1)) << (s + 1)) + j);
-                    const double2 a = p[0], b = p[q4], c = p[2 * q4], d = p[3 * q4];
+                    const int e0 = ((r >> (s - 1)) << (s + 1)) + j;
+                    double2* pa = buf + sk(e0);
+                    double2* pb = buf + sk(e0 + q4);
+                    double2* pc = buf + sk(e0 + 2 * q4);
+                    double2* pd = buf + sk(e0 + 3 * q4);
+                    const double2 a = *pa, b = *pb, c = *pc, d = *pd;
                     const double2 w1 = twid(j * tw_mul), w2 = twid(2 * j * tw_mul), w3 = twid(3 * j * tw_mul);
                     const double2 apc = make_double2(a.x + c.x, a.y + c.y), amc = make_double2(a.x - c.x, a.y - c.y);
                     const double2 bpd = make_double2(b.x + d.x, b.y + d.y), bmd = make_double2(b.x - d.x, b.y - d.y);
-                    p[0] = make_double2(apc.x + bpd.x, apc.y + bpd.y);
-                    p[q4] = cmul(make_double2(apc.x - bpd.x, apc.y - bpd.y), w2);
-                    p[2 * q4] = cmul(make_double2(amc.x + bmd.y, amc.y - bmd.x), w1);      // (a - c) - i (b - d)
-                    p[3 * q4] = cmul(make_double2(amc.x - bmd.y, amc.y + bmd.x), w3);      // (a - c) + i (b - d)
+                    *pa = make_double2(apc.x + bpd.x, apc.y + bpd.y);
+                    *pb = cmul(make_double2(apc.x - bpd.x, apc.y - bpd.y), w2);
+                    *pc = cmul(make_double2(amc.x + bmd.y, amc.y - bmd.x), w1);            // (a - c) - i (b - d)
+                    *pd = cmul(make_double2(amc.x - bmd.y, amc.y + bmd.x), w3);            // (a - c) + i (b - d)
                 }
                 __syncthreads();
             }
             if (s == 0) {                                                       // last radix-2 stage: blocks of 2, twiddle 1
                 for (int r = tid; r < (ni >> 1); r += kPsdThreads) {
-                    double2* p = buf + 2 * r;
+                    double2* p = buf + sk(2 * r);                               // 2 r and 2 r + 1 share a row of 8: adjacent
                     const double2 u = p[0], v = p[1];
                     p[0] = make_double2(u.x + v.x, u.y + v.y);
                     p[1] = make_double2(u.x - v.x, u.y - v.y);
@@ -801,8 +811,8 @@ __global__ void __launch_bounds__(kPsdThreads, 1) mt_psd_kernel(const PsdParams 
         // ---- power of both tapers at the requested bins; X[k1 + n1 k2] sits at buf[k1 * n2 + bitrev(k2)]
         for (int b = tid; b < P.nb; b += kPsdThreads) {
             const long long k = P.k_lo + b, km = (n - k) % n;
-            const double2 z = buf[(k % n1) * (long long)n2 + bitrev_bits((unsigned)(k / n1), P.log2n2)];
-            const double2 zm = buf[(km % n1) * (long long)n2 + bitrev_bits((unsigned)(km / n1), P.log2n2)];
+            const double2 z = buf[sk((k % n1) * (long long)n2 + bitrev_bits((unsigned)(k / n1), P.log2n2))];
+            const double2 zm = buf[sk((km % n1) * (long long)n2 + bitrev_bits((unsigned)(km / n1), P.log2n2))];
             const double sr = z.x + zm.x, si = z.y - zm.y;          // Z[k] + conj Z[n-k]  = 2 X_a[k]
             const double dr = z.x - zm.x, di = z.y + zm.y;          // Z[k] - conj Z[n-k]  = 2 i X_b[k]
             const double pa = 0.25 * fma(sr, sr, si * si), pb = 0.25 * fma(dr, dr, di * di);
@@ -856,14 +866,22 @@ static int launch_mt_psd(const double* x, int n_sig, long long n, const double* 
     // NOTE: sized with (n/2+1) bins per partial spectrum in hs_mt_psd_ws_bytes
     ws += ((size_t)n_sig * P.groups * (n / 2 + 1) * sizeof(double) + 255) / 256 * 256;
     const size_t accb = (((size_t)P.nb * sizeof(double) + 15) / 16) * 16;
-    size_t smem = accb + (size_t)n * 16;
+    const size_t buf_elems = (size_t)n + (size_t)(n >> 3) + 1;        // skewed layout: one pad element per row of 8
+    const size_t smem_plain = accb + (size_t)n * 16, smem_skew = accb + buf_elems * 16;
+    size_t smem;
     P.gbuf = nullptr;
     P.tw_in_smem = 0;
-    if (smem + (size_t)(n / 2) * 16 <= 220 * 1024 && (n & 1) == 0) {
-        smem += (size_t)(n / 2) * 16;
+    P.skew = 0;
+    if (smem_skew + (size_t)(n / 2) * 16 <= 220 * 1024 && (n & 1) == 0) {       // skewed buffer + half twiddle table
+        smem = smem_skew + (size_t)(n / 2) * 16;
         P.tw_in_smem = 1;
-    }
-    if (smem > kPsdSmemMax && !P.tw_in_smem) {
+        P.skew = 1;
+    } else if (smem_skew <= kPsdSmemMax) {                                       // skewed buffer, twiddles from L2
+        smem = smem_skew;
+        P.skew = 1;
+    } else if (smem_plain <= kPsdSmemMax) {                                      // plain buffer
+        smem = smem_plain;
+    } else {                                                                     // FFT buffer in global memory
         P.gbuf = reinterpret_cast<double2*>(ws);
         smem = accb;
         if (smem > 200 * 1024) return set_error(HS_ERR_UNSUPPORTED, "hs_mt_psd_f64: too many bins requested");

@@ -33,6 +33,7 @@ SIGNATURES = {
     "hs_yw_assemble_f64": (c_int, [c_dp, c_int, c_int, c_int, c_dp, c_dp, c_dp]),
     "hs_yw_ws_bytes": (c_sz, [c_int, c_int, c_int]),
     "hs_yw_solve_f64": (c_int, [c_dp, c_int, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    "hs_mvar_criterion_f64": (c_int, [c_dp, c_int, c_int, c_int, c_int, c_int, c_dp, c_dp, c_dp, c_dp]),
     "hs_ztable_f64": (c_int, [c_dp, c_int, c_int, c_dbl, c_dp, c_dp]),
     "hs_transfer_ws_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
     "hs_transfer_ws_flag_offset": (c_sz, [c_int, c_int, c_int, c_int]),
@@ -44,6 +45,14 @@ SIGNATURES = {
     "hs_plan_create": (c_int, [C.POINTER(C.c_void_p), c_int, c_int, c_int, c_int, c_int, c_i64]),
     "hs_plan_destroy": (None, [C.c_void_p]),
     "hs_plan_mvar_ffdtf_host": (c_int, [C.c_void_p, c_dp, c_i64, c_dp, c_int, c_dp, c_dbl, c_dp, c_dp]),
+    "hs_plan_host_result": (c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(c_sz)]),
+    "hs_set_compute_sm_limit": (c_int, [c_int]),
+    "hs_gather_push_f64": (c_int, [c_dp, c_i64, c_dp, C.POINTER(C.c_void_p), c_int, c_int, c_dp]),
+    "hs_gather_push_ce": (c_int, [c_dp, c_i64, C.POINTER(C.c_void_p), c_int, c_dp]),
+    "hs_ipc_alloc": (c_int, [C.POINTER(C.c_void_p), c_sz, C.c_char_p]),
+    "hs_ipc_open": (c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "hs_ipc_close": (c_int, [c_dp]),
+    "hs_ipc_free": (c_int, [c_dp]),
     "hs_filtfilt_ws_bytes": (c_sz, [c_int, c_i64]),
     "hs_iir_filtfilt_f64": (c_int, [c_dp, c_int, c_i64, c_i64, c_i64, c_dp, c_dp, c_int, c_int, c_int, c_dp, c_dp]),
     "hs_iir_lfilter_f64": (c_int, [c_dp, c_int, c_i64, c_i64, c_dp, c_dp, c_int, c_int, c_dp, c_i64, c_dp, c_dp]),

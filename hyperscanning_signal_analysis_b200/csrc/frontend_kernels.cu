@@ -950,7 +950,7 @@ static int iir_run(double* d_x, int n_sig, int64_t n, int64_t sig_stride, int64_
     ws += (((size_t)n_sig + 31) / 32 * 32 + (size_t)n_sig * kMeanParts) * sizeof(double) / 256 * 256 + 256;
     double* ppow_dev = reinterpret_cast<double*>(ws);
     static int tiled_mode = -1;      // HS_IIR_TILED=0 forces the thread-per-chunk kernels
-    if (tiled_mode < 0) { const char* ev = getenv("HS_IIR_TILED"); tiled_mode = (ev && atoi(ev) == 0) ? 0 : 1; }
+    if (tiled_mode < 0) tiled_mode = exp_env_int("HS_IIR_TILED", 1) ? 1 : 0;
     std::vector<double> ppow_host;
 
     if (remove_dc) {

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "hs_internal.h"
@@ -29,6 +30,13 @@ int check_launch(const char* what) {
     return HS_OK;
 }
 
+#ifdef HS_EXPERIMENT
+int exp_env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+#endif
+
 int device_sm_count() {
     static int cached[64] = {0};
     int dev = 0;
@@ -46,15 +54,16 @@ static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a
 
 // Optional CUDA-event bracket around the dominant kernel (the optimistic K5 pass), for bench.py's roofline:
 // events are recorded on the stream the kernel is launched on, only while hs_timing_enable(1) is in effect.
-static int g_timing = 0;
+// The hook is a bench facility: one timed stream at a time (the mutex only keeps concurrent callers from corrupting it).
+static std::atomic<int> g_timing{0};
+static std::mutex g_timing_mu;
 static cudaEvent_t g_ev[2] = {nullptr, nullptr};
 static bool g_ev_valid = false;
 
 static int k5_groups() {
     static int ng = 0;
     if (ng == 0) {
-        const char* e = getenv("HS_K5_GROUPS");
-        ng = e ? atoi(e) : 6;
+        ng = exp_env_int("HS_K5_GROUPS", 6);
         if (ng < 4 || ng > 8) ng = 6;
     }
     return ng;
@@ -68,9 +77,8 @@ static size_t k5_rowpart_bytes(int n_win, int n_seg, int m) {
 }
 
 static void k5_segments(int F, int ng, int* n_seg, int* seg_len) {
-    int target = 8 * ng;
-    const char* e = getenv("HS_K5_SEG");
-    if (e && atoi(e) > 0) target = atoi(e);
+    int target = exp_env_int("HS_K5_SEG", 8 * ng);
+    if (target < 1) target = 8 * ng;
     int ns = (F + target / 2) / target;
     if (ns < 1) ns = 1;
     int sl = (F + ns - 1) / ns;
@@ -105,10 +113,11 @@ const char* hs_last_error(void) { return g_err; }
 int hs_version(void) { return 100; }
 long long hs_launch_count(void) { return g_launches.load(); }
 
-void hs_timing_enable(int on) { g_timing = on ? 1 : 0; }
+void hs_timing_enable(int on) { g_timing.store(on ? 1 : 0); }
 
 int hs_timing_last_k5_ms(double* ms) {
     if (!ms) return set_error(HS_ERR_INVALID, "hs_timing_last_k5_ms: null pointer");
+    std::lock_guard<std::mutex> lock(g_timing_mu);
     if (!g_ev_valid) return set_error(HS_ERR_INVALID, "hs_timing_last_k5_ms: no timed launch yet (call hs_timing_enable(1) first)");
     if (cudaEventSynchronize(g_ev[1]) != cudaSuccess) return set_error(HS_ERR_CUDA, "hs_timing_last_k5_ms: event synchronize failed");
     float f = 0.f;
@@ -172,7 +181,7 @@ int hs_yw_assemble_f64(const double* d_R, int n_win, int m, int p, double* d_G, 
 
 static bool yw_use_batched(int m) {
     static int mode = -1;
-    if (mode < 0) { const char* e = getenv("HS_YW_BATCHED"); mode = e ? atoi(e) : 0; }
+    if (mode < 0) mode = exp_env_int("HS_YW_BATCHED", 0);
     return m > kPadMaxHost || mode == 1;
 }
 
@@ -240,7 +249,7 @@ int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double 
     int* bad_count = nullptr;
     double* stage = nullptr;
     static int k5_mode = -1;       // 1 (default): optimistic elimination + check + pivoted redo; 0: pivoted only
-    if (k5_mode < 0) { const char* e = getenv("HS_K5_PIVOT_ONLY"); k5_mode = (e && atoi(e)) ? 0 : 1; }
+    if (k5_mode < 0) k5_mode = exp_env_int("HS_K5_PIVOT_ONLY", 0) ? 0 : 1;
     int* bad_list = nullptr;
     if (m <= kPadMaxHost) {
         const size_t rp = k5_rowpart_bytes(n_win, ns, m);
@@ -271,7 +280,7 @@ int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double 
     P.n_seg = ns;
     P.seg_len = sl;
     P.per_cta = 0;
-    { const char* e = getenv("HS_K5_FLIP"); P.flip = e ? atoi(e) : 0; }
+    P.flip = exp_env_int("HS_K5_FLIP", 0);
     P.rowpart2 = nullptr;
     P.bad = bad;
     P.bad_count = bad_count;
@@ -291,8 +300,10 @@ int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double 
         if (cudaMemsetAsync(bad, 0, (size_t)n_win * F * sizeof(int), st) != cudaSuccess || cudaMemsetAsync(bad_count, 0, sizeof(int), st) != cudaSuccess)
             return set_error(HS_ERR_CUDA, "hs_transfer_dtf_f64: memset failed");
         static int use_mma = -1;   // default: blocked elimination on the FP64 tensor pipe; HS_K5_MMA=0 -> register-tile DFMA kernel
-        if (use_mma < 0) { const char* e = getenv("HS_K5_MMA"); use_mma = (e && atoi(e) == 0) ? 0 : 1; }
-        if (g_timing) {
+        if (use_mma < 0) use_mma = exp_env_int("HS_K5_MMA", 1) ? 1 : 0;
+        const bool timed = g_timing.load() != 0;
+        if (timed) {
+            std::lock_guard<std::mutex> lock(g_timing_mu);
             if (!g_ev[0] && (cudaEventCreate(&g_ev[0]) != cudaSuccess || cudaEventCreate(&g_ev[1]) != cudaSuccess))
                 return set_error(HS_ERR_CUDA, "hs_transfer_dtf_f64: cannot create timing events");
             cudaEventRecord(g_ev[0], st);
@@ -307,7 +318,8 @@ int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double 
         } else {
             rc = launch_transfer_dtf(P, ng, 1, st);
         }
-        if (g_timing) {
+        if (timed) {
+            std::lock_guard<std::mutex> lock(g_timing_mu);
             cudaEventRecord(g_ev[1], st);
             g_ev_valid = true;
         }
@@ -371,12 +383,13 @@ int hs_partial_coherence_f64(const void* d_S, int n_win, int m, int F, void* d_k
 }
 
 // ------------------------------------------------------------------------------------------
-// Host-buffer plan: chunked H2D -> K3/K4/K5 -> D2H pipeline on two streams.
+// Host-buffer plan: chunked H2D -> K3/K4/K5 -> D2H pipeline on three streams.
 // ------------------------------------------------------------------------------------------
 struct hs_plan {
     int max_windows, m, n, p, F;
     int64_t max_samples;
-    int chunk;                 // windows per chunk
+    int chunk;                 // windows per full chunk
+    int ramp;                  // 1: short first chunks (16, 32, 64 windows) so that the device-to-host stream starts early
     double* d_x = nullptr;
     int64_t* d_offsets = nullptr;
     double* d_freqs = nullptr;
@@ -384,24 +397,45 @@ struct hs_plan {
     void* d_ws[2] = {nullptr, nullptr};
     int32_t* d_status = nullptr;
     int64_t* h_offsets = nullptr;     // pinned
+    int32_t* h_status = nullptr;      // pinned
+    double* h_result = nullptr;       // pinned (max_windows, m, m, F), allocated on first use: the destination of every device-to-host
+                                      // copy unless the caller's own buffer is page-locked
     cudaStream_t s_compute[2] = {nullptr, nullptr};
     cudaStream_t s_copy = nullptr;
     cudaEvent_t ev_in = nullptr, ev_in0 = nullptr, ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_chunk;     // one per chunk: its device-to-host copy has finished
     size_t ws_bytes = 0;
+    std::mutex mu;                    // a plan runs one call at a time; different plans are independent
 };
 
 #define PLAN_CUDA(call)                                                                          \
     do {                                                                                         \
         cudaError_t e__ = (call);                                                                \
         if (e__ != cudaSuccess) {                                                                \
-            int rc__ = set_error(e__ == cudaErrorMemoryAllocation ? HS_ERR_NOMEM : HS_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
-            return rc__;                                                                         \
+            rc = set_error(e__ == cudaErrorMemoryAllocation ? HS_ERR_NOMEM : HS_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+            goto fail;                                                                           \
         }                                                                                        \
     } while (0)
+
+static int plan_chunk_at(const hs_plan* pl, int idx) {
+    // 16, 32, 64, then full chunks: chunk k's compute (~0.5 ms + 15 us/window) fits inside chunk k-1's copy (52 us/window)
+    const int c = pl->ramp ? (16 << (idx < 3 ? idx : 3)) : pl->chunk;
+    return c < pl->chunk ? c : pl->chunk;
+}
+
+static bool host_pointer_is_pinned(const void* ptr) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
 
 int hs_plan_create(hs_plan** plan, int max_windows, int m, int n, int p, int F, int64_t max_samples) {
     if (!plan || max_windows < 1 || m < 1 || n < 1 || p < 1 || F < 1 || max_samples < n)
         return set_error(HS_ERR_INVALID, "hs_plan_create: bad arguments");
+    int rc = HS_OK;
     hs_plan* pl = new hs_plan();
     pl->max_windows = max_windows;
     pl->m = m;
@@ -409,17 +443,18 @@ int hs_plan_create(hs_plan** plan, int max_windows, int m, int n, int p, int F, 
     pl->p = p;
     pl->F = F;
     pl->max_samples = max_samples;
-    int chunk = 96;
-    const char* e = getenv("HS_PLAN_CHUNK");
-    if (e && atoi(e) > 0) chunk = atoi(e);
+    int chunk = exp_env_int("HS_PLAN_CHUNK", 96);
+    if (chunk < 1) chunk = 96;
     if (chunk > max_windows) chunk = max_windows;
     pl->chunk = chunk;
+    pl->ramp = exp_env_int("HS_PLAN_RAMP", 1) ? 1 : 0;
     *plan = pl;
     PLAN_CUDA(cudaMalloc(&pl->d_x, (size_t)m * max_samples * sizeof(double)));
     PLAN_CUDA(cudaMalloc(&pl->d_offsets, (size_t)max_windows * sizeof(int64_t)));
     PLAN_CUDA(cudaMalloc(&pl->d_freqs, (size_t)F * sizeof(double)));
     PLAN_CUDA(cudaMalloc(&pl->d_status, (size_t)max_windows * sizeof(int32_t)));
     PLAN_CUDA(cudaMallocHost(&pl->h_offsets, (size_t)max_windows * sizeof(int64_t)));
+    PLAN_CUDA(cudaMallocHost(&pl->h_status, (size_t)max_windows * sizeof(int32_t)));
     pl->ws_bytes = hs_mvar_ffdtf_ws_bytes(chunk, m, p, F);
     for (int i = 0; i < 2; ++i) {
         PLAN_CUDA(cudaMalloc(&pl->d_out[i], (size_t)chunk * m * m * F * sizeof(double)));
@@ -431,7 +466,15 @@ int hs_plan_create(hs_plan** plan, int max_windows, int m, int n, int p, int F, 
     PLAN_CUDA(cudaStreamCreateWithFlags(&pl->s_copy, cudaStreamNonBlocking));
     PLAN_CUDA(cudaEventCreateWithFlags(&pl->ev_in, cudaEventDisableTiming));
     PLAN_CUDA(cudaEventCreateWithFlags(&pl->ev_in0, cudaEventDisableTiming));
+    {
+        int n_chunks = 0;
+        for (int w0 = 0, idx = 0; w0 < max_windows; ++idx, ++n_chunks) w0 += plan_chunk_at(pl, idx);
+        pl->ev_chunk.assign(n_chunks, nullptr);
+        for (int i = 0; i < n_chunks; ++i) PLAN_CUDA(cudaEventCreateWithFlags(&pl->ev_chunk[i], cudaEventDisableTiming));
+    }
     return HS_OK;
+fail:
+    return rc;       // the caller destroys the partially built plan (hs_plan_destroy accepts it)
 }
 
 void hs_plan_destroy(hs_plan* pl) {
@@ -442,6 +485,8 @@ void hs_plan_destroy(hs_plan* pl) {
     cudaFree(pl->d_freqs);
     cudaFree(pl->d_status);
     cudaFreeHost(pl->h_offsets);
+    cudaFreeHost(pl->h_status);
+    if (pl->h_result) cudaFreeHost(pl->h_result);
     for (int i = 0; i < 2; ++i) {
         cudaFree(pl->d_out[i]);
         cudaFree(pl->d_ws[i]);
@@ -449,38 +494,68 @@ void hs_plan_destroy(hs_plan* pl) {
         if (pl->ev_done[i]) cudaEventDestroy(pl->ev_done[i]);
         if (pl->ev_free[i]) cudaEventDestroy(pl->ev_free[i]);
     }
+    for (cudaEvent_t e : pl->ev_chunk)
+        if (e) cudaEventDestroy(e);
     if (pl->s_copy) cudaStreamDestroy(pl->s_copy);
     if (pl->ev_in) cudaEventDestroy(pl->ev_in);
     if (pl->ev_in0) cudaEventDestroy(pl->ev_in0);
     delete pl;
 }
 
+int hs_plan_host_result(hs_plan* pl, double** h_result, size_t* bytes) {
+    if (!pl || !h_result) return set_error(HS_ERR_INVALID, "hs_plan_host_result: null pointer");
+    std::lock_guard<std::mutex> lock(pl->mu);
+    const size_t nbytes = (size_t)pl->max_windows * pl->m * pl->m * pl->F * sizeof(double);
+    if (!pl->h_result) {
+        cudaError_t e = cudaMallocHost(&pl->h_result, nbytes);
+        if (e != cudaSuccess) {
+            pl->h_result = nullptr;
+            return set_error(HS_ERR_NOMEM, "hs_plan_host_result: cannot page-lock %zu bytes: %s", nbytes, cudaGetErrorString(e));
+        }
+    }
+    *h_result = pl->h_result;
+    if (bytes) *bytes = nbytes;
+    return HS_OK;
+}
+
 int hs_plan_mvar_ffdtf_host(hs_plan* pl, const double* h_x, int64_t t_total, const int64_t* h_starts, int n_win,
                             const double* h_freqs, double fs, double* h_ffdtf, int32_t* h_status) {
-    if (!pl || !h_x || !h_starts || !h_freqs || !h_ffdtf || !h_status)
+    if (!pl || !h_x || !h_starts || !h_freqs || !h_status)
         return set_error(HS_ERR_INVALID, "hs_plan_mvar_ffdtf_host: null pointer");
     if (n_win > pl->max_windows || t_total > pl->max_samples || n_win < 0)
         return set_error(HS_ERR_INVALID, "hs_plan_mvar_ffdtf_host: plan too small (n_win=%d, T=%lld)", n_win, (long long)t_total);
+    // where the device-to-host copies land: the caller's buffer when it is page-locked (cudaMemcpyAsync into pageable memory
+    // is staged by the driver and serialises with the kernels), else the plan's own pinned buffer, from which finished
+    // chunks are copied to the caller's buffer by the host while later chunks are still in flight
+    double* h_pinned = h_ffdtf;
+    if (!h_ffdtf || !host_pointer_is_pinned(h_ffdtf)) {
+        int rc0 = hs_plan_host_result(pl, &h_pinned, nullptr);
+        if (rc0) return rc0;
+    }
+    std::lock_guard<std::mutex> lock(pl->mu);
     for (int w = 0; w < n_win; ++w) {
         if (h_starts[w] < 0 || h_starts[w] + pl->n > t_total)
             return set_error(HS_ERR_INVALID, "hs_plan_mvar_ffdtf_host: window %d [%lld, +%d) outside the signal", w, (long long)h_starts[w], pl->n);
         pl->h_offsets[w] = h_starts[w];
     }
     if (n_win == 0) return HS_OK;
+    int rc = HS_OK;
     const int m = pl->m, F = pl->F;
-    // Chunk schedule: a short first chunk (and a medium second one) so that the device-to-host stream, which bounds the whole
-    // call (2.96 MB per window over PCIe), starts after ~1 ms instead of after a full chunk; HS_PLAN_RAMP=0 disables it.
-    static int ramp = -1;
-    if (ramp < 0) { const char* e = getenv("HS_PLAN_RAMP"); ramp = (e && atoi(e) == 0) ? 0 : 1; }
-    // 16, 32, 64, then full chunks: chunk k's compute (~0.5 ms + 15 us/window) fits inside chunk k-1's copy (52 us/window)
-    auto chunk_at = [&](int idx) { const int c = ramp ? (16 << (idx < 3 ? idx : 3)) : pl->chunk; return c < pl->chunk ? c : pl->chunk; };
-    const int c0 = chunk_at(0);
+    const int c0 = plan_chunk_at(pl, 0);
     // inputs: the samples the first chunk needs go first (columns [0, t_split) of every channel row), the rest follows
     int64_t t_split = 0;
     for (int w = 0; w < n_win && w < c0; ++w)
         if (h_starts[w] + pl->n > t_split) t_split = h_starts[w] + pl->n;
-    if (!ramp || t_split > t_total / 2) t_split = t_total;
+    if (!pl->ramp || t_split > t_total / 2) t_split = t_total;
     const size_t pitch = (size_t)t_total * sizeof(double);
+    const size_t per_win = (size_t)m * m * F;
+    int slot = 0, idx = 0, n_chunks = 0;
+    bool used[2] = {false, false};
+#ifdef HS_EXPERIMENT
+    const int dbg = exp_env_int("HS_DEBUG", 0);
+    cudaEvent_t tev[64];
+    int ntev = 0;
+#endif
     PLAN_CUDA(cudaMemcpyAsync(pl->d_offsets, pl->h_offsets, (size_t)n_win * sizeof(int64_t), cudaMemcpyHostToDevice, pl->s_copy));
     PLAN_CUDA(cudaMemcpyAsync(pl->d_freqs, h_freqs, (size_t)F * sizeof(double), cudaMemcpyHostToDevice, pl->s_copy));
     PLAN_CUDA(cudaMemsetAsync(pl->d_status, 0, (size_t)n_win * sizeof(int32_t), pl->s_copy));
@@ -490,45 +565,64 @@ int hs_plan_mvar_ffdtf_host(hs_plan* pl, const double* h_x, int64_t t_total, con
         PLAN_CUDA(cudaMemcpy2DAsync(pl->d_x + t_split, pitch, h_x + t_split, pitch, (size_t)(t_total - t_split) * sizeof(double), m,
                                     cudaMemcpyHostToDevice, pl->s_copy));
     PLAN_CUDA(cudaEventRecord(pl->ev_in, pl->s_copy));
-    const size_t per_win = (size_t)m * m * F;
-    int slot = 0;
-    bool used[2] = {false, false};
-    int idx = 0;
-    static int dbg = -1;
-    if (dbg < 0) dbg = getenv("HS_DEBUG") ? 1 : 0;
-    cudaEvent_t tev[64];
-    int ntev = 0;
+#ifdef HS_EXPERIMENT
     if (dbg) { cudaEventCreate(&tev[0]); cudaEventRecord(tev[0], pl->s_copy); ntev = 1; }
+#endif
     for (int w0 = 0; w0 < n_win; slot ^= 1, ++idx) {
-        const int want = chunk_at(idx);
+        const int want = plan_chunk_at(pl, idx);
         const int nw = (n_win - w0 < want) ? (n_win - w0) : want;
         cudaStream_t sc = pl->s_compute[slot];
         PLAN_CUDA(cudaStreamWaitEvent(sc, idx == 0 ? pl->ev_in0 : pl->ev_in, 0));
         if (used[slot]) PLAN_CUDA(cudaStreamWaitEvent(sc, pl->ev_free[slot], 0));    // previous D2H of this slot finished
-        int rc = hs_mvar_ffdtf_f64(pl->d_x, pl->d_offsets + w0, t_total, nw, m, pl->n, pl->p, pl->d_freqs, F, fs, pl->d_out[slot],
-                                   nullptr, nullptr, pl->d_status + w0, pl->d_ws[slot], sc);
-        if (rc) return rc;
+        rc = hs_mvar_ffdtf_f64(pl->d_x, pl->d_offsets + w0, t_total, nw, m, pl->n, pl->p, pl->d_freqs, F, fs, pl->d_out[slot],
+                               nullptr, nullptr, pl->d_status + w0, pl->d_ws[slot], sc);
+        if (rc) goto fail;
         PLAN_CUDA(cudaEventRecord(pl->ev_done[slot], sc));
         PLAN_CUDA(cudaStreamWaitEvent(pl->s_copy, pl->ev_done[slot], 0));
+#ifdef HS_EXPERIMENT
         if (dbg && ntev < 62) { cudaEventCreate(&tev[ntev]); cudaEventRecord(tev[ntev++], pl->s_copy); }
-        PLAN_CUDA(cudaMemcpyAsync(h_ffdtf + (size_t)w0 * per_win, pl->d_out[slot], (size_t)nw * per_win * sizeof(double),
+#endif
+        PLAN_CUDA(cudaMemcpyAsync(h_pinned + (size_t)w0 * per_win, pl->d_out[slot], (size_t)nw * per_win * sizeof(double),
                                   cudaMemcpyDeviceToHost, pl->s_copy));
         PLAN_CUDA(cudaEventRecord(pl->ev_free[slot], pl->s_copy));
+        PLAN_CUDA(cudaEventRecord(pl->ev_chunk[idx], pl->s_copy));
+#ifdef HS_EXPERIMENT
         if (dbg && ntev < 62) { cudaEventCreate(&tev[ntev]); cudaEventRecord(tev[ntev++], pl->s_copy); }
+#endif
         used[slot] = true;
         w0 += nw;
+        n_chunks = idx + 1;
     }
-    PLAN_CUDA(cudaMemcpyAsync(h_status, pl->d_status, (size_t)n_win * sizeof(int32_t), cudaMemcpyDeviceToHost, pl->s_copy));
+    PLAN_CUDA(cudaMemcpyAsync(pl->h_status, pl->d_status, (size_t)n_win * sizeof(int32_t), cudaMemcpyDeviceToHost, pl->s_copy));
+    if (h_ffdtf && h_pinned != h_ffdtf) {
+        // pageable destination: hand every chunk over as soon as its copy has landed in the pinned buffer
+        for (int i = 0, w0 = 0; i < n_chunks; ++i) {
+            const int want = plan_chunk_at(pl, i);
+            const int nw = (n_win - w0 < want) ? (n_win - w0) : want;
+            PLAN_CUDA(cudaEventSynchronize(pl->ev_chunk[i]));
+            memcpy(h_ffdtf + (size_t)w0 * per_win, h_pinned + (size_t)w0 * per_win, (size_t)nw * per_win * sizeof(double));
+            w0 += nw;
+        }
+    }
     PLAN_CUDA(cudaStreamSynchronize(pl->s_copy));
     PLAN_CUDA(cudaStreamSynchronize(pl->s_compute[0]));
     PLAN_CUDA(cudaStreamSynchronize(pl->s_compute[1]));
+    memcpy(h_status, pl->h_status, (size_t)n_win * sizeof(int32_t));
+#ifdef HS_EXPERIMENT
     if (dbg) {
         fprintf(stderr, "[hs] plan timeline (ms since first copy): ");
         for (int i = 1; i < ntev; ++i) { float ms = 0; cudaEventElapsedTime(&ms, tev[0], tev[i]); fprintf(stderr, "%s%.2f", (i & 1) ? " [" : "-", ms); if (!(i & 1)) fprintf(stderr, "]"); }
         fprintf(stderr, "\n");
         for (int i = 0; i < ntev; ++i) cudaEventDestroy(tev[i]);
     }
+#endif
     return HS_OK;
+fail:
+    // nothing of this call may still be in flight when the caller frees (or reuses) its buffers
+    cudaStreamSynchronize(pl->s_copy);
+    cudaStreamSynchronize(pl->s_compute[0]);
+    cudaStreamSynchronize(pl->s_compute[1]);
+    return rc;
 }
 
 }  // extern "C"

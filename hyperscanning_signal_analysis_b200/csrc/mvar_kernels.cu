@@ -459,6 +459,7 @@ static int launch_k5_ng(const K5Params& P, int sm, cudaStream_t stream) {
 // mode 0: pivoted only; mode 1: optimistic + verify; mode 2: pivoted redo of the flagged matrices
 int launch_transfer_dtf(const K5Params& P, int ng, int mode, cudaStream_t stream) {
     const int sm = device_sm_count();
+#ifdef HS_EXPERIMENT
     if (ng == 8) {
         if (mode == 0) return launch_k5_ng<8, 0>(P, sm, stream);
         if (mode == 1) return launch_k5_ng<8, 1>(P, sm, stream);
@@ -469,8 +470,11 @@ int launch_transfer_dtf(const K5Params& P, int ng, int mode, cudaStream_t stream
         if (mode == 1) return launch_k5_ng<7, 1>(P, sm, stream);
         return launch_k5_ng<7, 2>(P, sm, stream);
     }
-    if (mode == 0) return launch_k5_ng<6, 0>(P, sm, stream);
     if (mode == 1) return launch_k5_ng<6, 1>(P, sm, stream);
+#endif
+    // product build: the register-tile kernel only runs WITH pivoting (mode 0: every matrix, for shapes the tensor-pipe
+    // kernel does not take; mode 2: the matrices the optimistic tensor-pipe pass flagged)
+    if (mode == 0 || mode == 1) return launch_k5_ng<6, 0>(P, sm, stream);
     return launch_k5_ng<6, 2>(P, sm, stream);
 }
 
@@ -667,7 +671,7 @@ static int lagcov_mma_ld(int n, int p) {
 }
 
 int launch_lagcov(const K3Params& P, cudaStream_t stream) {
-    static const bool legacy = [] { const char* e = getenv("HS_K3_LEGACY"); return e && e[0] == '1'; }();
+    static const bool legacy = exp_env_int("HS_K3_LEGACY", 0) == 1;
     if (!legacy && P.m <= kPadMax) {
         const int ld = lagcov_mma_ld(P.n, P.p);
         const size_t smem_mma = (size_t)kPadMax * ld * sizeof(double);
@@ -736,6 +740,7 @@ int launch_toeplitz(const double* R, int n_win, int m, int p, double* G, double*
 //     k-major 40 x 40 panels in shared memory.
 // =====================================================================================
 
+#ifdef HS_EXPERIMENT
 constexpr int kK4Groups = 4;
 constexpr int kPanel = kPadMax * kPadMax;
 
@@ -900,6 +905,7 @@ __global__ void __launch_bounds__(kK4Groups * 64, 1) lwr_kernel(const K4Params P
     }
 }
 
+#endif  // HS_EXPERIMENT (legacy 4-group K4 kernel)
 // -------------------------------------------------------------------------------------
 // K4, one-group variant (the one that runs): ONE tile group (64 threads) per window and FIVE
 // CTAs per SM.  The recursion of a window is a sequential chain of ~107 small GEMMs and 15
@@ -1146,16 +1152,13 @@ __global__ void __launch_bounds__(64, kK4PerSM) lwr1_kernel(const K4Params P) {
     }
 }
 
-static bool k4_legacy() {
-    static const bool v = [] { const char* e = getenv("HS_K4_LEGACY"); return e && e[0] == '1'; }();
-    return v;
-}
 
 size_t lwr_ws_doubles(int grid, int m, int p) { return (size_t)grid * (4 * p + 2) * m * m; }
 int lwr_grid(int n_win) { const int slots = device_sm_count() * kK4PerSM; return n_win < slots ? n_win : slots; }
 
 int launch_lwr(const K4Params& P, int grid, cudaStream_t stream) {
-    if (k4_legacy()) {
+#ifdef HS_EXPERIMENT
+    if (exp_env_int("HS_K4_LEGACY", 0) == 1) {
         const int sm = device_sm_count();
         const size_t smem = (size_t)(kK4Groups * 2 + 4) * kPanel * sizeof(double) + kK4Groups * sizeof(GJScratch);
         cudaError_t e = cudaFuncSetAttribute(lwr_kernel<kTileMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1163,16 +1166,19 @@ int launch_lwr(const K4Params& P, int grid, cudaStream_t stream) {
         lwr_kernel<kTileMax><<<grid < sm ? grid : sm, kK4Groups * 64, smem, stream>>>(P);
         return check_launch("lwr_kernel");
     }
+#endif
     const size_t smem = (size_t)3 * kK4Panel * sizeof(double) + sizeof(GJScratch);
     cudaError_t e = cudaFuncSetAttribute(lwr1_kernel<kTileMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "lwr: %s", cudaGetErrorString(e));
     // five 41 KB CTAs per SM need the large shared-memory carve-out (the default split may leave room for two only)
     cudaFuncSetAttribute(lwr1_kernel<kTileMax>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (getenv("HS_DEBUG")) {
+#ifdef HS_EXPERIMENT
+    if (exp_env_int("HS_DEBUG", 0)) {
         int nb = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lwr1_kernel<kTileMax>, 64, smem);
         fprintf(stderr, "[hs] lwr1_kernel: %d CTAs/SM, smem %zu, grid %d\n", nb, smem, grid);
     }
+#endif
     lwr1_kernel<kTileMax><<<grid, 64, smem, stream>>>(P);
     return check_launch("lwr1_kernel");
 }

@@ -200,10 +200,13 @@ __device__ __forceinline__ void mma_tile_steps(double (&c)[T][T][2], const int m
         mma_extract<T, t>(c, h, x);
         mma_group_sync(x);
         double2 det = make_double2(1.0, 0.0);      // ADJ == 2: P holds adj(D), L comes out multiplied by det and U is divided by it below
+#ifdef HS_EXPERIMENT
         if (x.dbg & 1) {      // experiment: no 4 x 4 inverse (timing only, results are wrong)
             if (x.lane < 16) gs->u.p.P[x.part][x.lane] = make_double2((x.lane % 5 == 0) ? 1.0 : 0.0, 0.0);
             __syncwarp();
-        } else if (ADJ == 2) mma_inverse4_adj<false>(x, K0, h, det);
+        } else
+#endif
+        if (ADJ == 2) mma_inverse4_adj<false>(x, K0, h, det);
         else if (ADJ == 1) mma_inverse4_adj<true>(x, K0, h, det);
         else mma_inverse4(x, K0, h);
         // B fragments of -P with Re/Im interleaved by output column:  n = 2j -> Re, n = 2j+1 -> Im
@@ -482,12 +485,14 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
         }
         __syncthreads();
 
+#ifdef HS_EXPERIMENT
         if ((P.flip & 0xfffff) > 0) {
             // phase skew between the groups that share an SMSP pair (experiment): all groups run identical work, so after
             // every CTA barrier they would otherwise hit the FP64 pipe in the same phases
             const long long until = clock64() + (long long)(gid >> 1) * (P.flip & 0xfffff);
             while (clock64() < until) { }
         }
+#endif
         // z_k(f) of the group's current bin: a private 2 * n_planes slot in shared memory, filled from the (L2-resident) table by the
         // lanes l64 < 2 * n_planes, which fetch the NEXT bin's values one matrix ahead
         double2* zg = zs + gid * 2 * n_planes;
@@ -513,6 +518,7 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
             if (l64 < kMP) gs->vfull[l64] = vacc;
             if (l64 == 0) gs->flag = 0;
             // ---- A(f) = I - sum_k A_k z_k(f)
+#ifdef HS_EXPERIMENT
             if (P.flip & (1 << 30)) {       // experiment: skip the assembly (diagonally dominant dummy matrix)
 #pragma unroll
                 for (int ta = 0; ta < T; ++ta)
@@ -521,7 +527,9 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
                         c[ta][tb][0] = ((ta == tb && x.g4 == 2 * x.t4 && x.part == 0) ? 4.0 : 0.0) + 1e-3 * (x.lane + ta - tb + f);
                         c[ta][tb][1] = ((ta == tb && x.g4 == 2 * x.t4 + 1 && x.part == 0) ? 4.0 : 0.0) + 1e-3 * (x.lane - ta + tb);
                     }
-            } else if (n_planes == 4) mma_assemble<T, 4>(c, coef, zg, n_planes, x);
+            } else
+#endif
+            if (n_planes == 4) mma_assemble<T, 4>(c, coef, zg, n_planes, x);
             else mma_assemble<T, 0>(c, coef, zg, n_planes, x);
             if (P.Af) mma_store_generic<T, false>(c, P, w, f, x);
             // ---- blocked Gauss-Jordan on the tensor pipe
@@ -570,7 +578,9 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
                 for (int q = 0; q < T * T; ++q) X[q * 32] = x.part ? c[q / T][q % T][0] : c[q / T][q % T][1];
             }
             mma_group_sync(x);
+#ifdef HS_EXPERIMENT
             if (P.flip & (1 << 29)) continue;       // experiment: skip the epilogue
+#endif
             const bool good = (gs->flag == 0);
             if (!good) {
                 if (l64 == 0) {
@@ -623,10 +633,14 @@ int launch_mma_t(const K5Params& P, int sm_count, cudaStream_t stream) {
     if (smem > 227 * 1024) return set_error(HS_ERR_UNSUPPORTED, "transfer_mma: model order %d needs %zu B shared memory", P.p, smem);
     // 4 x 4 pivot-block inverse: 1 (default) cofactors; 2 cofactors with the division by det deferred to the U panel (measured
     // slower: 5.49 vs 5.24 ms, the 20 extra FP64 instructions per lane and step sit in front of the 50 update DMMAs); 0 in-place elimination
-    static const int adj = [] { const char* e = getenv("HS_K5_ADJ"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1; }();
+#ifdef HS_EXPERIMENT
+    static const int adj = exp_env_int("HS_K5_ADJ", 1);
     constexpr bool kMain = (T == 5 && NG == 6);
     auto kern = (adj == 2 && kMain) ? transfer_mma_kernel<T, NG, kMain ? 2 : 0>
               : (adj == 1 && kMain) ? transfer_mma_kernel<T, NG, kMain ? 1 : 0> : transfer_mma_kernel<T, NG, 0>;
+#else
+    auto kern = transfer_mma_kernel<T, NG, 1>;       // cofactor pivot-block inverse for every tile count
+#endif
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "transfer_mma: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
     const long long q_total = (long long)P.n_win * P.F;
@@ -639,7 +653,7 @@ int launch_mma_t(const K5Params& P, int sm_count, cudaStream_t stream) {
 
 void transfer_mma_partition(int n_win, int F, int* per_cta, int* slots, int ng) {
     const long long total = (long long)n_win * F;
-    int sm = device_sm_count();
+    int sm = compute_sm_count();
     if (sm < 1) sm = 148;
     long long per = (total + sm - 1) / sm;
     per = (per + ng - 1) / ng * ng;              // whole rounds of the ng groups
@@ -653,8 +667,10 @@ bool transfer_mma_fits(int p, int ng, int seg_len) { return ng >= 4 && ng <= 6 &
 // optimistic (unpivoted, verified) pass on the tensor pipe; the caller follows up with the pivoted redo
 int launch_transfer_mma(const K5Params& P, int ng, cudaStream_t stream) {
     const int sm = device_sm_count();
+#ifdef HS_EXPERIMENT
     if (ng == 4 && (P.m + 7) / 8 == 5) return launch_mma_t<5, 4>(P, sm, stream);      // experiments: fewer matrices in flight per SM
     if (ng == 5 && (P.m + 7) / 8 == 5) return launch_mma_t<5, 5>(P, sm, stream);
+#endif
     if (ng != 6) return set_error(HS_ERR_INVALID, "transfer_mma: %d groups per CTA not built", ng);
     switch ((P.m + 7) / 8) {
         case 1: return launch_mma_t<1, 6>(P, sm, stream);

@@ -48,13 +48,17 @@ def _apply_filters(multimodal_data, filters, raw_eeg_data, plot_flag=False):
         block = np.ascontiguousarray(raw_eeg_data[rows, :], dtype=np.float64)
         if filter_type == "iir":
             out = frontend.filtfilt_cascade(block, [(b_notch, a_notch), (b_low, a_low), (b_high, a_high)], remove_dc=True)
-        else:
-            if np.size(a_low) != 1 or np.size(a_high) != 1:
-                raise NotImplementedError("the causal branch expects FIR low-/high-pass filters (a = 1) as _design_eeg_filters makes them")
+        elif np.size(a_low) == 1 and np.size(a_high) == 1:
             bl = np.atleast_1d(np.asarray(b_low, dtype=np.float64)) / float(np.ravel(a_low)[0])
             bh = np.atleast_1d(np.asarray(b_high, dtype=np.float64)) / float(np.ravel(a_high)[0])
             import torch
             out = frontend.lfilter_fir_chain_dev(torch.from_numpy(block).cuda(), (b_notch, a_notch), bl, bh, remove_dc=True).cpu().numpy()
+        else:
+            # any other filter_type with recursive low-/high-pass coefficients (e.g. the Butterworth pair _design_eeg_filters
+            # returns for filter_type='butter'): the same causal chain, every stage a zero-state IIR sweep (:794-801)
+            import torch
+            out = frontend.lfilter_iir_chain_dev(torch.from_numpy(block).cuda(), [(b_notch, a_notch), (b_low, a_low), (b_high, a_high)],
+                                                 delay=(np.size(b_low) - 1) // 2 + (np.size(b_high) - 1) // 2, remove_dc=True).cpu().numpy()
         raw_eeg_data[rows, :] = out
     multimodal_data.eeg_filtration.notch["applied"] = True
     multimodal_data.eeg_filtration.low_pass["applied"] = True

@@ -112,6 +112,35 @@ def lfilter_fir_chain_dev(x_dev, notch, b_low, b_high, remove_dc=True):
     return out
 
 
+def lfilter_iir_chain_dev(x_dev, filters, delay, remove_dc=True):
+    """Causal branch of the loader for recursive filters (dataloader.py:794-801): ``lfilter`` with every (b, a) in turn (zero
+    initial state), then ``np.roll(s, -delay)`` and ``s[-delay:] = 0``.  (n_sig, n) CUDA float64 in, new tensor out."""
+    torch = _torch()
+    lib = _lib.load()
+    assert x_dev.is_cuda and x_dev.dtype == torch.float64 and x_dev.dim() == 2 and x_dev.is_contiguous()
+    n_sig, n = x_dev.shape
+    out = torch.zeros_like(x_dev)
+    if n_sig == 0 or n == 0:
+        return out
+    stream = torch.cuda.current_stream().cuda_stream
+    ws = torch.empty(max(int(lib.hs_filtfilt_ws_bytes(n_sig, n)), 16), dtype=torch.uint8, device="cuda")
+    cur, nxt = x_dev, torch.empty_like(x_dev)
+    for k, (b, a) in enumerate(filters):
+        b = np.atleast_1d(np.asarray(b, dtype=np.float64))
+        a = np.atleast_1d(np.asarray(a, dtype=np.float64))
+        nt = max(len(a), len(b), 2)
+        bb, aa = np.zeros(nt), np.zeros(nt)
+        bb[:len(b)] = b
+        aa[:len(a)] = a
+        _lib.check(lib.hs_iir_lfilter_f64(cur.data_ptr(), n_sig, n, n, bb.ctypes.data, aa.ctypes.data, nt, int(remove_dc and k == 0),
+                                          nxt.data_ptr(), n, ws.data_ptr(), stream), "hs_iir_lfilter_f64")
+        cur, nxt = nxt, (torch.empty_like(x_dev) if cur is x_dev else cur)
+    # delay == 0 zeroes the whole signal in the reference (s[-0:] is s[0:]), and so does delay >= n
+    if 0 < delay < n:
+        out[:, : n - delay] = cur[:, delay:]
+    return out
+
+
 def decimate_taps(q):
     """Anti-alias FIR of ``scipy.signal.decimate(..., ftype='fir')``: firwin(20 q + 1, 1/q, window='hamming')."""
     from scipy.signal import firwin

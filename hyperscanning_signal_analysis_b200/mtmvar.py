@@ -23,7 +23,7 @@ from . import _lib
 __all__ = [
     "count_corr", "ar_coeff", "mvar_transfer_function", "multivariate_spectra", "dtf_multivariate",
     "full_freq_dtf", "mvar_criterion", "gen_partial_directed_coherence", "partial_coherence", "direct_dtf",
-    "batched_partial_coherence", "batched_lagcov", "batched_ar_coeff", "batched_transfer", "windowed_ffdtf", "FfdtfPlan",
+    "batched_partial_coherence", "batched_mvar_criterion", "batched_lagcov", "batched_ar_coeff", "batched_transfer", "windowed_ffdtf", "FfdtfPlan",
 ]
 
 
@@ -176,8 +176,13 @@ def windowed_ffdtf(signals, starts, window_size, freqs, fs, p, return_model=Fals
 
 
 class FfdtfPlan:
-    """Host-buffer pipeline (pinned staging, chunked copies overlapped with compute):
-    NumPy (m, T) + window starts -> NumPy (n_win, m, m, F).  Wraps hs_plan_*."""
+    """Host-buffer pipeline (chunked copies overlapped with compute): NumPy (m, T) + window starts -> NumPy
+    (n_win, m, m, F).  Wraps hs_plan_*.
+
+    ``run(..., out=None)`` returns a VIEW of the plan's own page-locked result buffer (zero copy; valid until the next
+    ``run`` / ``close`` -- ``.copy()`` it to keep it).  ``run(..., out=array)`` fills the caller's array: directly when it is
+    page-locked (e.g. ``torch.empty(...).pin_memory().numpy()``), otherwise through the plan's pinned buffer with the host
+    copy of finished chunks overlapped with the transfers still in flight.  One call at a time per plan (internal lock)."""
 
     def __init__(self, max_windows, m, window_size, p, n_freqs, max_samples):
         import ctypes as C
@@ -191,28 +196,46 @@ class FfdtfPlan:
             self.close()
             raise _lib.HsError(f"hs_plan_create failed ({rc}): {msg}")
 
+    def _own_result(self, n_win):
+        import ctypes as C
+        max_windows, m, _, _, F, _ = self.shape
+        ptr, nbytes = C.c_void_p(), C.c_size_t()
+        _lib.check(self._lib.hs_plan_host_result(self._h, C.byref(ptr), C.byref(nbytes)), "hs_plan_host_result")
+        buf = (C.c_double * (max_windows * m * m * F)).from_address(ptr.value)
+        buf._plan = self                       # the view keeps the plan (and with it the pinned buffer) alive
+        return np.frombuffer(buf, dtype=np.float64).reshape(max_windows, m, m, F)[:n_win]
+
     def run(self, signals, starts, freqs, fs, out=None):
         max_windows, m, n, p, F, max_samples = self.shape
+        if self._h is None:
+            raise _lib.HsError("FfdtfPlan is closed")
         x = np.ascontiguousarray(signals, dtype=np.float64)
-        st = np.ascontiguousarray(starts, dtype=np.int64)
-        fr = np.ascontiguousarray(freqs, dtype=np.float64)
-        if x.shape[0] != m or fr.size != F:
+        st = np.ascontiguousarray(starts, dtype=np.int64).ravel()
+        fr = np.ascontiguousarray(freqs, dtype=np.float64).ravel()
+        if x.ndim != 2 or x.shape[0] != m or fr.size != F:
             raise ValueError("signals / freqs do not match the plan")
         n_win = st.size
+        if n_win > max_windows or x.shape[1] > max_samples:
+            raise ValueError("more windows / samples than the plan was created for")
         if out is None:
-            out = np.empty((n_win, m, m, F), dtype=np.float64)
-        status = np.zeros(n_win, dtype=np.int32)
+            res, out_ptr = self._own_result(n_win), None
+        else:
+            if not isinstance(out, np.ndarray) or out.dtype != np.float64 or not out.flags["C_CONTIGUOUS"] or not out.flags["WRITEABLE"] \
+                    or out.shape != (n_win, m, m, F):
+                raise ValueError(f"out must be a writable C-contiguous float64 ndarray of shape {(n_win, m, m, F)}")
+            res, out_ptr = out, out.ctypes.data
+        status = np.zeros(max(n_win, 1), dtype=np.int32)
         rc = self._lib.hs_plan_mvar_ffdtf_host(self._h, x.ctypes.data, x.shape[1], st.ctypes.data, n_win, fr.ctypes.data,
-                                               float(fs), out.ctypes.data, status.ctypes.data)
+                                               float(fs), out_ptr, status.ctypes.data)
         _lib.check(rc, "hs_plan_mvar_ffdtf_host")
-        if status.any():
-            raise np.linalg.LinAlgError(f"Singular matrix (window(s) {np.nonzero(status)[0][:8].tolist()})")
-        return out
+        if status[:n_win].any():
+            raise np.linalg.LinAlgError(f"Singular matrix (window(s) {np.nonzero(status[:n_win])[0][:8].tolist()})")
+        return res
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.hs_plan_destroy(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         try:
@@ -224,12 +247,16 @@ class FfdtfPlan:
 # ----------------------------------------------------------------------------- reference-signature functions
 def count_corr(x, ip, iwhat):
     """Reference ``count_corr`` (mtmvar.py:35-87): (r_left, r_right, r) for (m, n, trials) data."""
-    if iwhat != 1:
-        raise NotImplementedError("only iwhat == 1 (biased 1/n) is used by the reference's callers (mtmvar.py:113)")
+    if iwhat not in (1, 2):
+        raise ValueError("iwhat must be 1 (biased, 1/n) or 2 (1/(n-k)); the reference leaves the lag blocks undefined otherwise")
     torch = _torch()
     lib = _lib.load()
     t, offsets, trials, m, n = _window_tensor(x)
     R = batched_lagcov(t, offsets, n, 1, trials, m, n, ip)
+    if iwhat == 2:
+        # mtmvar.py:60-63: lag L = k + 1 is scaled by 1 / (n - k) instead of 1 / n; R(0) keeps 1 / n (:72-73)
+        scale = torch.tensor([1.0] + [n / (n - k) for k in range(ip)], dtype=torch.float64, device="cuda")
+        R = R * scale[None, :, None, None]
     mp = m * ip
     G = torch.empty((1, mp, mp), dtype=torch.float64, device="cuda")
     rhs = torch.empty((1, mp, m), dtype=torch.float64, device="cuda")
@@ -258,25 +285,39 @@ def mvar_transfer_function(ar_coeffs, freqs, fs):
     return res["H"][0].cpu().numpy(), res["Af"][0].cpu().numpy()
 
 
+_CRIT_CODES = {'AIC': 0, 'HQ': 1, 'SC': 2}
+
+
+def batched_mvar_criterion(x, offsets, ch_stride, n_win, m, n, max_model_order, crit_type='AIC', trials=1):
+    """Order criteria of ``n_win`` windows in one pass: lag covariances to ``max_model_order`` (K3), ONE LWR recursion per
+    window that yields the residual covariance of every order (K4), ``ln det`` + penalty + argmin in ``criterion_kernel``.
+    Returns CUDA tensors (crit (n_win, P) float64, popt (n_win) int32, status (n_win) int32)."""
+    torch = _torch()
+    lib = _lib.load()
+    if crit_type not in _CRIT_CODES:
+        raise ValueError("Invalid criterion type. Choose from 'AIC', 'HQ', 'SC'.")
+    P = int(max_model_order)
+    _, _, Vall, status, _ = batched_ar_coeff(x, offsets, ch_stride, n_win, m, n, P, trials, want_all_orders=True)
+    crit = torch.empty((n_win, P), dtype=torch.float64, device="cuda")
+    popt = torch.empty((n_win,), dtype=torch.int32, device="cuda")
+    _lib.check(lib.hs_mvar_criterion_f64(Vall.data_ptr(), n_win, P, m, n, _CRIT_CODES[crit_type], crit.data_ptr(), None,
+                                         popt.data_ptr(), _stream()), "hs_mvar_criterion_f64")
+    return crit, popt, status
+
+
 def mvar_criterion(data, max_model_order, crit_type='AIC', plot=False):
     """Reference ``mvar_criterion`` (mtmvar.py:551-601).  One LWR recursion to ``max_model_order`` yields the
     residual covariance of every lower order, so no refits.  ``plot`` is accepted and ignored (no matplotlib)."""
-    torch = _torch()
-    if crit_type not in ('AIC', 'HQ', 'SC'):
+    if crit_type not in _CRIT_CODES:
         raise ValueError("Invalid criterion type. Choose from 'AIC', 'HQ', 'SC'.")
     data = np.asarray(data)
     n_channels, n_samples = data.shape
     model_order_range = np.arange(1, max_model_order + 1, dtype=int)
-    _, _, Vall = _fit(data, max_model_order, want_all_orders=True)
-    logdet = torch.log(torch.linalg.det(Vall[0])).cpu().numpy()
-    if crit_type == 'AIC':
-        pen = 2 * model_order_range * n_channels ** 2 / n_samples
-    elif crit_type == 'HQ':
-        pen = 2 * np.log(np.log(n_samples)) * model_order_range * n_channels ** 2 / n_samples
-    else:
-        pen = np.log(n_samples) * model_order_range * n_channels ** 2 / n_samples
-    crit = logdet + pen
-    optimal_model_range = model_order_range[np.argmin(crit)]
+    t, offsets, trials, m, n = _window_tensor(data)
+    crit, popt, status = batched_mvar_criterion(t, offsets, n, 1, m, n, max_model_order, crit_type, trials)
+    _raise_if_singular(status, "mvar_criterion")
+    crit = crit[0].cpu().numpy()
+    optimal_model_range = model_order_range[int(popt[0].item()) - 1]
     return crit, model_order_range, optimal_model_range
 
 

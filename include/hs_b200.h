@@ -81,6 +81,14 @@ size_t hs_yw_ws_bytes(int n_win, int m, int p);
 int hs_yw_solve_f64(const double* d_R, int n_win, int m, int p, double* d_A, double* d_V, double* d_Vall,
                     int32_t* d_status, void* d_ws, void* stream);
 
+/* Model-order criteria for every window at once.  Replaces the refit loop of mvar_criterion, src/mtmvar.py:577-590:
+ * crit[w][k] = ln det V_{k+1}(w) + penalty * (k+1), penalty = 2 m^2/n (crit_type 0, 'AIC'), 2 ln ln n m^2/n (1, 'HQ'),
+ * ln n m^2/n (2, 'SC'); popt[w] = 1 + first index of the minimum (np.argmin).
+ *   d_Vall (n_win, P, m, m): residual covariance of every order, as hs_yw_solve_f64 writes it for model order P
+ *   d_crit (n_win, P) out;  d_logdet (n_win, P) out or NULL;  d_popt (n_win) int32 out;  n_samples = window length      */
+int hs_mvar_criterion_f64(const double* d_Vall, int n_win, int P, int m, int n_samples, int crit_type, double* d_crit,
+                          double* d_logdet, int32_t* d_popt, void* stream);
+
 /* z[k][f] = exp(-(k+1) 2 pi i f / fs), src/mtmvar.py:151-153.  d_z (p, F) complex128.        */
 int hs_ztable_f64(const double* d_freqs, int F, int p, double fs, void* d_z, void* stream);
 
@@ -128,8 +136,39 @@ int hs_mvar_ffdtf_f64(const double* d_x, const int64_t* d_offsets, int64_t ch_st
 typedef struct hs_plan hs_plan;
 int hs_plan_create(hs_plan** plan, int max_windows, int m, int n, int p, int F, int64_t max_samples);
 void hs_plan_destroy(hs_plan* plan);
+/* h_ffdtf page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory): results are copied straight into it.
+ * h_ffdtf pageable: the copies land in the plan's own pinned buffer and every finished chunk is handed to h_ffdtf by the
+ * host while later chunks are in flight.  h_ffdtf NULL: results stay in the plan's pinned buffer (hs_plan_host_result),
+ * valid until the next call on this plan.  A plan runs one call at a time (internal lock); plans are independent.       */
 int hs_plan_mvar_ffdtf_host(hs_plan* plan, const double* h_x, int64_t t_total, const int64_t* h_starts, int n_win,
                             const double* h_freqs, double fs, double* h_ffdtf, int32_t* h_status);
+/* the plan's pinned result buffer (max_windows, m, m, F) float64, allocated on first use */
+int hs_plan_host_result(hs_plan* plan, double** h_result, size_t* bytes);
+
+/* ---------------------------------------------------------------- multi-GPU result exchange */
+
+/* The reference keeps one result array per (dyad, film) (src/eeg_alpha_ibi_ffdtf.py:647-656); north_star shards the units
+ * by dyad over the GPUs of a box and all-gathers the result over NVLink.  Every rank owns a slot of a gather buffer that
+ * exists on every GPU; hs_mvar_ffdtf_f64 writes a chunk of windows into the local slot (d_ffdtf points into it) and
+ * hs_gather_push_f64 streams the chunk to the same offset on the peers, on another stream, while the next chunk computes.
+ *   d_src              local chunk, `count` float64 (even, 16-byte aligned)
+ *   d_multicast_dst    same offset inside an NVSwitch multicast mapping of the buffer (one multimem.st per 16 bytes,
+ *                      replicated by the switch to every GPU of the group), or NULL
+ *   h_peer_dst         HOST array of n_peers device pointers: the same offset inside each peer's mapping of its buffer
+ *                      (plain stores over NVLink); used when d_multicast_dst is NULL
+ *   n_ctas             CTAs of the push kernel (<= 0: 8).  The caller reserves that many SMs for it with
+ *                      hs_set_compute_sm_limit(sm_count - n_ctas): a K5 CTA owns a whole SM's register file.
+ * Cross-rank completion (all peers' pushes have landed) is the caller's barrier after the last push.                   */
+int hs_set_compute_sm_limit(int n_sms);      /* 0 = all SMs (default); process-wide */
+int hs_gather_push_f64(const double* d_src, int64_t count, void* d_multicast_dst, const void* const* h_peer_dst, int n_peers,
+                       int n_ctas, void* stream);
+/* same exchange on the copy engines (one cudaMemcpyAsync per peer): the measured alternative */
+int hs_gather_push_ce(const double* d_src, int64_t count, const void* const* h_peer_dst, int n_peers, void* stream);
+/* cudaMalloc + CUDA IPC export / import of a gather buffer, for setups without torch symmetric memory; handle = 64 bytes */
+int hs_ipc_alloc(void** d_ptr, size_t bytes, unsigned char* handle64);
+int hs_ipc_open(const unsigned char* handle64, void** d_ptr);
+int hs_ipc_close(void* d_ptr);
+int hs_ipc_free(void* d_ptr);
 
 /* ---------------------------------------------------------------- front end (K1, K2, K6) */
 

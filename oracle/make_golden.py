@@ -132,7 +132,72 @@ def gen_prewindow():
     print("prewindow.npz", os.path.getsize(os.path.join(OUT, "prewindow.npz")))
 
 
+def gen_round2():
+    """Round-2 additions, all from the REFERENCE's own code: count_corr(iwhat=2) (mtmvar.py:60-63), the causal branch of
+    _apply_filters with recursive low/high-pass coefficients (dataloader.py:793-801, filter_type='butter'), per-window order
+    search (mvar_criterion, mtmvar.py:551-601) and EEG_IBI_FFDTF_Pipeline._compute_ffDTF (eeg_alpha_ibi_ffdtf.py:521-634)
+    called on an instance, with a fixed order and with ar_p=None."""
+    sys.path.insert(0, ROOT)
+    import scipy
+    from hyperscanning_signal_analysis_b200 import synth
+    mtmvar, dataloader, ds, ffd = import_reference()
+    versions = f"numpy {np.__version__} scipy {scipy.__version__}"
+    rec = dict(versions=versions)
+    g4 = np.load(os.path.join(OUT, "mvar_m4.npz"))
+    rl, rr, r0 = mtmvar.count_corr(g4["x"][:, :, None], int(g4["p"]), 2)
+    rec.update(m4_iwhat2_left=rl, m4_iwhat2_right=rr, m4_iwhat2_zero=r0)
+    gt = np.load(os.path.join(OUT, "mvar_trials.npz"))
+    rl, rr, r0 = mtmvar.count_corr(gt["x"], int(gt["p"]), 2)
+    rec.update(tr_iwhat2_left=rl, tr_iwhat2_right=rr, tr_iwhat2_zero=r0)
+    # causal chain with Butterworth low/high-pass: any filter_type other than 'iir' takes the lfilter branch
+    raw = synth.dyad_eeg(seed=synth.BASE_SEED + 21, m=38, fs=256.0, n_samples=5000)
+    md = ds.MultimodalData()
+    md.fs = 256.0
+    names_ch = [f"c{i}" for i in range(19)]
+    names_cg = [f"c{i}_cg" for i in range(19)]
+    md.eeg_channel_names_ch = names_ch
+    md.eeg_channel_names_cg = names_cg
+    md.eeg_channel_mapping = {nm: i for i, nm in enumerate(names_ch + names_cg)}
+    fb = dataloader._design_eeg_filters(md, lowcut=1.0, highcut=40.0, filter_type="butter")
+    assert fb[3] == "butter" and np.size(fb[1][1]) == 3
+    out = raw.copy()
+    quiet(dataloader._apply_filters, md, fb, out)
+    sel = [0, 19, 37]
+    rec.update(butter_raw=raw[sel], butter_out=out[sel])
+    # the pipeline's real shape: 4 signals x 480 samples @ 8 Hz (prewindow.npz), 3 windows of 160, and 5 windows of 200
+    sig = np.load(os.path.join(OUT, "prewindow.npz"))["signals_to_ffDTF"]
+    pipe = ffd.EEG_IBI_FFDTF_Pipeline.__new__(ffd.EEG_IBI_FFDTF_Pipeline)
+    pipe.fs_ds = 8.0
+    pipe.freq_min, pipe.freq_step = 1.0, 0.1
+    pipe.freq_max = pipe.fs_ds / 2.0 - pipe.freq_step
+    names = ["faa_ch", "ibi_ch", "faa_cg", "ibi_cg"]
+    for tag, nw, ws in (("w3", 3, None), ("w5", 5, 200)):
+        wins = pipe._create_windows(sig, nw, ws)
+        for ar_p, ptag in ((5, "p5"), (None, "auto")):
+            pipe.ar_p = ar_p
+            ff, sp, po = [], [], []
+            for w in wins:
+                a, b, c = pipe._compute_ffDTF("D", w, names, 8.0, plot=False, save_plot=False)
+                ff.append(a); sp.append(b); po.append(c)
+            rec[f"{tag}_{ptag}_ffdtf"] = np.stack(ff)
+            rec[f"{tag}_{ptag}_spectra"] = np.stack(sp)
+            rec[f"{tag}_{ptag}_popt"] = np.array(po)
+        for crit in ("AIC", "HQ", "SC"):
+            rec[f"{tag}_crit_{crit}"] = np.stack([mtmvar.mvar_criterion(w, 20, crit, False)[0] for w in wins])
+            rec[f"{tag}_popt_{crit}"] = np.array([mtmvar.mvar_criterion(w, 20, crit, False)[2] for w in wins])
+    pipe.ar_p = 5
+    a, b, c = pipe._compute_ffDTF("D", sig, names, 8.0, plot=False, save_plot=False)
+    rec.update(global_p5_ffdtf=a, global_p5_spectra=b, freqs=np.arange(pipe.freq_min, pipe.freq_max + pipe.freq_step, pipe.freq_step))
+    # m = 38 windows (cfg2 fixture): criterion up to order 12
+    w38 = np.load(os.path.join(OUT, "mvar_cfg2_windows.npz"))["windows"]
+    rec["w38_crit_AIC"] = np.stack([mtmvar.mvar_criterion(w, 12, "AIC", False)[0] for w in w38])
+    np.savez_compressed(os.path.join(OUT, "round2.npz"), **rec)
+    print("round2.npz", os.path.getsize(os.path.join(OUT, "round2.npz")))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":
+        return gen_round2()
     if len(sys.argv) > 1 and sys.argv[1] == "pcoh":
         return gen_pcoh()
     if len(sys.argv) > 1 and sys.argv[1] == "prewindow":
@@ -308,6 +373,7 @@ def main():
 
     gen_pcoh()
     gen_prewindow()
+    gen_round2()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

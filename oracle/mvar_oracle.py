@@ -66,10 +66,24 @@ def yule_walker_system(R):
 
 
 def count_corr(x, ip, iwhat=1):
-    """Drop-in signature of reference ``count_corr`` (mtmvar.py:35)."""
-    if iwhat != 1:
-        raise NotImplementedError("only the biased estimator (iwhat=1) is used by callers (mtmvar.py:113)")
-    return yule_walker_system(lag_covariances(x, ip))
+    """Drop-in signature of reference ``count_corr`` (mtmvar.py:35).  ``iwhat == 2`` (mtmvar.py:60-63) scales lag
+    L = k + 1 by 1 / (n - k) instead of 1 / n; lag 0 keeps 1 / n (:72-73)."""
+    if iwhat not in (1, 2):
+        raise ValueError("iwhat must be 1 or 2")
+    R = lag_covariances(x, ip)
+    if iwhat == 2:
+        n = np.shape(x)[1]
+        x3 = np.asarray(x, dtype=np.float64)
+        if x3.ndim == 2:
+            x3 = x3[:, :, None]
+        R = R.copy()
+        for k in range(ip):
+            acc = np.zeros_like(R[0])
+            for tr in range(x3.shape[2]):
+                xt = x3[:, :, tr]
+                acc += (xt[:, : n - k - 1] @ xt[:, k + 1:].T) * (1.0 / (n - k))
+            R[k + 1] = acc / x3.shape[2] if x3.shape[2] > 1 else acc
+    return yule_walker_system(R)
 
 
 def ar_coeff(data, model_order=5):

@@ -1,0 +1,174 @@
+"""Round-2 coverage on the GPU, against vectors written by the reference's own code (tests/golden/round2.npz):
+count_corr(iwhat=2), the causal lfilter branch with recursive coefficients, batched model-order criteria, and the
+EEG_IBI_FFDTF_Pipeline class used through an INSTANCE (methods, not free functions); plus element-wise ffDTF parity."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+from scipy import signal
+
+from conftest import TOL_MODEL, TOL_SIGNAL, golden, relerr
+from test_oracle_cpu import _prewindow_inputs, elementwise_relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mv():
+    from hyperscanning_signal_analysis_b200 import mtmvar
+    return mtmvar
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def test_count_corr_unbiased_variant(mv):
+    g = golden("round2.npz")
+    m4 = golden("mvar_m4.npz")
+    rl, rr, r0 = mv.count_corr(m4["x"][:, :, None], int(m4["p"]), 2)
+    assert relerr(rl, g["m4_iwhat2_left"]) < TOL_SIGNAL and relerr(rr, g["m4_iwhat2_right"]) < TOL_SIGNAL
+    assert relerr(r0, g["m4_iwhat2_zero"]) < TOL_SIGNAL
+    tr = golden("mvar_trials.npz")
+    rl, rr, r0 = mv.count_corr(tr["x"], int(tr["p"]), 2)
+    assert relerr(rl, g["tr_iwhat2_left"]) < TOL_SIGNAL and relerr(rr, g["tr_iwhat2_right"]) < TOL_SIGNAL
+    with pytest.raises(ValueError):
+        mv.count_corr(m4["x"], 2, 3)
+
+
+def test_causal_branch_with_recursive_lowpass_highpass():
+    """filter_type='butter': not 'iir', so the reference runs the causal lfilter chain + delay roll (dataloader.py:793-801)."""
+    from hyperscanning_signal_analysis_b200 import dataloader
+    from test_frontend_gpu import _md
+    g = golden("round2.npz")
+    md = _md(256.0, 3)
+    fb = dataloader._design_eeg_filters(md, lowcut=1.0, highcut=40.0, filter_type="butter")
+    assert fb[3] == "butter" and np.size(fb[1][1]) == 3
+    buf = g["butter_raw"].copy()
+    quiet(dataloader._apply_filters, md, fb, buf)
+    assert relerr(buf, g["butter_out"]) < TOL_SIGNAL
+    assert np.all(buf[:, -2:] == 0.0)              # delay = 1 + 1 samples zeroed at the tail
+
+
+def test_batched_order_criteria(mv):
+    import torch
+    g = golden("round2.npz")
+    sig = golden("prewindow.npz")["signals_to_ffDTF"]
+    from hyperscanning_signal_analysis_b200.eeg_alpha_ibi_ffdtf import window_starts
+    x = torch.from_numpy(np.ascontiguousarray(sig)).cuda()
+    for tag, nw, ws in (("w3", 3, None), ("w5", 5, 200)):
+        starts, W = window_starts(sig.shape[1], nw, ws)
+        st = torch.from_numpy(starts).cuda()
+        for c in ("AIC", "HQ", "SC"):
+            crit, popt, status = mv.batched_mvar_criterion(x, st, sig.shape[1], nw, 4, W, 20, c)
+            assert int(status.max()) == 0
+            assert relerr(crit.cpu().numpy(), g[f"{tag}_crit_{c}"]) < TOL_MODEL
+            assert popt.cpu().numpy().tolist() == g[f"{tag}_popt_{c}"].tolist()
+            # the per-call reference signature agrees with the batch
+            c0, rng, p0 = mv.mvar_criterion(sig[:, starts[0]:starts[0] + W], 20, c)
+            assert np.array_equal(c0, crit[0].cpu().numpy()) and int(p0) == int(popt[0]) and rng.tolist() == list(range(1, 21))
+    # m = 38: orders 1..8 are well posed (tight), the nearly singular high orders to what conditioning allows
+    w38 = golden("mvar_cfg2_windows.npz")["windows"]
+    for k in range(w38.shape[0]):
+        crit = mv.mvar_criterion(w38[k], 12, "AIC")[0]
+        assert relerr(crit[:8], g["w38_crit_AIC"][k][:8]) < TOL_MODEL
+        assert relerr(crit, g["w38_crit_AIC"][k]) < 1e-4
+    with pytest.raises(ValueError):
+        mv.mvar_criterion(sig, 3, "BIC")
+
+
+def test_pipeline_class_methods_on_an_instance():
+    """Call sites written against the reference use the methods of an EEG_IBI_FFDTF_Pipeline instance."""
+    from hyperscanning_signal_analysis_b200.eeg_alpha_ibi_ffdtf import EEG_IBI_FFDTF_Pipeline
+    g = golden("round2.npz")
+    pw, x = _prewindow_inputs()
+    fs = float(pw["fs"])
+    names = [str(s) for s in pw["names"]]
+    pipe = EEG_IBI_FFDTF_Pipeline(None, None, ["M1"], fs_downsampled=8.0, n_windows=3, window_size=None, ar_p=5)
+    assert (pipe.left_chan, pipe.right_chan, pipe.fs_ds, pipe.freq_min, pipe.freq_step) == ("F3", "F4", 8.0, 1.0, 0.1)
+    assert abs(pipe.freq_max - 3.9) < 1e-12
+    rows = []
+    for who, sl, k in (("ch", slice(0, 19), 0), ("cg", slice(19, 38), 1)):
+        filt = pipe._alpha_bandpass_filter(x[sl], fs)
+        assert relerr(filt[[3, 5, 18]], pw[f"filt_{who}"]) < TOL_SIGNAL
+        faa = pipe._compute_asymmetry(filt, names, metric="amp")
+        assert relerr(faa, pw[f"faa_{who}"]) < 1e-7
+        faa_ds = pipe._downsample_signal(faa, fs, 8.0)
+        ibi_ds = pipe._downsample_signal(pw["ibi"][k], fs, 8.0)
+        assert relerr(faa_ds, pw[f"faa_ds_{who}"]) < 1e-7 and relerr(ibi_ds, pw[f"ibi_ds_{who}"]) < TOL_SIGNAL
+        rows += [pipe._crop_signal(faa_ds, 8.0, 10, 60), pipe._crop_signal(ibi_ds, 8.0, 10, 60)]
+    sig = np.vstack(rows)
+    sig = (sig - np.mean(sig, axis=1, keepdims=True)) / np.std(sig, axis=1, keepdims=True)
+    assert relerr(sig, pw["signals_to_ffDTF"]) < 1e-6
+    sig = pw["signals_to_ffDTF"]                   # continue from the reference's own array: isolates the MVAR stage
+    chan = ["faa_ch", "ibi_ch", "faa_cg", "ibi_cg"]
+    for tag, nw, ws in (("w3", 3, None), ("w5", 5, 200)):
+        pipe.n_windows, pipe.window_size = nw, ws
+        wins = pipe._create_windows(sig, nw, ws)
+        assert len(wins) == nw and all(w.base is not None for w in wins)          # views, like the reference
+        for ar_p, ptag in ((5, "p5"), (None, "auto")):
+            pipe.ar_p = ar_p
+            for k, w in enumerate(wins):
+                ff, sp, po = pipe._compute_ffDTF("D", w, chan, 8.0, plot=False, save_plot=False)
+                assert ff.shape == (4, 4, 30) and sp.dtype == np.complex128
+                assert int(po) == int(g[f"{tag}_{ptag}_popt"][k])
+                assert relerr(ff, g[f"{tag}_{ptag}_ffdtf"][k]) < TOL_MODEL
+                assert elementwise_relerr(ff, g[f"{tag}_{ptag}_ffdtf"][k]) < 1e-6
+                assert relerr(sp, g[f"{tag}_{ptag}_spectra"][k]) < TOL_MODEL
+            # the same windows as ONE batched call
+            ffw, spw, pw_ = pipe.compute_windows(sig)
+            assert [int(v) for v in pw_] == g[f"{tag}_{ptag}_popt"].tolist()
+            assert relerr(np.stack(ffw), g[f"{tag}_{ptag}_ffdtf"]) < TOL_MODEL
+            assert relerr(np.stack(spw), g[f"{tag}_{ptag}_spectra"]) < TOL_MODEL
+    pipe.ar_p = 5
+    ffg, spg, pg = pipe._compute_ffDTF("D", sig, chan, 8.0, plot=False)
+    assert pg == 5 and relerr(ffg, g["global_p5_ffdtf"]) < TOL_MODEL and relerr(spg, g["global_p5_spectra"]) < TOL_MODEL
+    with pytest.raises(ValueError):
+        pipe._create_windows(sig, 3, 100)
+    with pytest.raises(ValueError):
+        pipe._crop_signal(sig, 8.0, 10, 600)
+    with pytest.raises(ValueError):
+        pipe._compute_asymmetry(sig, ["a", "b", "c", "d"])
+    with pytest.raises(RuntimeError):
+        pipe.run_pipeline()                        # no files were scanned: same error as the reference (:662-663)
+
+
+def test_process_dyad_builds_the_reference_result(tmp_path):
+    from hyperscanning_signal_analysis_b200.eeg_alpha_ibi_ffdtf import EEG_IBI_FFDTF_Pipeline
+    g = golden("round2.npz")
+    pw, x = _prewindow_inputs()
+    names = [str(s) for s in pw["names"]]
+    pipe = EEG_IBI_FFDTF_Pipeline(None, tmp_path, ["M1"], n_windows=3, ar_p=5)
+    res = quiet(pipe.process_dyad, "W_001", "M1", x[:19], pw["ibi"][0][:, None], x[19:], pw["ibi"][1][:, None], float(pw["fs"]), float(pw["fs"]), names)
+    assert sorted(res["mvar"]) == ["ff_dtf_global", "ff_dtf_windowed", "p_opt_g", "p_opt_w", "spectra_global", "spectra_windowed"]
+    assert relerr(np.stack(res["mvar"]["ff_dtf_windowed"]), g["w3_p5_ffdtf"]) < 1e-5      # whole chain from raw EEG (FAA through a log)
+    path = quiet(pipe._save_single_result, "W_001", "M1", res)
+    z = np.load(path)
+    assert sorted(z.files) == ["ff_dtf_global", "ff_dtf_windowed", "meta", "p_opt_g", "p_opt_w", "spectra_global", "spectra_windowed"]
+    assert z["ff_dtf_windowed"].shape == (3, 4, 4, 30)
+
+
+def test_ffdtf_elementwise_above_floor(mv):
+    """Norm-wise 1e-7 leaves small entries unchecked (ffDTF spans many decades): element-wise check above 1e-6 max."""
+    g = golden("mvar_cfg2_windows.npz")
+    worst = 0.0
+    for w in range(g["windows"].shape[0]):
+        ff = quiet(mv.full_freq_dtf, g["windows"][w], g["freqs"], 256.0, optimal_model_order=8)
+        worst = max(worst, elementwise_relerr(ff, g["ffdtf"][w], 1e-6))
+    print("max element-wise relative error of ffDTF above 1e-6*max:", worst)
+    assert worst < 1e-5        # cond(G) ~ 3e7: an entry 1e-6 of the maximum keeps ~5 digits of the 1e-11 norm-wise agreement
+    m4 = golden("mvar_m4.npz")
+    ff4 = quiet(mv.full_freq_dtf, m4["x"], m4["freqs"], float(m4["fs"]), optimal_model_order=int(m4["p"]))
+    assert elementwise_relerr(ff4, m4["ffdtf"], 1e-9) < 1e-9
+
+
+def test_downsample_two_dimensional_is_axis_zero():
+    """resample_poly's default axis is 0 (the reference passes none, eeg_alpha_ibi_ffdtf.py:403)."""
+    from hyperscanning_signal_analysis_b200.eeg_alpha_ibi_ffdtf import downsample_signal
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((640, 3))
+    got = downsample_signal(x, 128, 8)
+    ref = signal.resample_poly(x, up=1, down=16)
+    assert got.shape == ref.shape == (40, 3) and relerr(got, ref) < TOL_SIGNAL

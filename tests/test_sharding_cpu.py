@@ -65,6 +65,17 @@ assert torch.equal(out[:, 0, 0, 0], torch.arange(9, dtype=torch.float64)), out[:
 # equal-count path
 out2 = sharding.all_gather_windows(torch.full((4, 3), float(rank), dtype=torch.float64), [4, 4])
 assert out2.shape == (8, 3) and out2[:4].eq(0).all() and out2[4:].eq(1).all()
+# slot layout of the gathered result and the push granularity
+assert sharding.window_layout([5, 4, 0, 3]) == [0, 5, 9, 9]
+assert sharding.chunk_ranges(24, 5) == [(0, 5), (5, 10), (10, 15), (15, 20), (20, 24)]
+assert sharding.chunk_ranges(0, 5) == []
+# cfg3: 64 dyads x 3 tasks split evenly over 1/2/4/8 ranks, whole dyads per rank
+u3 = sharding.unit_table(64, ["SECORE", "MOVIE", "TALK"])
+for wsz in (1, 2, 4, 8):
+    got = [sharding.shard_units(len(u3), r, wsz) for r in range(wsz)]
+    assert all(len(g) == len(u3) // wsz for g in got) and sum(len(g) for g in got) == 192
+    for g in got:
+        assert {u3[i][0] for i in g} & {u3[i][0] for h in got if h is not g for i in h} == set()
 # max-over-ranks timing reduction used by bench.py
 t = torch.tensor([1.0 + rank], dtype=torch.float64)
 dist.all_reduce(t, op=dist.ReduceOp.MAX)

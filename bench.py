@@ -328,6 +328,7 @@ def measure_cfg2(args, lib, mtmvar, _lib, torch, dist, world, rank, local, with_
            "host_numa_binding": res.get("numa", "none")}
     assert abs(float(out_np[0].sum()) - M) < 1e-6
     # the same call with the result left in the plan's own pinned buffer (what run(out=None) returns a view of)
+    view = plan.run(x_np, starts, freqs, FS)              # first call page-locks the plan's own result buffer (not timed)
     t0 = time.perf_counter()
     view = plan.run(x_np, starts, freqs, FS)
     e2e["value_plan_owned_output"] = n_win / (time.perf_counter() - t0)
@@ -578,14 +579,29 @@ def measure_cfg3(args, lib, _lib, torch, dist, world, rank, local):
           "what_is_gathered": "the full (windows, 38, 38, 256) float64 ffDTF of every (dyad, task, window): what the reference persists "
                               "(eeg_alpha_ibi_ffdtf.py:647-656)",
           "nvlink_in_gbs_per_rank": recv * args.steps / (total_ms * 1e-3) * 1e-9, "nvlink_peer_copy_gbs_reference": 770.0}
-    # the same shard without any exchange, and with the exchange as ONE NCCL all-gather after the compute (the baseline)
+    # the same shard without any exchange, with the exchange as ONE NCCL all-gather after the compute (the baseline), and with
+    # the other push mechanisms (each a few steps; `value` above is the --gather mode)
     extra_steps = max(2, min(args.steps, 3))
-    for mode, key in (("none", "value_excl_allgather"), ("nccl", "value_nccl_allgather_after_compute")):
+    others = [("none", "value_excl_allgather"), ("nccl", "value_nccl_allgather_after_compute"), ("ce", "value_push_copy_engines"),
+              ("p2p", "value_push_store_kernel")]
+    if sh.buf.multicast_ptr:
+        others.append(("multicast", "value_push_multicast_kernel"))
+    for mode, key in others:
+        if mode == push:
+            ag[key] = out["value"]
+            continue
         sh.push = mode
+        sh.sm_limit = sh.sm_total - sh.push_ctas if mode in ("p2p", "multicast") else 0
+        _lib.check(lib.hs_set_compute_sm_limit(sh.sm_limit), "hs_set_compute_sm_limit")
         ms2, _ = timed(sh, extra_steps, 1)
         ag[key] = total_windows * extra_steps / (ms2 * 1e-3)
     sh.push = push
-    ag["overlap_efficiency_vs_max(compute, gather)"] = None
+    # what bounds the step: this rank's compute (value_excl_allgather) or the bytes it must RECEIVE over NVLink
+    link = 770.0
+    t_gather = recv / (link * 1e9)
+    t_compute = total_windows / ag["value_excl_allgather"]
+    ag["bound"] = {"compute_s": t_compute, "nvlink_receive_s_at_770GBs": t_gather, "step_s": total_ms * 1e-3 / args.steps,
+                   "frac_of_max(compute, receive)": max(t_compute, t_gather) / (total_ms * 1e-3 / args.steps)}
     out["allgather"] = ag
     sh.close()
     del sh, x_all
@@ -662,11 +678,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="N=1: skip the cfg4 front-end and cfg5 stress legs")
-    ap.add_argument("--gather", default="p2p", choices=["p2p", "multicast", "ce", "nccl"],
+    ap.add_argument("--gather", default="ce", choices=["ce", "p2p", "multicast", "nccl"],
                     help="N>1: how a finished chunk reaches the peers (own store kernel over peer mappings / NVSwitch multicast, copy engines, "
                          "or one NCCL all-gather after the compute)")
     ap.add_argument("--gather-buffer", default="auto", choices=["auto", "symm", "ipc"])
-    ap.add_argument("--push-ctas", type=int, default=8)
+    ap.add_argument("--push-ctas", type=int, default=16)
     ap.add_argument("--chunk-units", type=int, default=5, help="N>1: tasks per chunk (5 x 119 windows ~ one cfg2 batch)")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 on their own (NCCL prints its version

@@ -60,6 +60,7 @@ SIGNATURES = {
     "hs_fir_decimate_f64": (c_int, [c_dp, c_int, c_i64, c_i64, c_int, c_dp, c_int, c_dp, c_i64, c_dp]),
     "hs_hilbert_ws_bytes": (c_sz, [c_int, c_i64]),
     "hs_hilbert_f64": (c_int, [c_dp, c_int, c_i64, c_i64, c_i64, c_dp, c_i64, c_dp, c_dp, c_dp]),
+    "hs_mt_psd_set_path": (c_int, [c_int]),
     "hs_mt_psd_ws_bytes": (c_sz, [c_int, c_i64, c_int]),
     "hs_mt_psd_f64": (c_int, [c_dp, c_int, c_i64, c_dp, c_dp, c_int, c_int, c_int, c_dp, c_dp, c_dp]),
 }

@@ -639,266 +639,6 @@ __global__ void __launch_bounds__(kDecThreads) fir_decimate_kernel(const double*
         if (k0 + o0 + i < n_out) ys[i] = acc[i];
 }
 
-// =====================================================================================
-// K6  multitaper PSD (mne.time_frequency.psd_array_multitaper defaults reached through
-//     compute_psd_multitaper, src/psd.py:30-32; restated in SURVEY.md A.6):
-//       x0 = x - mean(x);  X_k = rfft(x0 * taper_k);  DC (and Nyquist for even n) / sqrt(2);
-//       psd = sum_k |w_k X_k|^2 * 2 / sum_k w_k^2,   w_k = sqrt(eigval_k).
-//     No cuFFT: a hand-written transform in shared memory.  n = N1 * N2 with N2 the power-of-two part:
-//       1. direct DFT of length N1 over the stride-N2 subsequences (reads x0*taper straight from global),
-//       2. twiddle W_n^(t2 k1),
-//       3. N1 in-place radix-2 DIF FFTs of length N2 (output left in bit-reversed order and read that way).
-//     Two tapers are packed into one complex transform (z = x0 h_a + i x0 h_b) and separated in the power sum:
-//       |X_a[k]|^2 = |Z[k] + conj Z[n-k]|^2 / 4,   |X_b[k]|^2 = |Z[k] - conj Z[n-k]|^2 / 4.
-//     The (signals x tapers x n) complex intermediate never leaves the SM.
-// =====================================================================================
-constexpr size_t kPsdSmemMax = 200 * 1024;
-constexpr int kPsdThreads = 512;
-
-// Taper-pair groups per signal: CTAs = n_sig * groups run one per SM (the FFT buffer fills the shared memory), so the group
-// count is chosen to fill whole waves of 148 CTAs (342 segments: 1 group = 2.3 waves -> 3 rounds, 3 groups = 6.93 -> 7 rounds).
-static int psd_groups(int n_sig, int pairs) {
-    const int sm = 148;            // sizing only (also used by the GPU-less workspace query); any SM count gives a valid split
-    int best = 1;
-    double best_eff = 0.0;
-    for (int g = 1; g <= 8 && g <= pairs; ++g) {
-        const double waves = (double)n_sig * g / sm;
-        const double rounds = (double)((long long)((n_sig * (long long)g + sm - 1) / sm));
-        const double eff = waves / rounds - 0.004 * g;      // small penalty: every CTA recomputes the mean and reloads the twiddles
-        if (eff > best_eff) { best_eff = eff; best = g; }
-    }
-    return best;
-}
-
-__global__ void twiddle_kernel(double2* w, long long n) {
-    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    double s, c;
-    sincospi(-2.0 * (double)j / (double)n, &s, &c);      // exp(-2 pi i j / n)
-    w[j] = make_double2(c, s);
-}
-
-__device__ __forceinline__ unsigned bitrev_bits(unsigned v, int bits) { return bits ? (__brev(v) >> (32 - bits)) : 0u; }
-__device__ __forceinline__ double2 cmul(const double2 a, const double2 b) {
-    return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
-}
-
-struct PsdParams {
-    const double* x;         // (n_sig, n)
-    const double* tapers;    // (K, n)
-    const double* weights;   // (K)
-    const double2* tw;       // (n) W_n^j
-    double2* gbuf;           // global FFT buffers (n_sig*groups, n) when n*16 B does not fit shared memory, else null
-    double* partial;         // (n_sig, groups, nb)
-    long long n;
-    int n1, n2, log2n2;      // n = n1 * n2, n2 = 2^log2n2
-    int K, groups, k_lo, nb, n_sig;
-    int tw_in_smem;          // 1: the half twiddle table sits behind the FFT buffer in shared memory
-    int skew;                // 1: FFT buffer in shared memory with the i + (i >> 3) layout
-};
-
-__global__ void __launch_bounds__(kPsdThreads, 1) mt_psd_kernel(const PsdParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int sig = blockIdx.x / P.groups, grp = blockIdx.x % P.groups;
-    const long long n = P.n;
-    const int n1 = P.n1, n2 = P.n2;
-    double* acc = reinterpret_cast<double*>(smem_raw);                       // [nb]
-    double2* buf = P.gbuf ? (P.gbuf + (size_t)blockIdx.x * n)
-                          : reinterpret_cast<double2*>(smem_raw + (((size_t)P.nb * sizeof(double) + 15) / 16) * 16);
-    // Shared-memory layout of the FFT buffer: element i sits at i + (i >> 3) (one 16-byte pad per 128-byte row), so the strided
-    // accesses of the late stages (stride 4, 16, ... elements) and the bit-reversed read-out spread over the banks
-    // (61 % of the wavefronts were bank-conflict replays without it).  No skew for the global-memory fallback.
-    const int skew = P.skew;
-    auto sk = [skew](const long long i) -> long long { return skew ? i + (i >> 3) : i; };
-    double2* tws = P.tw_in_smem ? buf + (n + (n >> 3) + 1) : nullptr;        // W_n^j, j < n/2 (only with the shared-memory FFT buffer)
-    if (tws)
-        for (int e = threadIdx.x; e < (int)(n >> 1); e += kPsdThreads) tws[e] = P.tw[e];
-    __shared__ double red[kPsdThreads];
-    const double* xs = P.x + (size_t)sig * n;
-    const int tid = threadIdx.x;
-
-    // mean of the signal (fixed-order tree)
-    double a0 = 0.0;
-    for (long long t = tid; t < n; t += kPsdThreads) a0 += xs[t];
-    red[tid] = a0;
-    __syncthreads();
-    for (int off = kPsdThreads / 2; off > 0; off >>= 1) {
-        if (tid < off) red[tid] += red[tid + off];
-        __syncthreads();
-    }
-    const double mean = red[0] / (double)n;
-    for (int b = tid; b < P.nb; b += kPsdThreads) acc[b] = 0.0;
-
-    const int pairs = (P.K + 1) / 2;
-    for (int pr = grp; pr < pairs; pr += P.groups) {
-        const int ka = 2 * pr, kb = 2 * pr + 1;
-        const double* ha = P.tapers + (size_t)ka * n;
-        const double* hb = (kb < P.K) ? P.tapers + (size_t)kb * n : nullptr;
-        const double wa = P.weights[ka], wb = hb ? P.weights[kb] : 0.0;
-        __syncthreads();
-        // ---- step 1+2: Y[k1][t2] = W_n^(t2 k1) * sum_t1 z[n2 t1 + t2] W_n1^(t1 k1)
-        for (long long e = tid; e < n; e += kPsdThreads) {
-            const int k1 = (int)(e / n2), t2 = (int)(e - (long long)k1 * n2);
-            double2 y;
-            if (n1 == 1) {
-                const double v = xs[t2] - mean;
-                y = make_double2(v * ha[t2], hb ? v * hb[t2] : 0.0);
-            } else {
-                double yr = 0.0, yi = 0.0;
-                long long tw_idx = 0;                               // (n2 * t1 * k1) mod n
-                const long long tw_step = ((long long)n2 * k1) % n;
-                for (int t1 = 0; t1 < n1; ++t1) {
-                    const long long t = (long long)n2 * t1 + t2;
-                    const double v = xs[t] - mean;
-                    const double2 z = make_double2(v * ha[t], hb ? v * hb[t] : 0.0);
-                    const double2 wv = P.tw[tw_idx];
-                    yr += fma(z.x, wv.x, -z.y * wv.y);
-                    yi += fma(z.x, wv.y, z.y * wv.x);
-                    tw_idx += tw_step;
-                    if (tw_idx >= n) tw_idx -= n;
-                }
-                y = cmul(make_double2(yr, yi), P.tw[((long long)t2 * k1) % n]);
-            }
-            buf[sk(e)] = y;
-        }
-        __syncthreads();
-        // ---- step 3: n1 independent in-place DIF FFTs of length n2 (32-bit index arithmetic, shifts only).  Two radix-2 stages
-        //      are fused into one radix-4 pass (same data placement as the two stages, so the bit-reversed read-out below is
-        //      unchanged): half the passes through shared memory and half the barriers; a single radix-2 stage is left over
-        //      when log2(n2) is odd.  Twiddles come from the shared-memory half table when it fits (tws), else from L2.
-        {
-            const int ni = (int)n;
-            auto twid = [&](const int idx) -> double2 {
-                if (tws) {
-                    const int h = ni >> 1;
-                    const double2 v = tws[idx >= h ? idx - h : idx];
-                    return idx >= h ? make_double2(-v.x, -v.y) : v;             // W^(k + n/2) = -W^k
-                }
-                return P.tw[idx];
-            };
-            int s = P.log2n2 - 1;
-            for (; s >= 1; s -= 2) {
-                const int q4 = 1 << (s - 1);                                    // quarter of the block length L = 2^(s+1)
-                const int tw_mul = ni >> (s + 1);                               // W_L^j = W_n^(j * n / L)
-                for (int r = tid; r < (ni >> 2); r += kPsdThreads) {
-                    const int j = r & (q4 - 1);
-                    const int e0 = ((r >> (s - 1)) << (s + 1)) + j;
-                    double2* pa = buf + sk(e0);
-                    double2* pb = buf + sk(e0 + q4);
-                    double2* pc = buf + sk(e0 + 2 * q4);
-                    double2* pd = buf + sk(e0 + 3 * q4);
-                    const double2 a = *pa, b = *pb, c = *pc, d = *pd;
-                    const double2 w1 = twid(j * tw_mul), w2 = twid(2 * j * tw_mul), w3 = twid(3 * j * tw_mul);
-                    const double2 apc = make_double2(a.x + c.x, a.y + c.y), amc = make_double2(a.x - c.x, a.y - c.y);
-                    const double2 bpd = make_double2(b.x + d.x, b.y + d.y), bmd = make_double2(b.x - d.x, b.y - d.y);
-                    *pa = make_double2(apc.x + bpd.x, apc.y + bpd.y);
-                    *pb = cmul(make_double2(apc.x - bpd.x, apc.y - bpd.y), w2);
-                    *pc = cmul(make_double2(amc.x + bmd.y, amc.y - bmd.x), w1);            // (a - c) - i (b - d)
-                    *pd = cmul(make_double2(amc.x - bmd.y, amc.y + bmd.x), w3);            // (a - c) + i (b - d)
-                }
-                __syncthreads();
-            }
-            if (s == 0) {                                                       // last radix-2 stage: blocks of 2, twiddle 1
-                for (int r = tid; r < (ni >> 1); r += kPsdThreads) {
-                    double2* p = buf + sk(2 * r);                               // 2 r and 2 r + 1 share a row of 8: adjacent
-                    const double2 u = p[0], v = p[1];
-                    p[0] = make_double2(u.x + v.x, u.y + v.y);
-                    p[1] = make_double2(u.x - v.x, u.y - v.y);
-                }
-                __syncthreads();
-            }
-        }
-        // ---- power of both tapers at the requested bins; X[k1 + n1 k2] sits at buf[k1 * n2 + bitrev(k2)]
-        for (int b = tid; b < P.nb; b += kPsdThreads) {
-            const long long k = P.k_lo + b, km = (n - k) % n;
-            const double2 z = buf[sk((k % n1) * (long long)n2 + bitrev_bits((unsigned)(k / n1), P.log2n2))];
-            const double2 zm = buf[sk((km % n1) * (long long)n2 + bitrev_bits((unsigned)(km / n1), P.log2n2))];
-            const double sr = z.x + zm.x, si = z.y - zm.y;          // Z[k] + conj Z[n-k]  = 2 X_a[k]
-            const double dr = z.x - zm.x, di = z.y + zm.y;          // Z[k] - conj Z[n-k]  = 2 i X_b[k]
-            const double pa = 0.25 * fma(sr, sr, si * si), pb = 0.25 * fma(dr, dr, di * di);
-            acc[b] += fma(wa * wa, pa, wb * wb * pb);
-        }
-    }
-    __syncthreads();
-    double* out = P.partial + ((size_t)sig * P.groups + grp) * P.nb;
-    for (int b = tid; b < P.nb; b += kPsdThreads) out[b] = acc[b];
-}
-
-__global__ void mt_psd_finish_kernel(const double* partial, const double* weights, int K, int groups, int nb, int k_lo, long long n,
-                                     double* psd) {
-    const int sig = blockIdx.y;
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nb) return;
-    double wsum = 0.0;
-    for (int k = 0; k < K; ++k) wsum = fma(weights[k], weights[k], wsum);
-    double acc = 0.0;
-    for (int g = 0; g < groups; ++g) acc += partial[((size_t)sig * groups + g) * nb + b];
-    const long long k = k_lo + b;
-    if (k == 0 || ((n & 1) == 0 && k == n / 2)) acc *= 0.5;          // amplitude / sqrt(2) at DC and Nyquist
-    psd[(size_t)sig * nb + b] = acc * 2.0 / wsum;
-}
-
-static int launch_mt_psd(const double* x, int n_sig, long long n, const double* tapers, const double* weights, int K, int k_lo,
-                         int k_hi, double* psd, void* d_ws, cudaStream_t st) {
-    PsdParams P;
-    P.x = x;
-    P.tapers = tapers;
-    P.weights = weights;
-    P.n = n;
-    long long n2 = 1;
-    int l2 = 0;
-    while (((n / n2) & 1) == 0) { n2 <<= 1; ++l2; }
-    if (n / n2 > 4096) return set_error(HS_ERR_UNSUPPORTED, "hs_mt_psd_f64: odd factor %lld of n=%lld is too large for the direct stage", n / n2, n);
-    P.n1 = (int)(n / n2);
-    P.n2 = (int)n2;
-    P.log2n2 = l2;
-    P.K = K;
-    P.k_lo = k_lo;
-    P.nb = k_hi - k_lo;
-    P.n_sig = n_sig;
-    const int pairs = (K + 1) / 2;
-    P.groups = psd_groups(n_sig, pairs);
-    unsigned char* ws = reinterpret_cast<unsigned char*>(d_ws);
-    double2* tw = reinterpret_cast<double2*>(ws);
-    ws += ((size_t)n * 16 + 255) / 256 * 256;
-    P.tw = tw;
-    P.partial = reinterpret_cast<double*>(ws);
-    // NOTE: sized with (n/2+1) bins per partial spectrum in hs_mt_psd_ws_bytes
-    ws += ((size_t)n_sig * P.groups * (n / 2 + 1) * sizeof(double) + 255) / 256 * 256;
-    const size_t accb = (((size_t)P.nb * sizeof(double) + 15) / 16) * 16;
-    const size_t buf_elems = (size_t)n + (size_t)(n >> 3) + 1;        // skewed layout: one pad element per row of 8
-    const size_t smem_plain = accb + (size_t)n * 16, smem_skew = accb + buf_elems * 16;
-    size_t smem;
-    P.gbuf = nullptr;
-    P.tw_in_smem = 0;
-    P.skew = 0;
-    if (smem_skew + (size_t)(n / 2) * 16 <= 220 * 1024 && (n & 1) == 0) {       // skewed buffer + half twiddle table
-        smem = smem_skew + (size_t)(n / 2) * 16;
-        P.tw_in_smem = 1;
-        P.skew = 1;
-    } else if (smem_skew <= kPsdSmemMax) {                                       // skewed buffer, twiddles from L2
-        smem = smem_skew;
-        P.skew = 1;
-    } else if (smem_plain <= kPsdSmemMax) {                                      // plain buffer
-        smem = smem_plain;
-    } else {                                                                     // FFT buffer in global memory
-        P.gbuf = reinterpret_cast<double2*>(ws);
-        smem = accb;
-        if (smem > 200 * 1024) return set_error(HS_ERR_UNSUPPORTED, "hs_mt_psd_f64: too many bins requested");
-    }
-    twiddle_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tw, n);
-    int rc = check_launch("twiddle_kernel");
-    if (rc) return rc;
-    cudaError_t e = cudaFuncSetAttribute(mt_psd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "mt_psd: %s", cudaGetErrorString(e));
-    mt_psd_kernel<<<n_sig * P.groups, kPsdThreads, smem, st>>>(P);
-    rc = check_launch("mt_psd_kernel");
-    if (rc) return rc;
-    dim3 grid((P.nb + 255) / 256, n_sig);
-    mt_psd_finish_kernel<<<grid, 256, 0, st>>>(P.partial, weights, K, P.groups, P.nb, k_lo, n, psd);
-    return check_launch("mt_psd_finish_kernel");
-}
-
 }  // namespace hs
 
 using namespace hs;
@@ -1101,26 +841,6 @@ int hs_fir_decimate_f64(const double* d_x, int n_sig, int64_t n, int64_t sig_str
     if (ntaps < 1 || (ntaps & 1) == 0) return set_error(HS_ERR_INVALID, "hs_fir_decimate_f64: q >= 1 and an odd tap count are required");
     if (q < 1) return set_error(HS_ERR_INVALID, "hs_fir_decimate_f64: q >= 1 and an odd tap count are required");
     return hs_fir_filter_f64(d_x, n_sig, n, sig_stride, q, (ntaps - 1) / 2, d_b, ntaps, d_y, (n + q - 1) / q, y_stride, stream);
-}
-
-size_t hs_mt_psd_ws_bytes(int n_sig, int64_t n, int K) {
-    if (n_sig <= 0 || n <= 0 || K <= 0) return 256;
-    const int pairs = (K + 1) / 2;
-    int groups = psd_groups(n_sig, pairs);
-    size_t b = 0;
-    b += ((size_t)n * 16 + 255) / 256 * 256;                                          // twiddle table W_n^j
-    b += ((size_t)n_sig * groups * (n / 2 + 1) * sizeof(double) + 255) / 256 * 256;   // partial spectra
-    if ((size_t)n * 16 + (size_t)(n / 2 + 1) * 8 + 16 > kPsdSmemMax) b += ((size_t)n_sig * groups * n * 16 + 255) / 256 * 256;   // global FFT buffers
-    return b + 256;
-}
-
-int hs_mt_psd_f64(const double* d_x, int n_sig, int64_t n, const double* d_tapers, const double* d_weights, int K, int k_lo,
-                  int k_hi, double* d_psd, void* d_ws, void* stream) {
-    if (!d_x || !d_tapers || !d_weights || !d_psd || !d_ws) return set_error(HS_ERR_INVALID, "hs_mt_psd_f64: null pointer");
-    if (n < 2 || K < 1 || k_lo < 0 || k_hi > n / 2 + 1 || k_lo > k_hi) return set_error(HS_ERR_INVALID, "hs_mt_psd_f64: bad sizes");
-    if (n > (1 << 24)) return set_error(HS_ERR_UNSUPPORTED, "hs_mt_psd_f64: n too large");
-    if (n_sig <= 0 || k_lo == k_hi) return HS_OK;
-    return launch_mt_psd(d_x, n_sig, (long long)n, d_tapers, d_weights, K, k_lo, k_hi, d_psd, d_ws, (cudaStream_t)stream);
 }
 
 }

@@ -14,6 +14,7 @@
 #include <cmath>
 #include <vector>
 
+#include "fft_internal.h"
 #include "hs_internal.h"
 
 namespace hs {
@@ -135,6 +136,26 @@ bool factorize(long long N, std::vector<int>& radices) {
 }
 
 }  // namespace
+
+bool fft_smooth(long long N) {
+    std::vector<int> r;
+    return N >= 1 && factorize(N, r);
+}
+
+int fft_forward_batched(double2*& a, double2*& b, int batch, long long N, cudaStream_t st) {
+    std::vector<int> radices;
+    if (!factorize(N, radices)) return set_error(HS_ERR_UNSUPPORTED, "fft: N = %lld has a prime factor > %d", N, kMaxRadix);
+    // the batch index is the grid's y dimension (<= 65535 rows per launch)
+    for (int b0 = 0; b0 < batch; b0 += 65535) {
+        const int nb = batch - b0 < 65535 ? batch - b0 : 65535;
+        double2* aa = a + (size_t)b0 * N;
+        double2* bb = b + (size_t)b0 * N;
+        int rc = fft_passes(aa, bb, nb, N, radices, st);
+        if (rc) return rc;
+    }
+    if (radices.size() & 1) { double2* t = a; a = b; b = t; }
+    return HS_OK;
+}
 
 }  // namespace hs
 

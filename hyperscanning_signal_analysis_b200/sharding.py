@@ -98,11 +98,18 @@ def window_layout(counts: Sequence[int]) -> List[int]:
     return out
 
 
-def chunk_ranges(n_units: int, units_per_chunk: int) -> List[Tuple[int, int]]:
-    """Contiguous [lo, hi) unit ranges of at most ``units_per_chunk`` units (the push granularity)."""
+def chunk_ranges(n_units: int, units_per_chunk: int, ramp: bool = False) -> List[Tuple[int, int]]:
+    """Contiguous [lo, hi) unit ranges of at most ``units_per_chunk`` units (the push granularity).  ``ramp``: the first
+    chunks hold 1 and 2 units, so the exchange starts after a fraction of a full chunk's compute time."""
     if units_per_chunk < 1:
         raise ValueError("units_per_chunk must be >= 1")
-    return [(lo, min(n_units, lo + units_per_chunk)) for lo in range(0, n_units, units_per_chunk)]
+    out, lo, k = [], 0, 0
+    while lo < n_units:
+        size = min(units_per_chunk, 1 << k) if ramp else units_per_chunk
+        out.append((lo, min(n_units, lo + size)))
+        lo += size
+        k += 1
+    return out
 
 
 class GatherBuffer:
@@ -182,8 +189,9 @@ class GatherBuffer:
         return self.peer_ptrs[self.rank]
 
     def remote_ptrs(self) -> List[int]:
-        """Mapped base pointers of the OTHER ranks' buffers."""
-        return [p for r, p in enumerate(self.peer_ptrs) if r != self.rank]
+        """Mapped base pointers of the OTHER ranks' buffers, in rotation order (rank+1, rank+2, ...): when every rank walks
+        its list in step, each GPU receives from one sender at a time instead of all ranks converging on rank 0 first."""
+        return [self.peer_ptrs[(self.rank + d) % self.world] for d in range(1, self.world)]
 
     def close(self):
         import torch
@@ -214,12 +222,14 @@ class ShardedFfdtf:
     ``x_all``: CUDA float64 ``(n_units_local, m, T)`` (all units the same length), windows ``starts`` (the same for every
     unit, ``_create_windows``), so unit u / window k is global window ``rank_offset + u * n_win + k`` of the gathered
     ``(total_windows, m, m, F)`` tensor.  Every rank must own the same number of units (pad with repeats otherwise).
-    push: 'p2p' (stores to every peer mapping), 'multicast' (multimem.st, needs mode 'symm' with a multicast pointer),
-    'ce' (copy engines), 'nccl' (one all_gather_into_tensor per chunk; chunk-major result layout differs -- baseline only).
+    push: 'ce' (one peer copy per destination on the copy engines: measured fastest, 774 GB/s in per rank at N = 2, and it
+    leaves every SM to the MVAR kernels), 'p2p' (gather_push_kernel: stores to every peer mapping, 650 GB/s with 16 CTAs),
+    'multicast' (gather_push_kernel with multimem.st through the NVSwitch multicast mapping; needs mode 'symm'),
+    'nccl' (ONE in-place all_gather_into_tensor after the last chunk: the unoverlapped baseline), 'none' (no exchange).
     """
 
-    def __init__(self, n_units_local, m, T, window_size, starts, freqs, fs, p, units_per_chunk=5, push="p2p", push_ctas=8,
-                 buffer_mode="auto"):
+    def __init__(self, n_units_local, m, T, window_size, starts, freqs, fs, p, units_per_chunk=5, push="ce", push_ctas=16,
+                 buffer_mode="auto", ramp=True):
         import ctypes as C
         import numpy as np
         import torch
@@ -239,7 +249,7 @@ class ShardedFfdtf:
         self.win_local = self.n_units * self.n_win
         self.total_windows = self.win_local * self.world
         self.rank_offset = self.rank * self.win_local
-        self.chunks = chunk_ranges(self.n_units, units_per_chunk)
+        self.chunks = chunk_ranges(self.n_units, units_per_chunk, ramp=ramp and self.world > 1)
         self.push = push
         self.push_ctas = int(push_ctas)
         dev = torch.device("cuda", torch.cuda.current_device())
@@ -261,9 +271,9 @@ class ShardedFfdtf:
         remote = self.buf.remote_ptrs()
         self._n_remote = len(remote)
         self._remote = remote
-        sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        self.sm_total = torch.cuda.get_device_properties(dev).multi_processor_count
         # the push kernel's CTAs need SMs of their own next to K5 (one K5 CTA owns a whole SM's register file)
-        self.sm_limit = sm - self.push_ctas if (self.world > 1 and push in ("p2p", "multicast")) else 0
+        self.sm_limit = self.sm_total - self.push_ctas if (self.world > 1 and push in ("p2p", "multicast")) else 0
         self._check(self.lib.hs_set_compute_sm_limit(self.sm_limit), "hs_set_compute_sm_limit")
 
     def _peer_array(self, elem_off):

@@ -217,8 +217,13 @@ int hs_fir_decimate_f64(const double* d_x, int n_sig, int64_t n, int64_t sig_str
  * compute_psd_multitaper, src/psd.py:30-32): remove mean, taper, FFT, eigenvalue-weighted power.
  *   d_x (n_sig, n)   d_tapers (K, n)   d_weights (K) = sqrt(eigvals)
  *   bins k_lo..k_hi-1 of the rfft grid are returned in d_psd (n_sig, k_hi-k_lo).
- * Hand-written FFT (no cuFFT): any n (power-of-two direct, otherwise Bluestein).             */
+ * Hand-written FFTs (no cuFFT), ANY n < 2^24: n = 4096 / 8192 in registers (radix-16 stages), n = n1 * 2^a with a small odd
+ * n1 in shared memory, every other length through the batched global-memory mixed-radix transform -- directly when all
+ * prime factors are <= 31, otherwise as Bluestein's chirp-z over a power-of-two length >= 2n - 1.                     */
 size_t hs_mt_psd_ws_bytes(int n_sig, int64_t n, int K);
+/* Test / measurement hook: force one of the paths for the following calls (0 automatic, 1 register radix-16,
+ * 2 shared memory, 3 general); call hs_mt_psd_ws_bytes again after changing it.  Process-wide.                    */
+int hs_mt_psd_set_path(int path);
 int hs_mt_psd_f64(const double* d_x, int n_sig, int64_t n, const double* d_tapers, const double* d_weights, int K,
                   int k_lo, int k_hi, double* d_psd, void* d_ws, void* stream);
 

@@ -345,6 +345,225 @@ __global__ void __launch_bounds__(kTileThreads) iir_tile_apply_kernel(const IirP
     }
 }
 
+// ------------------------------------------------------------------ K1, single-pass tiled sweep (decoupled look-back)
+// tile_local + carry + tile_apply read the signal twice per sweep.  Here ONE kernel does the sweep: a CTA takes a ticket
+// (tiles of a signal in sweep order), stages its tile once, computes the tile's zero-state end state e (its "aggregate"),
+// publishes it, and then obtains its true start state by LOOKING BACK over the predecessors' records:
+//      s_in(t) = e(t-1) + Q e(t-2) + Q^2 e(t-3) + ... ,   Q = M^8192,
+// stopping at the first predecessor that already published its inclusive state, at the beginning of the signal
+// (s_0 = zi * x_0), or when Q^k has decayed below 1e-100 (stable filters: |Q| ~ 1e-15 for the loader's 1 Hz high-pass at
+// 1024 Hz, so one or two records are read).  Tickets make the wait deadlock free: every predecessor holds an earlier
+// ticket, i.e. it is already running.  Records are tagged with the sweep number, so they are cleared once per call, not
+// per sweep.  Per sweep: 1 coalesced read + 1 coalesced write of the signal.
+struct IirLookback {
+    double* agg;         // (n_sig, n_tiles, 2) zero-state end state of every tile
+    double* incl;        // (n_sig, n_tiles, 2) true end state
+    int* flags;          // (n_sig, n_tiles) 2 sw + 1: aggregate published, 2 sw + 2: inclusive published
+    unsigned* ticket;    // one counter per sweep of the call
+    int sweep;           // sweep number within the call
+};
+
+__device__ __forceinline__ int ld_flag(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_flag(int* p, const int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+template <int D>
+__global__ void __launch_bounds__(kTileThreads) iir_tile_fused_kernel(const IirPass P, const IirCoef c, const IirCoef ct, const double* __restrict__ ppow,
+                                                                       const IirLookback S) {
+    extern __shared__ double tile_sm[];
+    __shared__ double red[kTileThreads / 32][2];
+    __shared__ double wtot[kTileThreads / 32][2];
+    __shared__ double e_sh[2], sin_sh[2];
+    __shared__ unsigned tk_sh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) tk_sh = atomicAdd(S.ticket, 1u);
+    __syncthreads();
+    const long long n_tiles = P.n_chunks;
+    const int s = (int)(tk_sh / n_tiles);
+    const long long tile = tk_sh - (long long)s * n_tiles;
+    double z[D];
+    tile_stage_and_local<D>(P, c, tile_sm, s, tile, z);
+    // ---- aggregate of the tile: e = sum_t P^(255-t) z_t (fixed-order block reduction)
+    {
+        double w[D];
+        mv2<D>(ppow + (size_t)(kTileThreads - 1 - threadIdx.x) * 4, z, w);
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) w[k] += __shfl_xor_sync(0xffffffffu, w[k], off);
+            if (lane == 0) red[warp][k] = w[k];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < D) {
+        double acc = 0.0;
+        for (int q = 0; q < kTileThreads / 32; ++q) acc += red[q][threadIdx.x];
+        e_sh[threadIdx.x] = acc;
+    }
+    __syncthreads();
+    // ---- look-back (warp 0): publish the aggregate, combine the predecessors' records, publish the inclusive state
+    if (warp == 0) {
+        const long long rec0 = (long long)s * n_tiles;
+        const int f_agg = 2 * S.sweep + 1, f_incl = 2 * S.sweep + 2;
+        double e[D];
+#pragma unroll
+        for (int q = 0; q < D; ++q) e[q] = e_sh[q];
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < D; ++q) S.agg[(rec0 + tile) * 2 + q] = e[q];
+            st_flag(S.flags + rec0 + tile, f_agg);
+        }
+        const double* base = P.in + (long long)s * P.in_sig_stride;
+        const double dc = P.mean ? P.mean[s] : 0.0;
+        double acc[D], Pw[D][D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            acc[i] = 0.0;
+#pragma unroll
+            for (int j = 0; j < D; ++j) Pw[i][j] = (i == j) ? 1.0 : 0.0;
+        }
+        bool done = false;
+        long long j0 = tile - 1;
+        while (!done) {
+            const long long j = j0 - lane;
+            int f = 0;
+            double a[D];
+#pragma unroll
+            for (int q = 0; q < D; ++q) a[q] = 0.0;
+            if (j >= 0) {
+                do { f = ld_flag(S.flags + rec0 + j); } while (f < f_agg);
+                const double* src = (f == f_incl) ? S.incl : S.agg;
+#pragma unroll
+                for (int q = 0; q < D; ++q) a[q] = __ldcg(src + (rec0 + j) * 2 + q);
+            }
+            for (int l = 0; l < 32 && !done; ++l) {
+                const int fl = __shfl_sync(0xffffffffu, f, l);
+                double al[D];
+#pragma unroll
+                for (int q = 0; q < D; ++q) al[q] = __shfl_sync(0xffffffffu, a[q], l);
+                if (j0 - l < 0) {      // beginning of the signal: s_0 = zi * x_0 (the first sample of the extended sweep)
+                    const double x0 = sweep_read(P, base, dc, 0);
+#pragma unroll
+                    for (int q = 0; q < D; ++q) al[q] = c.zi[q] * x0;
+                    done = true;
+                } else if (fl == f_incl) {
+                    done = true;
+                }
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    double v = acc[i];
+#pragma unroll
+                    for (int q = 0; q < D; ++q) v = fma(Pw[i][q], al[q], v);
+                    acc[i] = v;
+                }
+                if (!done) {           // Pw <- Pw Q
+                    double nx[D][D], mx = 0.0;
+#pragma unroll
+                    for (int i = 0; i < D; ++i)
+#pragma unroll
+                        for (int q = 0; q < D; ++q) {
+                            double v = 0.0;
+#pragma unroll
+                            for (int r = 0; r < D; ++r) v = fma(Pw[i][r], ct.pw[0][r * D + q], v);
+                            nx[i][q] = v;
+                            mx = fmax(mx, fabs(v));
+                        }
+#pragma unroll
+                    for (int i = 0; i < D; ++i)
+#pragma unroll
+                        for (int q = 0; q < D; ++q) Pw[i][q] = nx[i][q];
+                    if (mx < 1e-100) done = true;
+                }
+            }
+            j0 -= 32;
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                double v = e[i];
+#pragma unroll
+                for (int q = 0; q < D; ++q) v = fma(ct.pw[0][i * D + q], acc[q], v);
+                S.incl[(rec0 + tile) * 2 + i] = v;
+                sin_sh[i] = acc[i];
+            }
+            st_flag(S.flags + rec0 + tile, f_incl);
+        }
+    }
+    // ---- inclusive scan of the zero-state pieces inside the warp:  v_l = sum_{l' <= l} P^(l-l') z_l'
+    double v[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) v[k] = z[k];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        double o[D], t[D];
+#pragma unroll
+        for (int q = 0; q < D; ++q) o[q] = __shfl_up_sync(0xffffffffu, v[q], 1 << k);
+        mv2<D>(ppow + (size_t)(1 << k) * 4, o, t);
+        if (lane >= (1 << k)) {
+#pragma unroll
+            for (int q = 0; q < D; ++q) v[q] += t[q];
+        }
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int q = 0; q < D; ++q) wtot[warp][q] = v[q];
+    }
+    __syncthreads();
+    double W[D];
+#pragma unroll
+    for (int q = 0; q < D; ++q) W[q] = 0.0;
+    for (int j = 0; j < warp; ++j) {
+        double t[D];
+        mv2<D>(ppow + (size_t)32 * 4, W, t);
+#pragma unroll
+        for (int q = 0; q < D; ++q) W[q] = t[q] + wtot[j][q];
+    }
+    double sin_[D], st[D], e2[D];
+#pragma unroll
+    for (int q = 0; q < D; ++q) sin_[q] = sin_sh[q];
+    mv2<D>(ppow + (size_t)threadIdx.x * 4, sin_, st);
+    mv2<D>(ppow + (size_t)lane * 4, W, e2);
+#pragma unroll
+    for (int q = 0; q < D; ++q) {
+        const double prev = __shfl_up_sync(0xffffffffu, v[q], 1);
+        st[q] += e2[q] + (lane ? prev : 0.0);
+    }
+#pragma unroll 8
+    for (int i = 0; i < kTilePer; ++i) {
+        double* slot = tile_sm + i * kTileLd + threadIdx.x;
+        *slot = df2t_step<D>(c, st, *slot);
+    }
+    __syncthreads();
+    double* ob = P.out + (long long)s * P.out_sig_stride;
+    const long long u0 = tile * kTile;
+    const long long n = P.L - 2 * (long long)P.e;
+    if (u0 + kTile <= P.L && (P.forward || (P.L - u0 - kTile - P.e >= 0 && P.L - 1 - u0 - P.e < n))) {
+        // interior tile: branch-free coalesced stores, 8 values per thread in flight
+#pragma unroll 4
+        for (int it = 0; it < kTilePer; ++it) {
+            const int idx = it * kTileThreads + threadIdx.x;
+            const double y = tile_sm[(idx & (kTilePer - 1)) * kTileLd + (idx >> 5)];
+            if (P.forward) ob[u0 + idx] = y;
+            else ob[P.L - 1 - (u0 + idx) - P.e] = y;
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < kTile; idx += kTileThreads) {
+            const long long u = u0 + idx;
+            if (u >= P.L) break;
+            const double y = tile_sm[(idx & (kTilePer - 1)) * kTileLd + (idx >> 5)];
+            if (P.forward) {
+                ob[u] = y;
+            } else {
+                const long long t = P.L - 1 - u - P.e;
+                if (t >= 0 && t < n) ob[t] = y;
+            }
+        }
+    }
+}
+
 // per-signal mean in two deterministic stages: kMeanParts CTAs per signal reduce contiguous slices (fixed tree order),
 // one more CTA per signal adds the partials in index order.
 constexpr int kMeanParts = 64;
@@ -504,6 +723,24 @@ static void prepare_tile_tables(const IirCoef& c, std::vector<double>& ppow, Iir
 }
 
 template <int D>
+static int run_sweep_fused(IirPass P, const IirCoef& c, const IirCoef& ct, const double* d_ppow, const IirLookback& S, cudaStream_t st) {
+    const long long n_tiles = (P.L + kTile - 1) / kTile;
+    P.n_chunks = n_tiles;
+    const size_t smem = (size_t)kTilePer * kTileLd * sizeof(double);
+    static bool attr_done[3] = {false, false, false};
+    if (!attr_done[D]) {
+        if (cudaFuncSetAttribute(iir_tile_fused_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return set_error(HS_ERR_CUDA, "filtfilt: cannot reserve %zu B shared memory", smem);
+        cudaFuncSetAttribute(iir_tile_fused_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        attr_done[D] = true;
+    }
+    const long long ctas = n_tiles * P.n_sig;
+    if (ctas > 0x7fffffffLL) return set_error(HS_ERR_UNSUPPORTED, "filtfilt: too many tiles");
+    iir_tile_fused_kernel<D><<<(unsigned)ctas, kTileThreads, smem, st>>>(P, c, ct, d_ppow, S);
+    return check_launch("iir_tile_fused_kernel");
+}
+
+template <int D>
 static int run_sweep_tiled(IirPass P, const IirCoef& c, const IirCoef& ct, const double* d_ppow, cudaStream_t st) {
     const long long n_tiles = (P.L + kTile - 1) / kTile;
     P.n_chunks = n_tiles;
@@ -653,6 +890,12 @@ struct PreparedFilter {
 static std::mutex g_prep_mutex;
 static std::deque<PreparedFilter> g_prep_cache;
 
+static size_t lookback_bytes(int n_sig, long long tiles) {
+    const size_t recs = (size_t)n_sig * (size_t)tiles;
+    return recs * 4 * sizeof(double) + ((recs + 63) / 64) * 64 * sizeof(int) + 64 * sizeof(unsigned) + 256;
+}
+
+
 extern "C" {
 
 size_t hs_filtfilt_ws_bytes(int n_sig, int64_t n) {
@@ -664,6 +907,7 @@ size_t hs_filtfilt_ws_bytes(int n_sig, int64_t n) {
     b += ((size_t)n_sig * n_chunks * kMaxOrder * sizeof(double) + 255) / 256 * 256;     // chunk states
     b += (((size_t)n_sig + 31) / 32 * 32 + (size_t)n_sig * kMeanParts) * sizeof(double) / 256 * 256 + 256;   // means + partial sums
     b += (size_t)kMaxTiledFilters * kPpowEntries * 4 * sizeof(double);                  // power tables of the tiled path
+    b += lookback_bytes(n_sig, (L + kTile - 1) / kTile);                                // look-back records of the single-pass sweep
     return b + 256;
 }
 
@@ -691,6 +935,18 @@ static int iir_run(double* d_x, int n_sig, int64_t n, int64_t sig_stride, int64_
     double* ppow_dev = reinterpret_cast<double*>(ws);
     static int tiled_mode = -1;      // HS_IIR_TILED=0 forces the thread-per-chunk kernels
     if (tiled_mode < 0) tiled_mode = exp_env_int("HS_IIR_TILED", 1) ? 1 : 0;
+    static int fused_mode = -1;      // HS_IIR_FUSED=0: round 1's three-kernel tiled sweep (two reads of the signal per sweep)
+    if (fused_mode < 0) fused_mode = exp_env_int("HS_IIR_FUSED", 1) ? 1 : 0;
+    // look-back records of the single-pass sweep: behind the power tables
+    const long long tiles_max = (Lmax + kTile - 1) / kTile;
+    double* lb_base = ppow_dev + (size_t)kMaxTiledFilters * kPpowEntries * 4;
+    IirLookback LB;
+    LB.agg = lb_base;
+    LB.incl = lb_base + (size_t)n_sig * tiles_max * 2;
+    LB.flags = reinterpret_cast<int*>(lb_base + (size_t)n_sig * tiles_max * 4);
+    LB.ticket = reinterpret_cast<unsigned*>(LB.flags + (((size_t)n_sig * tiles_max + 63) / 64) * 64);
+    LB.sweep = 0;
+    bool lb_cleared = false;
     std::vector<double> ppow_host;
 
     if (remove_dc) {
@@ -783,7 +1039,21 @@ static int iir_run(double* d_x, int n_sig, int64_t n, int64_t sig_stride, int64_
         const bool tiled = use_tiled[k];
         const IirCoef& ct = coefs_tile[k];
         double* d_ppow = ppow_dev + (size_t)k * kPpowEntries * 4;
-        rc = tiled ? (c.d == 1 ? run_sweep_tiled<1>(P, c, ct, d_ppow, st) : run_sweep_tiled<2>(P, c, ct, d_ppow, st)) : run_sweep_d(c.d, P, c, st);
+        auto sweep = [&](const IirPass& Pp) -> int {
+            if (!tiled) return run_sweep_d(c.d, Pp, c, st);
+            if (!fused_mode) return c.d == 1 ? run_sweep_tiled<1>(Pp, c, ct, d_ppow, st) : run_sweep_tiled<2>(Pp, c, ct, d_ppow, st);
+            if (!lb_cleared) {      // flags and the per-sweep ticket counters: cleared once per call (records carry the sweep number)
+                const size_t bytes = (((size_t)n_sig * tiles_max + 63) / 64) * 64 * sizeof(int) + 64 * sizeof(unsigned);
+                if (cudaMemsetAsync(LB.flags, 0, bytes, st) != cudaSuccess) return set_error(HS_ERR_CUDA, "filtfilt: memset failed");
+                lb_cleared = true;
+            }
+            IirLookback S = LB;
+            S.ticket = LB.ticket + LB.sweep;
+            const int r = c.d == 1 ? run_sweep_fused<1>(Pp, c, ct, d_ppow, S, st) : run_sweep_fused<2>(Pp, c, ct, d_ppow, S, st);
+            ++LB.sweep;
+            return r;
+        };
+        rc = sweep(P);
         if (rc) return rc;
         if (causal) continue;
         // backward: f reversed -> x (middle n samples), in place
@@ -796,7 +1066,7 @@ static int iir_run(double* d_x, int n_sig, int64_t n, int64_t sig_stride, int64_
         P.out_t_stride = t_stride;
         P.forward = 0;
         P.mean = nullptr;
-        rc = tiled ? (c.d == 1 ? run_sweep_tiled<1>(P, c, ct, d_ppow, st) : run_sweep_tiled<2>(P, c, ct, d_ppow, st)) : run_sweep_d(c.d, P, c, st);
+        rc = sweep(P);
         if (rc) return rc;
     }
     return HS_OK;

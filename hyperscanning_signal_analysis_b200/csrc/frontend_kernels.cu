@@ -224,17 +224,14 @@ __device__ __forceinline__ void tile_stage_and_local(const IirPass& P, const Iir
     const bool interior = P.in_t_stride == 1 && (P.forward ? (u0 >= P.e && u0 + kTile <= P.e + P.n_in) : (u0 + kTile <= P.L));
     const double* src = P.forward ? base + (u0 - P.e) : base + (P.L - u0 - kTile);      // forward: x[u - e]; backward: f[L-1-u], walked downwards
     if (interior) {
-#pragma unroll 1
-        for (int it = 0; it < kTilePer; it += 16) {
-            double v[16];
+        double v[kTilePer];            // the whole tile's loads in flight: 32 per thread
 #pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = src[(it + k) * kTileThreads + threadIdx.x];
+        for (int k = 0; k < kTilePer; ++k) v[k] = __ldcs(src + k * kTileThreads + threadIdx.x);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int j = (it + k) * kTileThreads + threadIdx.x;               // offset inside the staged span
-                const int i0 = P.forward ? j : kTile - 1 - j;
-                sm[(i0 & (kTilePer - 1)) * kTileLd + (i0 >> 5)] = v[k] - dc;
-            }
+        for (int k = 0; k < kTilePer; ++k) {
+            const int j = k * kTileThreads + threadIdx.x;               // offset inside the staged span
+            const int i0 = P.forward ? j : kTile - 1 - j;
+            sm[(i0 & (kTilePer - 1)) * kTileLd + (i0 >> 5)] = v[k] - dc;
         }
     } else {
         for (int idx = threadIdx.x; idx < kTile; idx += kTileThreads) {
@@ -371,7 +368,7 @@ __device__ __forceinline__ int ld_flag(const int* p) {
 __device__ __forceinline__ void st_flag(int* p, const int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 template <int D>
-__global__ void __launch_bounds__(kTileThreads) iir_tile_fused_kernel(const IirPass P, const IirCoef c, const IirCoef ct, const double* __restrict__ ppow,
+__global__ void __launch_bounds__(kTileThreads, 3) iir_tile_fused_kernel(const IirPass P, const IirCoef c, const IirCoef ct, const double* __restrict__ ppow,
                                                                        const IirLookback S) {
     extern __shared__ double tile_sm[];
     __shared__ double red[kTileThreads / 32][2];
@@ -379,11 +376,19 @@ __global__ void __launch_bounds__(kTileThreads) iir_tile_fused_kernel(const IirP
     __shared__ double e_sh[2], sin_sh[2];
     __shared__ unsigned tk_sh;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) tk_sh = atomicAdd(S.ticket, 1u);
-    __syncthreads();
+    // Tile id = linear CTA index: CTAs are dispatched in index order, so every predecessor of a running CTA is running or done
+    // (the assumption cub::DeviceScan's decoupled look-back makes); HS_EXPERIMENT builds can switch to an atomic ticket.
+    unsigned tk = blockIdx.x;
+#ifdef HS_EXPERIMENT
+    if (S.ticket) {
+        if (threadIdx.x == 0) tk_sh = atomicAdd(S.ticket, 1u);
+        __syncthreads();
+        tk = tk_sh;
+    }
+#endif
     const long long n_tiles = P.n_chunks;
-    const int s = (int)(tk_sh / n_tiles);
-    const long long tile = tk_sh - (long long)s * n_tiles;
+    const int s = (int)(tk / n_tiles);
+    const long long tile = tk - (long long)s * n_tiles;
     double z[D];
     tile_stage_and_local<D>(P, c, tile_sm, s, tile, z);
     // ---- aggregate of the tile: e = sum_t P^(255-t) z_t (fixed-order block reduction)
@@ -427,19 +432,20 @@ __global__ void __launch_bounds__(kTileThreads) iir_tile_fused_kernel(const IirP
         }
         bool done = false;
         long long j0 = tile - 1;
+        int width = 4;                 // records polled per round: the nearest 4 first (stable filters need 1-2), then 32 at a time
         while (!done) {
             const long long j = j0 - lane;
             int f = 0;
             double a[D];
 #pragma unroll
             for (int q = 0; q < D; ++q) a[q] = 0.0;
-            if (j >= 0) {
+            if (j >= 0 && lane < width) {
                 do { f = ld_flag(S.flags + rec0 + j); } while (f < f_agg);
                 const double* src = (f == f_incl) ? S.incl : S.agg;
 #pragma unroll
                 for (int q = 0; q < D; ++q) a[q] = __ldcg(src + (rec0 + j) * 2 + q);
             }
-            for (int l = 0; l < 32 && !done; ++l) {
+            for (int l = 0; l < width && !done; ++l) {
                 const int fl = __shfl_sync(0xffffffffu, f, l);
                 double al[D];
 #pragma unroll
@@ -478,7 +484,8 @@ __global__ void __launch_bounds__(kTileThreads) iir_tile_fused_kernel(const IirP
                     if (mx < 1e-100) done = true;
                 }
             }
-            j0 -= 32;
+            j0 -= width;
+            width = 32;
         }
         if (lane == 0) {
 #pragma unroll
@@ -1048,7 +1055,7 @@ static int iir_run(double* d_x, int n_sig, int64_t n, int64_t sig_stride, int64_
                 lb_cleared = true;
             }
             IirLookback S = LB;
-            S.ticket = LB.ticket + LB.sweep;
+            S.ticket = exp_env_int("HS_IIR_TICKET", 0) ? LB.ticket + LB.sweep : nullptr;
             const int r = c.d == 1 ? run_sweep_fused<1>(Pp, c, ct, d_ppow, S, st) : run_sweep_fused<2>(Pp, c, ct, d_ppow, S, st);
             ++LB.sweep;
             return r;

@@ -575,9 +575,35 @@ __device__ __forceinline__ void dmma884_k3(double& c0, double& c1, const double 
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// ---- bulk asynchronous copies (TMA unit, cp.async.bulk + mbarrier): one elected warp issues a copy per channel row, the
+//      barrier's transaction count tells every thread when the bytes have landed; no registers and no LSU instructions are
+//      spent on the staging.  16-byte aligned source rows only (window starts on an even sample), else plain loads.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, const int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, const unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, const unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_%=;\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, const unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 template <int KC>      // column tiles per warp: 3 (up to 48 column tiles with 16 warps), 6 (up to 96)
 __global__ void __launch_bounds__(512, 1) lagcov_mma_kernel(const K3Params P, const int ld) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long stage_bar;
     double* xs = reinterpret_cast<double*>(smem_raw);                 // [40][ld], channel-major, zero padded
     const int m = P.m, n = P.n, p = P.p;
     const int w = blockIdx.x;
@@ -607,9 +633,24 @@ __global__ void __launch_bounds__(512, 1) lagcov_mma_kernel(const K3Params P, co
 #pragma unroll
         for (int u = 0; u < KC; ++u) acc[ta][u][0] = acc[ta][u][1] = 0.0;
 
+    if (threadIdx.x == 0) mbar_init(&stage_bar, 1);
+    unsigned stage_phase = 0;
+    const bool rows_aligned = ((n & 1) == 0) && ((P.ch_stride & 1) == 0) && ((reinterpret_cast<uintptr_t>(P.x) & 15) == 0);
     for (int tr = 0; tr < P.trials; ++tr) {
-        const double* xu = P.x + P.offsets[(size_t)w * P.trials + tr];
-        __syncthreads();                                               // previous trial's products are done with xs
+        const long long off = P.offsets[(size_t)w * P.trials + tr];
+        const double* xu = P.x + off;
+        __syncthreads();                                               // previous trial's products are done with xs (and the barrier is initialised)
+        if (rows_aligned && (off & 1) == 0) {
+            // TMA path: warp 0 issues one bulk copy per channel row (n * 8 bytes each), all threads wait on the transaction barrier
+            if (warp == 0) {
+                fence_proxy_async();                                   // the generic-proxy reads of the previous trial precede these async writes
+                if (lane == 0) mbar_expect_tx(&stage_bar, (unsigned)(m * n * sizeof(double)));
+                __syncwarp();
+                for (int r = lane; r < m; r += 32) bulk_g2s(xs + (size_t)r * ld, xu + (size_t)r * P.ch_stride, (unsigned)(n * sizeof(double)), &stage_bar);
+            }
+            mbar_wait(&stage_bar, stage_phase);
+            stage_phase ^= 1;
+        } else
         for (int r = warp; r < m; r += nwarps) {                       // one warp per channel row: coalesced
             const double* src = xu + (size_t)r * P.ch_stride;
             double* dst = xs + (size_t)r * ld;
@@ -664,6 +705,149 @@ __global__ void __launch_bounds__(512, 1) lagcov_mma_kernel(const K3Params P, co
     }
 }
 
+
+// -------------------------------------------------------------------------------------
+// K3 for many channels / many epochs (cfg5: 2 x 64 ch, 100 epochs per window, p = 15: the dense lag-covariance contraction,
+// 26.5 GFLOP per window): a tiled FP64 tensor-core GEMM.
+//   R(L)[i][j] = scale * sum_trials sum_t x_i(t) x_j(t + L):  per (window, lag, 128 x 128 block of (i, j)) one CTA; K dimension =
+//   epochs x samples, walked in chunks of 64 samples.  A chunk (128 channel rows x 80 samples: 64 + a 16-sample halo for the lag)
+//   is brought in by ONE bulk copy per row (cp.async.bulk, transaction barrier) into one of two buffers while the 16 warps
+//   (4 x 4 grid, 32 x 32 outputs = 16 accumulator tiles each) multiply the other: A = X[i][t], B = X[j][t + L] are fragments of the
+//   same staged rows (row stride = 4 mod 16 doubles: conflict free).  Samples beyond the epoch's end are zero, which implements the
+//   shrinking sum range of count_corr (mtmvar.py:57-59) without branches.
+// -------------------------------------------------------------------------------------
+constexpr int kG3Block = 128;               // output block edge
+constexpr int kG3Chunk = 64;                // samples per K chunk
+constexpr int kG3Halo = 16;                 // halo (>= max lag, multiple of 2)
+constexpr int kG3Ld = kG3Chunk + kG3Halo + 4;      // 84 = 4 (mod 16)
+constexpr int kG3MaxLag = kG3Halo;
+
+__global__ void __launch_bounds__(512, 1) lagcov_gemm_kernel(const K3Params P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long full_bar[2];
+    double* buf[2] = {reinterpret_cast<double*>(smem_raw), reinterpret_cast<double*>(smem_raw) + (size_t)2 * kG3Block * kG3Ld};
+    // buf[b]: rows 0..127 = the i block, rows 128..255 = the j block (the same rows when the block is on the diagonal)
+    const int m = P.m, n = P.n, p = P.p;
+    const int nbk = (m + kG3Block - 1) / kG3Block;
+    const int w = blockIdx.x / (p + 1), L = blockIdx.x % (p + 1);
+    const int bi = blockIdx.y / nbk, bj = blockIdx.y % nbk;
+    const bool diag = (bi == bj);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g4 = lane >> 2, t4 = lane & 3;
+    const int wr = warp >> 2, wc = warp & 3;                       // 32 x 32 sub-block of the warp
+    const int rows_i = min(kG3Block, m - bi * kG3Block), rows_j = min(kG3Block, m - bj * kG3Block);
+    const int chunks_per_trial = (n + kG3Chunk - 1) / kG3Chunk;
+    const int n_chunks = chunks_per_trial * P.trials;
+    // rows beyond m and the 4 pad columns stay zero for the whole kernel
+    for (int e = threadIdx.x; e < 2 * 2 * kG3Block * kG3Ld; e += blockDim.x) reinterpret_cast<double*>(smem_raw)[e] = 0.0;
+    if (threadIdx.x == 0) {
+        mbar_init(&full_bar[0], 1);
+        mbar_init(&full_bar[1], 1);
+    }
+    __syncthreads();
+    auto issue = [&](const int c) {          // warp 0: bulk copies of chunk c into buffer c & 1
+        const int tr = c / chunks_per_trial, t0 = (c - tr * chunks_per_trial) * kG3Chunk;
+        const int valid = min(kG3Chunk + kG3Halo, n - t0);       // samples of this chunk that exist (even: n and t0 are even)
+        const double* xu = P.x + P.offsets[(size_t)w * P.trials + tr] + t0;
+        double* dst = buf[c & 1];
+        const int n_rows = rows_i + (diag ? 0 : rows_j);
+        fence_proxy_async();
+        if (lane == 0) mbar_expect_tx(&full_bar[c & 1], (unsigned)((size_t)n_rows * valid * sizeof(double)));
+        __syncwarp();
+        for (int r = lane; r < rows_i; r += 32)
+            bulk_g2s(dst + (size_t)r * kG3Ld, xu + (size_t)(bi * kG3Block + r) * P.ch_stride, (unsigned)(valid * sizeof(double)), &full_bar[c & 1]);
+        if (!diag)
+            for (int r = lane; r < rows_j; r += 32)
+                bulk_g2s(dst + (size_t)(kG3Block + r) * kG3Ld, xu + (size_t)(bj * kG3Block + r) * P.ch_stride, (unsigned)(valid * sizeof(double)),
+                         &full_bar[c & 1]);
+    };
+    // 16-byte aligned rows for every epoch of this window?  (uniform per CTA)
+    bool aligned = true;
+    for (int tr = 0; tr < P.trials; ++tr) aligned = aligned && ((P.offsets[(size_t)w * P.trials + tr] & 1) == 0);
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    auto multiply = [&](const double* xb) {
+        const double* pa = xb + (size_t)(32 * wr + g4) * kG3Ld + t4;
+        const double* pb = xb + (size_t)((diag ? 0 : kG3Block) + 32 * wc + g4) * kG3Ld + t4 + L;
+#pragma unroll 4
+        for (int t = 0; t < kG3Chunk; t += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                a[q] = pa[(size_t)q * 8 * kG3Ld + t];
+                b[q] = pb[(size_t)q * 8 * kG3Ld + t];
+            }
+#pragma unroll
+            for (int qa = 0; qa < 4; ++qa)
+#pragma unroll
+                for (int qb = 0; qb < 4; ++qb) dmma884_k3(acc[qa][qb][0], acc[qa][qb][1], a[qa], b[qb]);
+        }
+    };
+    if (aligned) {
+        if (warp == 0) {
+            issue(0);
+            if (n_chunks > 1) issue(1);
+        }
+        for (int c = 0; c < n_chunks; ++c) {
+            mbar_wait(&full_bar[c & 1], (unsigned)((c >> 1) & 1));
+            const int t0 = (c % chunks_per_trial) * kG3Chunk;
+            const int valid = min(kG3Chunk + kG3Halo, n - t0);
+            double* xb = buf[c & 1];
+            if (valid < kG3Chunk + kG3Halo) {
+                // last chunk of an epoch: the columns behind the end still hold the previous contents of this buffer -> zero them
+                __syncthreads();
+                const int nz = kG3Chunk + kG3Halo - valid;
+                for (int e = threadIdx.x; e < 2 * kG3Block * nz; e += blockDim.x) xb[(size_t)(e / nz) * kG3Ld + valid + e % nz] = 0.0;
+                __syncthreads();
+            }
+            multiply(xb);
+            __syncthreads();                                           // everyone is done with this buffer
+            if (warp == 0 && c + 2 < n_chunks) issue(c + 2);
+        }
+    } else {
+        // odd epoch offset: rows are only 8-byte aligned -> plain loads, one buffer, no overlap
+        double* xb = buf[0];
+        for (int c = 0; c < n_chunks; ++c) {
+            const int tr = c / chunks_per_trial, t0 = (c - tr * chunks_per_trial) * kG3Chunk;
+            const int valid = min(kG3Chunk + kG3Halo, n - t0);
+            const double* xu = P.x + P.offsets[(size_t)w * P.trials + tr] + t0;
+            __syncthreads();
+            for (int e = threadIdx.x; e < 2 * kG3Block * (kG3Chunk + kG3Halo); e += blockDim.x) {
+                const int r = e / (kG3Chunk + kG3Halo), col = e - r * (kG3Chunk + kG3Halo);
+                const bool second = r >= kG3Block;
+                if (second && diag) continue;
+                const int rr = second ? r - kG3Block : r;
+                const int ch = (second ? bj : bi) * kG3Block + rr;
+                xb[(size_t)r * kG3Ld + col] = (ch < m && col < valid) ? xu[(size_t)ch * P.ch_stride + col] : 0.0;
+            }
+            __syncthreads();
+            multiply(xb);
+        }
+    }
+    const double scale = 1.0 / ((double)n * (double)P.trials);
+    double* Rl = P.R + ((size_t)w * (p + 1) + L) * m * m;
+#pragma unroll
+    for (int qa = 0; qa < 4; ++qa) {
+        const int i = bi * kG3Block + 32 * wr + 8 * qa + g4;
+#pragma unroll
+        for (int qb = 0; qb < 4; ++qb) {
+            const int j = bj * kG3Block + 32 * wc + 8 * qb + 2 * t4;
+            if (i < m) {
+                if (j < m) Rl[(size_t)i * m + j] = acc[qa][qb][0] * scale;
+                if (j + 1 < m) Rl[(size_t)i * m + j + 1] = acc[qa][qb][1] * scale;
+            }
+        }
+    }
+}
+
+static bool lagcov_gemm_ok(const K3Params& P) {
+    // bulk copies need 16-byte aligned rows: even sample counts / strides here, even epoch offsets checked per window on the device
+    // (a window with an odd offset is staged with plain loads instead)
+    return P.m > kPadMax && P.p <= kG3MaxLag && (P.n & 1) == 0 && (P.ch_stride & 1) == 0 && (reinterpret_cast<uintptr_t>(P.x) & 15) == 0;
+}
+
 static int lagcov_mma_ld(int n, int p) {
     int ld = n + p + 4;                        // fragments read up to column (n - 4) + 3 + p
     ld += (4 - ld % 16 + 16) % 16;             // = 4 (mod 16) doubles: the 32 lanes of a fragment load hit 32 distinct banks
@@ -672,6 +856,15 @@ static int lagcov_mma_ld(int n, int p) {
 
 int launch_lagcov(const K3Params& P, cudaStream_t stream) {
     static const bool legacy = exp_env_int("HS_K3_LEGACY", 0) == 1;
+    if (!legacy && lagcov_gemm_ok(P)) {
+        const size_t smem = (size_t)2 * 2 * kG3Block * kG3Ld * sizeof(double);
+        cudaError_t e = cudaFuncSetAttribute(lagcov_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "lagcov: %s", cudaGetErrorString(e));
+        const int nbk = (P.m + kG3Block - 1) / kG3Block;
+        dim3 grid(P.n_win * (P.p + 1), nbk * nbk);
+        lagcov_gemm_kernel<<<grid, 512, smem, stream>>>(P);
+        return check_launch("lagcov_gemm_kernel");
+    }
     if (!legacy && P.m <= kPadMax) {
         const int ld = lagcov_mma_ld(P.n, P.p);
         const size_t smem_mma = (size_t)kPadMax * ld * sizeof(double);

@@ -717,16 +717,18 @@ __global__ void __launch_bounds__(512, 1) lagcov_mma_kernel(const K3Params P, co
 //   shrinking sum range of count_corr (mtmvar.py:57-59) without branches.
 // -------------------------------------------------------------------------------------
 constexpr int kG3Block = 128;               // output block edge
-constexpr int kG3Chunk = 64;                // samples per K chunk
 constexpr int kG3Halo = 16;                 // halo (>= max lag, multiple of 2)
-constexpr int kG3Ld = kG3Chunk + kG3Halo + 4;      // 84 = 4 (mod 16)
 constexpr int kG3MaxLag = kG3Halo;
 
+// CH = samples per K chunk, ROWS = staged rows per buffer: (64, 128) when the channel count fits one block (only diagonal blocks:
+// the i and j operands are the same rows), (32, 256) otherwise; row stride CH + 20 = 4 (mod 16) doubles in both cases.
+template <int kG3Chunk, int kG3Rows>
 __global__ void __launch_bounds__(512, 1) lagcov_gemm_kernel(const K3Params P) {
+    constexpr int kG3Ld = kG3Chunk + kG3Halo + 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long full_bar[2];
-    double* buf[2] = {reinterpret_cast<double*>(smem_raw), reinterpret_cast<double*>(smem_raw) + (size_t)2 * kG3Block * kG3Ld};
-    // buf[b]: rows 0..127 = the i block, rows 128..255 = the j block (the same rows when the block is on the diagonal)
+    double* buf[2] = {reinterpret_cast<double*>(smem_raw), reinterpret_cast<double*>(smem_raw) + (size_t)kG3Rows * kG3Ld};
+    // buf[b]: rows 0..127 = the i block, rows 128..255 = the j block (kG3Rows == 128: diagonal blocks only, one set of rows)
     const int m = P.m, n = P.n, p = P.p;
     const int nbk = (m + kG3Block - 1) / kG3Block;
     const int w = blockIdx.x / (p + 1), L = blockIdx.x % (p + 1);
@@ -738,7 +740,7 @@ __global__ void __launch_bounds__(512, 1) lagcov_gemm_kernel(const K3Params P) {
     const int chunks_per_trial = (n + kG3Chunk - 1) / kG3Chunk;
     const int n_chunks = chunks_per_trial * P.trials;
     // rows beyond m and the 4 pad columns stay zero for the whole kernel
-    for (int e = threadIdx.x; e < 2 * 2 * kG3Block * kG3Ld; e += blockDim.x) reinterpret_cast<double*>(smem_raw)[e] = 0.0;
+    for (int e = threadIdx.x; e < 2 * kG3Rows * kG3Ld; e += blockDim.x) reinterpret_cast<double*>(smem_raw)[e] = 0.0;
     if (threadIdx.x == 0) {
         mbar_init(&full_bar[0], 1);
         mbar_init(&full_bar[1], 1);
@@ -799,7 +801,7 @@ __global__ void __launch_bounds__(512, 1) lagcov_gemm_kernel(const K3Params P) {
                 // last chunk of an epoch: the columns behind the end still hold the previous contents of this buffer -> zero them
                 __syncthreads();
                 const int nz = kG3Chunk + kG3Halo - valid;
-                for (int e = threadIdx.x; e < 2 * kG3Block * nz; e += blockDim.x) xb[(size_t)(e / nz) * kG3Ld + valid + e % nz] = 0.0;
+                for (int e = threadIdx.x; e < kG3Rows * nz; e += blockDim.x) xb[(size_t)(e / nz) * kG3Ld + valid + e % nz] = 0.0;
                 __syncthreads();
             }
             multiply(xb);
@@ -814,7 +816,7 @@ __global__ void __launch_bounds__(512, 1) lagcov_gemm_kernel(const K3Params P) {
             const int valid = min(kG3Chunk + kG3Halo, n - t0);
             const double* xu = P.x + P.offsets[(size_t)w * P.trials + tr] + t0;
             __syncthreads();
-            for (int e = threadIdx.x; e < 2 * kG3Block * (kG3Chunk + kG3Halo); e += blockDim.x) {
+            for (int e = threadIdx.x; e < kG3Rows * (kG3Chunk + kG3Halo); e += blockDim.x) {
                 const int r = e / (kG3Chunk + kG3Halo), col = e - r * (kG3Chunk + kG3Halo);
                 const bool second = r >= kG3Block;
                 if (second && diag) continue;
@@ -857,12 +859,14 @@ static int lagcov_mma_ld(int n, int p) {
 int launch_lagcov(const K3Params& P, cudaStream_t stream) {
     static const bool legacy = exp_env_int("HS_K3_LEGACY", 0) == 1;
     if (!legacy && lagcov_gemm_ok(P)) {
-        const size_t smem = (size_t)2 * 2 * kG3Block * kG3Ld * sizeof(double);
-        cudaError_t e = cudaFuncSetAttribute(lagcov_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "lagcov: %s", cudaGetErrorString(e));
         const int nbk = (P.m + kG3Block - 1) / kG3Block;
+        const bool one = nbk == 1;
+        const size_t smem = one ? (size_t)2 * 128 * (64 + kG3Halo + 4) * sizeof(double) : (size_t)2 * 256 * (32 + kG3Halo + 4) * sizeof(double);
+        auto kern = one ? lagcov_gemm_kernel<64, 128> : lagcov_gemm_kernel<32, 256>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "lagcov: %s", cudaGetErrorString(e));
         dim3 grid(P.n_win * (P.p + 1), nbk * nbk);
-        lagcov_gemm_kernel<<<grid, 512, smem, stream>>>(P);
+        kern<<<grid, 512, smem, stream>>>(P);
         return check_launch("lagcov_gemm_kernel");
     }
     if (!legacy && P.m <= kPadMax) {

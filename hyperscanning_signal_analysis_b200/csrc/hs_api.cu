@@ -60,6 +60,8 @@ static std::mutex g_timing_mu;
 static cudaEvent_t g_ev[2] = {nullptr, nullptr};
 static bool g_ev_valid = false;
 
+static std::atomic<int> g_k5_kernel{0};      // hs_transfer_set_kernel: 0 automatic, 1 transfer_mma_kernel (6 groups), 2 transfer_ws_kernel
+
 static int k5_groups() {
     static int ng = 0;
     if (ng == 0) {
@@ -112,6 +114,16 @@ extern "C" {
 const char* hs_last_error(void) { return g_err; }
 int hs_version(void) { return 100; }
 long long hs_launch_count(void) { return g_launches.load(); }
+
+int hs_transfer_set_kernel(int which) {
+    if (which < 0 || which > 3)
+        return set_error(HS_ERR_INVALID, "hs_transfer_set_kernel: 0 (automatic), 1 (transfer_mma_kernel), 2 / 3 (transfer_ws_kernel with 4 / 6 groups)");
+#ifndef HS_EXPERIMENT
+    if (which >= 2) return set_error(HS_ERR_UNSUPPORTED, "hs_transfer_set_kernel: the warp-specialised kernel is compiled into HS_EXPERIMENT builds only");
+#endif
+    g_k5_kernel.store(which);
+    return HS_OK;
+}
 
 void hs_timing_enable(int on) { g_timing.store(on ? 1 : 0); }
 
@@ -308,13 +320,16 @@ int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double 
                 return set_error(HS_ERR_CUDA, "hs_transfer_dtf_f64: cannot create timing events");
             cudaEventRecord(g_ev[0], st);
         }
-        if (use_mma && transfer_mma_fits(p, ng, sl)) {
+        const int which = g_k5_kernel.load();          // 2: warp-specialised, 4 groups; 3: warp-specialised, 6 groups
+        const int ws_ng = which == 3 ? 6 : 4;
+        const bool ws = (which == 2 || which == 3) && transfer_mma_fits(p, ws_ng, sl);
+        if (use_mma && (ws || transfer_mma_fits(p, ng, sl))) {
             // balanced partition: a window may be covered by fewer CTAs than it has row-sum slots -> the slots start at zero
-            transfer_mma_partition(n_win, F, &P.per_cta, &P.n_seg, ng);
+            transfer_mma_partition(n_win, F, &P.per_cta, &P.n_seg, ws ? ws_ng : ng);
             ns = P.n_seg;
             if (P.rowpart && cudaMemsetAsync(P.rowpart, 0, (size_t)n_win * ns * m * sizeof(double), st) != cudaSuccess)
                 return set_error(HS_ERR_CUDA, "hs_transfer_dtf_f64: memset failed");
-            rc = launch_transfer_mma(P, ng, st);
+            rc = ws ? launch_transfer_ws(P, ws_ng, st) : launch_transfer_mma(P, ng, st);
         } else {
             rc = launch_transfer_dtf(P, ng, 1, st);
         }

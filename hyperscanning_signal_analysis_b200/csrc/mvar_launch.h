@@ -55,7 +55,8 @@ int launch_ztable(const double* freqs, int F, int p, double fs, void* z, cudaStr
 int launch_transfer_dtf(const K5Params& P, int ng, int mode, cudaStream_t stream);
 bool transfer_mma_fits(int p, int ng, int seg_len);
 void transfer_mma_partition(int n_win, int F, int* per_cta, int* slots, int ng);      // balanced split of the n_win * F matrices over the SMs       // shared memory for the coefficient planes of order p fits next to ng groups
-int launch_transfer_mma(const K5Params& P, int ng, cudaStream_t stream);      // optimistic pass on the FP64 tensor pipe (transfer_mma.cu)
+int launch_transfer_mma(const K5Params& P, int ng, cudaStream_t stream);
+int launch_transfer_ws(const K5Params& P, int ng, cudaStream_t stream);               // warp-specialised variant: 4 groups x (Re, Im, helper) warps      // optimistic pass on the FP64 tensor pipe (transfer_mma.cu)
 int launch_dtf_finalize(const double* stage, const double* rowpart, const int* bad, int n_win, int m, int F, int n_seg,
                         double* dtf_out, double* ffdtf_out, cudaStream_t stream);
 int launch_ffdtf_normalize(double* dtf, const double* rowpart, const double* rowpart2, int n_win, int m, int F, int n_seg, double* out,

@@ -73,6 +73,10 @@ struct __align__(16) MmaGroupSmem {
     double rs[2][kMP];                     // ffDTF row sums of this unit, per warp
     int flag;
     int pad_[3];
+    // warp-specialised kernel only (transfer_ws_kernel): the helper warp's mailbox
+    double2 Ph[16];                        // D^-1 of the current block step, written by the helper warp
+    double Dblk[2][16];                    // [part][i*4 + j]  the NEXT pivot block, published early by the two main warps
+    unsigned long long bar_d, bar_p;       // mbarriers: "pivot block published" (2 arrivals), "inverse ready" (1 arrival)
 };
 
 struct MmaCtx {
@@ -401,6 +405,167 @@ __device__ __forceinline__ double2 probe_u2(const int j) {
     return make_double2(1.0 + 0.03125 * j, ((j & 1) ? -1.0 : 1.0) * (0.5 + 0.015625 * j));
 }
 
+
+#ifdef HS_EXPERIMENT
+// =====================================================================================
+// Warp-specialised variant (transfer_ws_kernel).  In transfer_mma_kernel every dependent scalar FP64 instruction of the 4 x 4
+// pivot-block inverse queues behind the other warps' 16-cycle DMMAs, and the two warps of a group cannot issue a DMMA until
+// the chain (64 instructions, both warps redundantly) is through: 24 % of the kernel.  Here a group is THREE warps: the Re and
+// Im warps only stream DMMAs; right after the L panel they update the diagonal tile that holds the NEXT pivot block, publish
+// those 16 entries (bar_d) and go on with the other 48 update DMMAs, while the group's HELPER warp inverts the block (cofactors,
+// one reciprocal) and hands P back (bar_p) before the main warps need it.  Register budgets follow the roles (setmaxnreg: the
+// helper warpgroup gives registers to the main warpgroups), so the main warps hold the 50 accumulators + fragments without spills.
+// =====================================================================================
+__device__ __forceinline__ unsigned ws_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ws_mbar_init(unsigned long long* bar, const int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ws_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ws_mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ws_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool ws_mbar_test(unsigned long long* bar, const unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(ws_smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void ws_mbar_wait(unsigned long long* bar, const unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WS_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WS_WAIT_%=;\n"
+        "}\n" ::"r"(ws_smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// helper warp: P = D^-1 by cofactors from the published block (same arithmetic as mma_inverse4_adj<true>)
+__device__ __forceinline__ void ws_inverse4(MmaGroupSmem* gs, const int lane) {
+    const int i = (lane >> 2) & 3, j = lane & 3;
+    const double* Dr = gs->Dblk[0];
+    const double* Di = gs->Dblk[1];
+    const int r0 = (0 >= j) ? 1 : 0, r1 = (1 >= j) ? 2 : 1, r2 = (2 >= j) ? 3 : 2;
+    const int c0 = (0 >= i) ? 1 : 0, c1 = (1 >= i) ? 2 : 1, c2 = (2 >= i) ? 3 : 2;
+#define HS_LD(R, C, vr, vi) const double vr = Dr[(R) * 4 + (C)], vi = Di[(R) * 4 + (C)]
+    HS_LD(r0, c0, a00r, a00i); HS_LD(r0, c1, a01r, a01i); HS_LD(r0, c2, a02r, a02i);
+    HS_LD(r1, c0, a10r, a10i); HS_LD(r1, c1, a11r, a11i); HS_LD(r1, c2, a12r, a12i);
+    HS_LD(r2, c0, a20r, a20i); HS_LD(r2, c1, a21r, a21i); HS_LD(r2, c2, a22r, a22i);
+    HS_LD(0, 0, d0r, d0i); HS_LD(0, 1, d1r, d1i); HS_LD(0, 2, d2r, d2i); HS_LD(0, 3, d3r, d3i);
+#undef HS_LD
+#define HS_DET2(pr, pi, qr, qi, sr, si, tr, ti, outr, outi)                                        \
+    const double outr = fma(pr, qr, -pi * qi) - fma(sr, tr, -si * ti);                              \
+    const double outi = fma(pr, qi, pi * qr) - fma(sr, ti, si * tr)
+    HS_DET2(a11r, a11i, a22r, a22i, a12r, a12i, a21r, a21i, m0r, m0i);
+    HS_DET2(a10r, a10i, a22r, a22i, a12r, a12i, a20r, a20i, m1r, m1i);
+    HS_DET2(a10r, a10i, a21r, a21i, a11r, a11i, a20r, a20i, m2r, m2i);
+#undef HS_DET2
+    double cr = fma(a00r, m0r, -a00i * m0i) - fma(a01r, m1r, -a01i * m1i) + fma(a02r, m2r, -a02i * m2i);
+    double ci = fma(a00r, m0i, a00i * m0r) - fma(a01r, m1i, a01i * m1r) + fma(a02r, m2i, a02i * m2r);
+    if ((i + j) & 1) { cr = -cr; ci = -ci; }
+    const double b0r = __shfl_sync(0xffffffffu, cr, 0, 16), b0i = __shfl_sync(0xffffffffu, ci, 0, 16);
+    const double b1r = __shfl_sync(0xffffffffu, cr, 4, 16), b1i = __shfl_sync(0xffffffffu, ci, 4, 16);
+    const double b2r = __shfl_sync(0xffffffffu, cr, 8, 16), b2i = __shfl_sync(0xffffffffu, ci, 8, 16);
+    const double b3r = __shfl_sync(0xffffffffu, cr, 12, 16), b3i = __shfl_sync(0xffffffffu, ci, 12, 16);
+    const double detr = (fma(d0r, b0r, -d0i * b0i) + fma(d1r, b1r, -d1i * b1i)) + (fma(d2r, b2r, -d2i * b2i) + fma(d3r, b3r, -d3i * b3i));
+    const double deti = (fma(d0r, b0i, d0i * b0r) + fma(d1r, b1i, d1i * b1r)) + (fma(d2r, b2i, d2i * b2r) + fma(d3r, b3i, d3i * b3r));
+    const double y = rcp_newton2(fma(detr, detr, deti * deti));
+    const double ivr = detr * y, ivi = -deti * y;
+    const double pr = fma(cr, ivr, -ci * ivi), pi = fma(cr, ivi, ci * ivr);
+    if (lane < 16) gs->Ph[lane] = make_double2(pr, pi);
+}
+
+// main warps: publish the 4 x 4 block (half hn of tile (tn, tn)) for the helper
+template <int T, int tn>
+__device__ __forceinline__ void ws_publish(const double (&c)[T][T][2], const int hn, const MmaCtx& x) {
+    if ((x.g4 >> 2) == hn && (x.t4 >> 1) == hn)
+        *reinterpret_cast<double2*>(&x.gs->Dblk[x.part][(x.g4 & 3) * 4 + 2 * (x.t4 & 1)]) = make_double2(c[tn][tn][0], c[tn][tn][1]);
+    __syncwarp();
+    if (x.lane == 0) ws_mbar_arrive(&x.gs->bar_d);
+}
+
+template <int T, int t>
+__device__ __forceinline__ void ws_tile_steps(double (&c)[T][T][2], const int m, const MmaCtx& x, unsigned& ph) {
+    MmaGroupSmem* gs = x.gs;
+    const int fo = x.g4 * 4 + x.t4;
+    const int sgn = x.part ? 0 : (int)0x80000000;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+        const int K0 = 8 * t + 4 * h;
+        if (K0 >= m) break;
+        mma_extract<T, t>(c, h, x);
+        mma_group_sync(x);
+        ws_mbar_wait(&gs->bar_p, ph & 1u);                 // P = D^-1 of this step, from the helper warp
+        ++ph;
+        double a0[T], a1[T];
+        {
+            const double2 pv = gs->Ph[x.t4 * 4 + (x.g4 >> 1)];
+            const bool odd = x.g4 & 1;
+            const double bB1 = odd ? -pv.y : -pv.x;
+            const double bB2 = odd ? -pv.x : pv.y;
+            const double* Cr = gs->u.p.Craw[h][0] + fo;
+            const double* Ci = gs->u.p.Craw[h][1] + fo;
+#pragma unroll
+            for (int ta = 0; ta < T; ++ta) {
+                double l0 = 0.0, l1 = 0.0;
+                dmma884(l0, l1, Cr[32 * ta], bB1);
+                dmma884(l0, l1, Ci[32 * ta], bB2);
+                a0[ta] = l0;
+                a1[ta] = l1;
+            }
+            const double2 pk = gs->Ph[(x.g4 & 3) * 4 + x.t4];
+            if ((x.g4 >> 2) == h) {
+                const bool dg = (x.g4 & 3) == x.t4;
+                a0[t] = pk.x - (dg ? 1.0 : 0.0);
+                a1[t] = pk.y;
+            }
+#pragma unroll
+            for (int ta = 0; ta < T; ++ta) a1[ta] = flip_sign(a1[ta], sgn);
+        }
+        const double* Ua = gs->u.p.Rraw[h][x.part] + x.t4 * kUS + x.g4;
+        const double* Ub = gs->u.p.Rraw[h][x.part ^ 1] + x.t4 * kUS + x.g4;
+        double b0[T], b1[T];
+#pragma unroll
+        for (int tb = 0; tb < T; ++tb) {
+            b0[tb] = Ua[8 * tb];
+            b1[tb] = Ub[8 * tb];
+        }
+        // the diagonal tile that holds the NEXT pivot block first, so the helper can start on its inverse
+        const bool has_next = (K0 + 4 < m);
+        if (h == 0) {
+            dmma884(c[t][t][0], c[t][t][1], a0[t], b0[t]);
+            dmma884(c[t][t][0], c[t][t][1], a1[t], b1[t]);
+            if (has_next) ws_publish<T, t>(c, 1, x);
+        } else if constexpr (t + 1 < T) {
+            dmma884(c[t + 1][t + 1][0], c[t + 1][t + 1][1], a0[t + 1], b0[t + 1]);
+            dmma884(c[t + 1][t + 1][0], c[t + 1][t + 1][1], a1[t + 1], b1[t + 1]);
+            if (has_next) ws_publish<T, t + 1>(c, 0, x);
+        }
+#pragma unroll
+        for (int ta = 0; ta < T; ++ta) {
+#pragma unroll
+            for (int tb = 0; tb < T; ++tb) {
+                if (ta == tb && ((h == 0 && ta == t) || (h == 1 && ta == t + 1))) continue;      // done above
+                dmma884(c[ta][tb][0], c[ta][tb][1], a0[ta], b0[tb]);
+                dmma884(c[ta][tb][0], c[ta][tb][1], a1[ta], b1[tb]);
+            }
+        }
+    }
+}
+
+template <int T, int t>
+__device__ __forceinline__ void ws_all_tiles(double (&c)[T][T][2], const int m, const MmaCtx& x, unsigned& ph) {
+    if constexpr (t < T) {
+        ws_tile_steps<T, t>(c, m, x, ph);
+        ws_all_tiles<T, t + 1>(c, m, x, ph);
+    }
+}
+
+#endif  // HS_EXPERIMENT (warp-specialised device functions)
+
 template <int T>
 struct MmaSmem {
     static __host__ __device__ int planes(int p) { return (p + 1) / 2; }
@@ -627,6 +792,278 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
     }
 }
 
+#ifdef HS_EXPERIMENT
+// Role layout: warps 0 .. 2 NG - 1 = main warps (whole warpgroups of 4), then ONE warpgroup of helpers.
+//   NG = 4: 4 helpers, one per group;            registers 256 x 200 + 128 x 96 = 63 488
+//   NG = 6: 3 helpers, each serving two groups;  registers 384 x 152 + 128 x 56 = 65 536   (the fourth warp of the helper warpgroup idles)
+template <int NG> struct WsCfg;
+template <> struct WsCfg<4> { static constexpr int kMainRegs = 200, kHelperRegs = 96, kPerHelper = 1; };
+template <> struct WsCfg<6> { static constexpr int kMainRegs = 152, kHelperRegs = 56, kPerHelper = 2; };
+
+template <int T, int NG>
+__global__ void __launch_bounds__(NG * 64 + 128, 1) transfer_ws_kernel(const K5Params P) {
+    constexpr int kThreads = NG * 64 + 128;
+    constexpr int kPerHelper = WsCfg<NG>::kPerHelper;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int m = P.m, p = P.p, F = P.F;
+    double* coef = reinterpret_cast<double*>(smem_raw);
+    double2* probe = reinterpret_cast<double2*>(smem_raw + MmaSmem<T>::coef_bytes(p));
+    double2* zs = reinterpret_cast<double2*>(smem_raw + MmaSmem<T>::coef_bytes(p) + MmaSmem<T>::probe_bytes(p));      // [bin of the unit][2 * n_planes]
+    MmaGroupSmem* groups = reinterpret_cast<MmaGroupSmem*>(smem_raw + MmaSmem<T>::coef_bytes(p) + MmaSmem<T>::probe_bytes(p) + MmaSmem<T>::z_bytes(p, P.seg_len));
+    const int warp = threadIdx.x >> 5;
+    const bool helper = warp >= 2 * NG;
+    MmaCtx x;
+    x.lane = threadIdx.x & 31;
+    x.part = warp & 1;
+    x.g4 = x.lane >> 2;
+    x.t4 = x.lane & 3;
+    const int gid = helper ? min((warp - 2 * NG) * kPerHelper, NG - 1) : warp >> 1;      // helper: its first group
+    const int n_served = helper ? max(0, min(kPerHelper, NG - (warp - 2 * NG) * kPerHelper)) : 0;
+    x.bar = 1 + gid;
+    x.dbg = 0;
+    x.gs = groups + gid;
+    MmaGroupSmem* gs = x.gs;
+    const int l64 = x.part * 32 + x.lane;
+    const int n_planes = MmaSmem<T>::planes(p);
+    const int n_steps = (m + 3) >> 2;
+    constexpr int NW = kThreads / 32;          // warps per CTA
+    if (!helper && l64 == 0) {
+        ws_mbar_init(&gs->bar_d, 2);
+        ws_mbar_init(&gs->bar_p, 1);
+    }
+    unsigned ph = 0;                           // block steps done by this group since the kernel started (barrier phase)
+    unsigned ph2[kPerHelper];                  // the same per served group (helpers serving several groups)
+#pragma unroll
+    for (int u = 0; u < kPerHelper; ++u) ph2[u] = 0;
+    // zero the coefficient planes once: padding rows / columns / the odd lag stay zero for every unit
+    for (int e = threadIdx.x; e < n_planes * kPlaneD; e += kThreads) coef[e] = 0.0;
+
+    // Balanced static partition: CTA c owns the matrices q = w * F + f in [c * per_cta, (c + 1) * per_cta): every CTA gets the
+    // same count (+-1 round of NG), and a window's coefficients are loaded once per PIECE (= the part of a window inside the range).
+    const long long q_total = (long long)P.n_win * F;
+    long long q = (long long)blockIdx.x * P.per_cta;
+    const long long q_end = min(q_total, q + (long long)P.per_cta);
+    // The two roles run SEPARATE copies of the piece loop (same barriers, same order): ptxas gives each role its own register
+    // budget only when the roles never re-join after setmaxnreg -- a shared loop body would be compiled for the smaller one.
+    auto prepare_piece = [&](const int w) {
+    __syncthreads();
+    {   // AR coefficients of window w -> shared, layout [lag pair][row][col][lag & 1]
+        const double* Aw = P.A + (size_t)w * m * m * p;
+        const int row_len = m * p;
+        for (int i = warp; i < m; i += NW) {       // one warp per row, 5 independent loads in flight per lane
+            const double* Ar = Aw + (size_t)i * row_len;
+            for (int c0 = x.lane; c0 < row_len; c0 += 5 * 32) {
+                double v[5];
+#pragma unroll
+                for (int u = 0; u < 5; ++u) v[u] = (c0 + 32 * u < row_len) ? Ar[c0 + 32 * u] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 5; ++u) {
+                    const int cidx = c0 + 32 * u;
+                    if (cidx < row_len) {
+                        const int j = cidx / p, k = cidx - j * p;
+                        coef[(k >> 1) * kPlaneD + i * kRowD + 2 * j + (k & 1)] = v[u];
+                    }
+                }
+            }
+        }
+        if (!helper)
+            for (int e = l64; e < 2 * kMP; e += 64) (&gs->rs[0][0])[e] = 0.0;
+    }
+    __syncthreads();
+    // probe[i][k] = sum_j A_k[i][j] u_j : the window-dependent part of v = A(f) u = u - sum_k z_k(f) probe[.][k]
+    for (int e = threadIdx.x; e < kMP * p; e += kThreads) {
+        const int i = e / p, k = e - i * p;
+        double sr = 0.0, si = 0.0;
+        const double* cp = coef + (k >> 1) * kPlaneD + i * kRowD + (k & 1);
+        for (int j = 0; j < m; ++j) {
+            const double2 u = probe_u2(j);
+            const double cv = cp[2 * j];
+            sr = fma(cv, u.x, sr);
+            si = fma(cv, u.y, si);
+        }
+        probe[e] = make_double2(sr, si);
+    }
+    __syncthreads();
+
+    };
+    if (helper) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WsCfg<NG>::kHelperRegs));
+        while (q < q_end) {
+            const int w = (int)(q / F);
+            const int f_begin = (int)(q - (long long)w * F);
+            const int f_end = (int)min((long long)F, f_begin + (q_end - q));
+            q += f_end - f_begin;
+            prepare_piece(w);
+            // ---- helper warp: one pivot-block inverse per block step of every matrix of the group(s) it serves; with two
+            //      groups it polls both mailboxes and serves whichever published first
+            if constexpr (kPerHelper == 1) {
+                for (int f = f_begin + gid; f < f_end; f += NG) {
+                    for (int st = 0; st < n_steps; ++st) {
+                        ws_mbar_wait(&gs->bar_d, ph & 1u);
+                        ++ph;
+                        ws_inverse4(gs, x.lane);
+                        __syncwarp();
+                        if (x.lane == 0) ws_mbar_arrive(&gs->bar_p);
+                    }
+                }
+            } else {
+                int left[kPerHelper];
+                int total = 0;
+#pragma unroll
+                for (int u = 0; u < kPerHelper; ++u) {
+                    const int first = f_begin + gid + u;
+                    left[u] = (u < n_served && first < f_end) ? ((f_end - first + NG - 1) / NG) * n_steps : 0;
+                    total += left[u];
+                }
+                while (total > 0) {
+#pragma unroll
+                    for (int u = 0; u < kPerHelper; ++u) {
+                        if (left[u] > 0 && ws_mbar_test(&gs[u].bar_d, (ph2[u] & 1u))) {
+                            ++ph2[u];
+                            --left[u];
+                            --total;
+                            ws_inverse4(gs + u, x.lane);
+                            __syncwarp();
+                            if (x.lane == 0) ws_mbar_arrive(&gs[u].bar_p);
+                        }
+                    }
+                }
+            }
+            __syncthreads();       // the main warps' row-sum write-out
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WsCfg<NG>::kMainRegs));
+        while (q < q_end) {
+            const int w = (int)(q / F);
+            const int f_begin = (int)(q - (long long)w * F);
+            const int f_end = (int)min((long long)F, f_begin + (q_end - q));
+            q += f_end - f_begin;
+            prepare_piece(w);
+        // z_k(f) of the group's current bin: a private 2 * n_planes slot in shared memory, filled from the (L2-resident) table by the
+        // lanes l64 < 2 * n_planes, which fetch the NEXT bin's values one matrix ahead
+        double2* zg = zs + gid * 2 * n_planes;
+        auto z_fetch = [&](const int f) {
+            return (l64 < p && f < f_end) ? P.z[(size_t)l64 * F + f] : make_double2(0.0, 0.0);
+        };
+        double2 z_next = z_fetch(f_begin + gid);
+        for (int f = f_begin + gid; f < f_end; f += NG) {
+            double c[T][T][2];
+            mma_group_sync(x);                      // previous matrix' check / epilogue is done with zg, vfull, wpart, X
+            if (l64 < 2 * n_planes) zg[l64] = z_next;
+            z_next = z_fetch(f + NG);
+            mma_group_sync(x);
+            // ---- v = A(f) u for the check (thread l64 < 40 owns entry l64)
+            const int vi = min(l64, kMP - 1);
+            double2 vacc = (l64 < m) ? probe_u2(l64) : make_double2(0.0, 0.0);
+            for (int k = 0; k < p; ++k) {
+                const double2 zz = zg[k];
+                const double2 q0 = probe[vi * p + k];
+                vacc.x = fma(-q0.x, zz.x, fma(q0.y, zz.y, vacc.x));
+                vacc.y = fma(-q0.x, zz.y, fma(-q0.y, zz.x, vacc.y));
+            }
+            if (l64 < kMP) gs->vfull[l64] = vacc;
+            if (l64 == 0) gs->flag = 0;
+            // ---- A(f) = I - sum_k A_k z_k(f)
+            if (n_planes == 4) mma_assemble<T, 4>(c, coef, zg, n_planes, x);
+            else mma_assemble<T, 0>(c, coef, zg, n_planes, x);
+            if (P.Af) mma_store_generic<T, false>(c, P, w, f, x);
+            // ---- blocked Gauss-Jordan on the tensor pipe
+            mma_group_sync(x);                 // previous users of the panel buffers (assembly exchange) are done
+            ws_publish<T, 0>(c, 0, x);         // pivot block of step 0
+            ws_all_tiles<T, 0>(c, m, x, ph);
+            // ---- a-posteriori check:  S v == u ?   (v = A(f) u)
+            {
+                double sr[T], si[T];
+#pragma unroll
+                for (int ta = 0; ta < T; ++ta) sr[ta] = si[ta] = 0.0;
+#pragma unroll
+                for (int tb = 0; tb < T; ++tb) {
+                    const double2 v0 = gs->vfull[8 * tb + 2 * x.t4], v1 = gs->vfull[8 * tb + 2 * x.t4 + 1];
+#pragma unroll
+                    for (int ta = 0; ta < T; ++ta) {
+                        sr[ta] = fma(c[ta][tb][0], v0.x, fma(c[ta][tb][1], v1.x, sr[ta]));
+                        si[ta] = fma(c[ta][tb][0], v0.y, fma(c[ta][tb][1], v1.y, si[ta]));
+                    }
+                }
+#pragma unroll
+                for (int ta = 0; ta < T; ++ta) {
+                    sr[ta] += __shfl_xor_sync(0xffffffffu, sr[ta], 1);
+                    si[ta] += __shfl_xor_sync(0xffffffffu, si[ta], 1);
+                    sr[ta] += __shfl_xor_sync(0xffffffffu, sr[ta], 2);
+                    si[ta] += __shfl_xor_sync(0xffffffffu, si[ta], 2);
+                    if (x.t4 == 0) {
+                        gs->wpart[x.part][0][8 * ta + x.g4] = sr[ta];
+                        gs->wpart[x.part][1][8 * ta + x.g4] = si[ta];
+                    }
+                }
+            }
+            mma_group_sync(x);
+            if (l64 < m) {
+                // S v = (Sr vr - Si vi) + i (Sr vi + Si vr)
+                const double wr = gs->wpart[0][0][l64] - gs->wpart[1][1][l64];
+                const double wi = gs->wpart[0][1][l64] + gs->wpart[1][0][l64];
+                const double2 u = probe_u2(l64);
+                const double er = wr - u.x, ei = wi - u.y;
+                const double err = fma(er, er, ei * ei), ref = fma(u.x, u.x, u.y * u.y);
+                if (!(err <= P.verify_tol2 * ref)) gs->flag = 1;      // also catches NaN / Inf
+            }
+            // ---- Re/Im exchange for |H|^2 (the panel buffers are free: the barrier above is past every fragment load).
+            //      The Re warp finishes the entries in even columns, the Im warp those in odd columns.
+            {
+                double* X = reinterpret_cast<double*>(gs->u.X) + x.part * (25 * 32) + x.lane;      // outbox of this warp
+#pragma unroll
+                for (int q = 0; q < T * T; ++q) X[q * 32] = x.part ? c[q / T][q % T][0] : c[q / T][q % T][1];
+            }
+            mma_group_sync(x);
+            const bool good = (gs->flag == 0);
+            if (!good) {
+                if (l64 == 0) {
+                    P.bad[(size_t)w * F + f] = 1;
+                    P.bad_list[atomicAdd(P.bad_count, 1)] = w * F + f;
+                }
+                continue;
+            }
+            if (P.H || (P.dtf && !P.dtf_fij)) {
+                mma_store_generic<T, true>(c, P, w, f, x);        // outputs in the reference layout: not the metric path
+            } else {
+                const double* X = reinterpret_cast<const double*>(gs->u.X) + (x.part ^ 1) * (25 * 32) + x.lane;      // the partner's outbox
+                const int j0 = 2 * x.t4 + x.part;
+                double* dst = P.dtf ? P.dtf + (((size_t)w * F + f) * m + x.g4) * m + j0 : nullptr;
+                const size_t row_step = (size_t)8 * m;
+#pragma unroll
+                for (int ta = 0; ta < T; ++ta) {
+                    double rsum = 0.0;
+                    const bool row_ok = (8 * ta + x.g4 < m);
+#pragma unroll
+                    for (int tb = 0; tb < T; ++tb) {
+                        const double mine = x.part ? c[ta][tb][1] : c[ta][tb][0];
+                        const double got = X[(ta * T + tb) * 32];
+                        const double v = fma(mine, mine, got * got);
+                        if (row_ok && (8 * tb + j0 < m)) {
+                            rsum += v;
+                            if (dst) dst[ta * row_step + 8 * tb] = v;
+                        }
+                    }
+                    rsum += __shfl_xor_sync(0xffffffffu, rsum, 1);
+                    rsum += __shfl_xor_sync(0xffffffffu, rsum, 2);
+                    if (x.t4 == 0 && row_ok) gs->rs[x.part][8 * ta + x.g4] += rsum;      // one writer per (warp, row): deterministic
+                }
+            }
+        }
+        // ---- row sums of the piece (fixed summation order -> deterministic); slot = CTA index - first CTA of the window
+        __syncthreads();
+        if (P.rowpart && threadIdx.x < m) {
+            double acc = 0.0;
+            for (int g2 = 0; g2 < NG; ++g2) acc += groups[g2].rs[0][threadIdx.x] + groups[g2].rs[1][threadIdx.x];
+            const int slot = (int)blockIdx.x - (int)(((long long)w * F) / P.per_cta);
+            P.rowpart[((size_t)w * P.n_seg + slot) * m + threadIdx.x] = acc;
+        }
+        }
+    }
+}
+
+#endif  // HS_EXPERIMENT (transfer_ws_kernel)
+
 template <int T, int NG>
 int launch_mma_t(const K5Params& P, int sm_count, cudaStream_t stream) {
     const size_t smem = MmaSmem<T>::total(P.p, NG, P.seg_len);
@@ -649,7 +1086,51 @@ int launch_mma_t(const K5Params& P, int sm_count, cudaStream_t stream) {
     return check_launch("transfer_mma_kernel");
 }
 
+#ifdef HS_EXPERIMENT
+template <int T, int NG>
+int launch_ws_t(const K5Params& P, cudaStream_t stream) {
+    const size_t smem = MmaSmem<T>::total(P.p, NG, P.seg_len);
+    if (smem > 227 * 1024) return set_error(HS_ERR_UNSUPPORTED, "transfer_ws: model order %d needs %zu B shared memory", P.p, smem);
+    auto kern = transfer_ws_kernel<T, NG>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "transfer_ws: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
+    const long long q_total = (long long)P.n_win * P.F;
+    const int grid = (int)((q_total + P.per_cta - 1) / P.per_cta);
+    kern<<<grid, NG * 64 + 128, smem, stream>>>(P);
+    return check_launch("transfer_ws_kernel");
+}
+
+#endif
+
 }  // namespace
+
+// Warp-specialised optimistic pass (groups of Re / Im warps + helper warps that invert the pivot blocks one step ahead); same
+// contract as launch_transfer_mma.  Measured on 599 cfg2 windows: 5.48 ms (4 groups, one helper each) and 5.91 ms (6 groups, three
+// helpers) against 5.31 ms for transfer_mma_kernel, so it is compiled only into HS_EXPERIMENT builds.
+int launch_transfer_ws(const K5Params& P, int ng, cudaStream_t stream) {
+#ifndef HS_EXPERIMENT
+    (void)P; (void)ng; (void)stream;
+    return set_error(HS_ERR_UNSUPPORTED, "transfer_ws_kernel is compiled into HS_EXPERIMENT builds only");
+#else
+    if (ng == 6) {
+        switch ((P.m + 7) / 8) {
+            case 1: return launch_ws_t<1, 6>(P, stream);
+            case 2: return launch_ws_t<2, 6>(P, stream);
+            case 3: return launch_ws_t<3, 6>(P, stream);
+            case 4: return launch_ws_t<4, 6>(P, stream);
+            case 5: return launch_ws_t<5, 6>(P, stream);
+        }
+    }
+    switch ((P.m + 7) / 8) {
+        case 1: return launch_ws_t<1, 4>(P, stream);
+        case 2: return launch_ws_t<2, 4>(P, stream);
+        case 3: return launch_ws_t<3, 4>(P, stream);
+        case 4: return launch_ws_t<4, 4>(P, stream);
+        case 5: return launch_ws_t<5, 4>(P, stream);
+    }
+    return set_error(HS_ERR_UNSUPPORTED, "transfer_ws: no kernel for m=%d", P.m);
+#endif
+}
 
 void transfer_mma_partition(int n_win, int F, int* per_cta, int* slots, int ng) {
     const long long total = (long long)n_win * F;

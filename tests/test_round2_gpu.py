@@ -172,3 +172,54 @@ def test_downsample_two_dimensional_is_axis_zero():
     got = downsample_signal(x, 128, 8)
     ref = signal.resample_poly(x, up=1, down=16)
     assert got.shape == ref.shape == (40, 3) and relerr(got, ref) < TOL_SIGNAL
+
+
+@pytest.mark.parametrize("which", [1, 2, 3])
+def test_both_transfer_kernels_against_reference(mv, which):
+    """transfer_mma_kernel (6 groups of Re/Im warps) and transfer_ws_kernel (4 groups of Re/Im/helper warps) deliver the same
+    H / ffDTF: reference goldens at m = 4 and m = 38, odd shapes against the oracle, and the forced-pivot fallback."""
+    import torch
+    from hyperscanning_signal_analysis_b200 import _lib
+    from oracle import mvar_oracle as mo
+    lib = _lib.load()
+    if lib.hs_transfer_set_kernel(which) != 0:
+        assert which >= 2 and "HS_EXPERIMENT" in _lib.last_error()
+        pytest.skip("warp-specialised kernel: HS_EXPERIMENT builds only")
+    try:
+        g = golden("mvar_cfg2_windows.npz")
+        for w in range(g["windows"].shape[0]):
+            ff = quiet(mv.full_freq_dtf, g["windows"][w], g["freqs"], 256.0, optimal_model_order=8)
+            assert relerr(ff, g["ffdtf"][w]) < TOL_MODEL
+        m4 = golden("mvar_m4.npz")
+        H, Af = mv.mvar_transfer_function(m4["A"], m4["freqs"], float(m4["fs"]))
+        assert relerr(H, m4["H"]) < TOL_MODEL and relerr(Af, m4["Af"]) < 1e-12
+        rng = np.random.default_rng(17)
+        for m, p, F in ((9, 3, 11), (17, 5, 40), (33, 2, 7), (38, 8, 130), (40, 4, 64)):
+            A = rng.standard_normal((m, m, p)) * (0.4 / np.sqrt(m))
+            freqs = np.linspace(0.0, 100.0, F)
+            H, _ = mv.mvar_transfer_function(A, freqs, 256.0)
+            Hr, _ = mo.mvar_transfer_function(A, freqs, 256.0)
+            assert relerr(H, Hr) < TOL_MODEL, (m, p, F)
+        # zero diagonal at f = 0: the optimistic pass must flag, the pivoted redo must deliver
+        m, p = 38, 2
+        Pm = np.roll(np.eye(m), 1, axis=1)
+        A = np.zeros((m, m, p))
+        A[:, :, 0] = np.eye(m) - Pm
+        A[:, :, 1] = 0.01 * rng.standard_normal((m, m))
+        freqs = np.array([0.0, 3.0, 17.0, 40.0, 64.0, 90.0, 127.5])
+        H, _ = mv.mvar_transfer_function(A, freqs, 256.0)
+        Hr, _ = mo.mvar_transfer_function(A, freqs, 256.0)
+        for fi in range(len(freqs)):
+            assert relerr(H[:, :, fi], Hr[:, :, fi]) < TOL_MODEL, fi
+        # many windows: row sums and determinism
+        from hyperscanning_signal_analysis_b200 import mtmvar, synth
+        x = synth.dyad_eeg(seed=5, n_samples=8192, line_amp=0.0)
+        starts = np.arange(0, 8192 - 512 + 1, 128)
+        freqs = np.linspace(0, 128, 256, endpoint=False)
+        a = mtmvar.windowed_ffdtf(x, starts, 512, freqs, 256.0, 8)
+        b = mtmvar.windowed_ffdtf(x, starts, 512, freqs, 256.0, 8)
+        assert torch.equal(a, b)
+        assert float((a.sum(dim=(2, 3)) - 1).abs().max()) < 1e-9
+    finally:
+        lib.hs_transfer_set_kernel(0)
+    assert lib.hs_transfer_set_kernel(7) != 0 and lib.hs_transfer_set_kernel(-1) != 0

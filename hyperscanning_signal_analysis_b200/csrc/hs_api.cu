@@ -116,10 +116,10 @@ int hs_version(void) { return 100; }
 long long hs_launch_count(void) { return g_launches.load(); }
 
 int hs_transfer_set_kernel(int which) {
-    if (which < 0 || which > 3)
-        return set_error(HS_ERR_INVALID, "hs_transfer_set_kernel: 0 (automatic), 1 (transfer_mma_kernel), 2 / 3 (transfer_ws_kernel with 4 / 6 groups)");
+    if (which < 0 || which > 4)
+        return set_error(HS_ERR_INVALID, "hs_transfer_set_kernel: 0 (automatic), 1 (transfer_mma_kernel), 2 / 3 (transfer_ws_kernel with 4 / 6 groups), 4 (pipe-turn lock)");
 #ifndef HS_EXPERIMENT
-    if (which >= 2) return set_error(HS_ERR_UNSUPPORTED, "hs_transfer_set_kernel: the warp-specialised kernel is compiled into HS_EXPERIMENT builds only");
+    if (which >= 2) return set_error(HS_ERR_UNSUPPORTED, "hs_transfer_set_kernel: the warp-specialised kernel and the pipe-turn lock are compiled into HS_EXPERIMENT builds only");
 #endif
     g_k5_kernel.store(which);
     return HS_OK;
@@ -293,6 +293,7 @@ int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double 
     P.seg_len = sl;
     P.per_cta = 0;
     P.flip = exp_env_int("HS_K5_FLIP", 0);
+    P.pipe_turns = (g_k5_kernel.load() == 4) ? 1 : 0;
     P.rowpart2 = nullptr;
     P.bad = bad;
     P.bad_count = bad_count;

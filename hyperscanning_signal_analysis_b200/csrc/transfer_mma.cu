@@ -82,7 +82,32 @@ struct __align__(16) MmaGroupSmem {
 struct MmaCtx {
     int part, lane, g4, t4, bar, dbg;
     MmaGroupSmem* gs;
+    int* lock;          // tensor-pipe turn lock of this warp's SM sub-partition, or null (transfer_mma_kernel)
 };
+
+// Experiment (HS_EXPERIMENT builds, hs_transfer_set_kernel(4)): one warp at a time per SM sub-partition streams its block step's
+// DMMAs.  The idea: three warps sharing a sub-partition's FP64 tensor pipe might fall into lock-step (all streaming DMMAs at a third
+// of the rate, then all in their scalar phases with the pipe idle); a single warp can feed the pipe alone (tools/dmma_rate.cu: 16.5
+// cycles per DMMA with one warp, 16.0 with two or more).  Measured: 5.85 ms against 5.29 ms without the lock -- the hand-over of the
+// lock and the exposed latencies at the start of every hold cost more than the interleaving wins.
+__device__ __forceinline__ void pipe_lock(const MmaCtx& x) {
+#ifdef HS_EXPERIMENT
+    if (x.lock) {
+        if (x.lane == 0) {
+            while (atomicCAS(x.lock, 0, 1) != 0) { }
+        }
+        __syncwarp();
+    }
+#endif
+}
+__device__ __forceinline__ void pipe_unlock(const MmaCtx& x) {
+#ifdef HS_EXPERIMENT
+    if (x.lock) {
+        __syncwarp();
+        if (x.lane == 0) atomicExch(x.lock, 0);
+    }
+#endif
+}
 
 __device__ __forceinline__ void mma_group_sync(const MmaCtx& x) { asm volatile("bar.sync %0, 64;" ::"r"(x.bar) : "memory"); }
 
@@ -215,6 +240,7 @@ __device__ __forceinline__ void mma_tile_steps(double (&c)[T][T][2], const int m
         else mma_inverse4(x, K0, h);
         // B fragments of -P with Re/Im interleaved by output column:  n = 2j -> Re, n = 2j+1 -> Im
         double a0[T], a1[T];
+        pipe_lock(x);
         {
             const double2 pv = gs->u.p.P[x.part][x.t4 * 4 + (x.g4 >> 1)];
             const bool odd = x.g4 & 1;
@@ -271,6 +297,7 @@ __device__ __forceinline__ void mma_tile_steps(double (&c)[T][T][2], const int m
                 }
             }
         }
+        pipe_unlock(x);
     }
 }
 
@@ -595,6 +622,13 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
     x.bar = 1 + gid;
     x.dbg = (P.flip >> 27) & 1;
     x.gs = groups + gid;
+#ifdef HS_EXPERIMENT
+    __shared__ int pipe_locks[4];
+    if (threadIdx.x < 4) pipe_locks[threadIdx.x] = 0;
+    x.lock = P.pipe_turns ? &pipe_locks[warp & 3] : nullptr;       // warp w runs on sub-partition w % 4
+#else
+    x.lock = nullptr;
+#endif
     MmaGroupSmem* gs = x.gs;
     const int l64 = x.part * 32 + x.lane;
     const int n_planes = MmaSmem<T>::planes(p);
@@ -821,6 +855,7 @@ __global__ void __launch_bounds__(NG * 64 + 128, 1) transfer_ws_kernel(const K5P
     const int n_served = helper ? max(0, min(kPerHelper, NG - (warp - 2 * NG) * kPerHelper)) : 0;
     x.bar = 1 + gid;
     x.dbg = 0;
+    x.lock = nullptr;
     x.gs = groups + gid;
     MmaGroupSmem* gs = x.gs;
     const int l64 = x.part * 32 + x.lane;

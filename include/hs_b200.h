@@ -104,7 +104,8 @@ size_t hs_transfer_ws_bytes(int n_win, int m, int p, int F);
 size_t hs_transfer_ws_flag_offset(int n_win, int m, int p, int F);
 /* Test / measurement hook: which optimistic A(f)^-1 kernel the following calls use: 0 automatic, 1 transfer_mma_kernel
  * (6 groups of Re / Im warps); 2 / 3 transfer_ws_kernel (4 / 6 groups with helper warps inverting the pivot blocks one step
- * ahead) exist in `make HS_EXPERIMENT=1` builds only (measured slower) and return HS_ERR_UNSUPPORTED otherwise.
+ * ahead) and 4 (transfer_mma_kernel with a per-sub-partition tensor-pipe turn lock) exist in `make HS_EXPERIMENT=1` builds only
+ * (both measured slower) and return HS_ERR_UNSUPPORTED otherwise.
  * Process-wide.                                                                                                        */
 int hs_transfer_set_kernel(int which);
 int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double fs, int n_win, int m, int p,

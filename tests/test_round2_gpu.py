@@ -174,7 +174,7 @@ def test_downsample_two_dimensional_is_axis_zero():
     assert got.shape == ref.shape == (40, 3) and relerr(got, ref) < TOL_SIGNAL
 
 
-@pytest.mark.parametrize("which", [1, 2, 3])
+@pytest.mark.parametrize("which", [1, 2, 3, 4])
 def test_both_transfer_kernels_against_reference(mv, which):
     """transfer_mma_kernel (6 groups of Re/Im warps) and transfer_ws_kernel (4 groups of Re/Im/helper warps) deliver the same
     H / ffDTF: reference goldens at m = 4 and m = 38, odd shapes against the oracle, and the forced-pivot fallback."""

@@ -99,16 +99,38 @@ def window_layout(counts: Sequence[int]) -> List[int]:
 
 
 def chunk_ranges(n_units: int, units_per_chunk: int, ramp: bool = False) -> List[Tuple[int, int]]:
-    """Contiguous [lo, hi) unit ranges of at most ``units_per_chunk`` units (the push granularity).  ``ramp``: the first
-    chunks hold 1 and 2 units, so the exchange starts after a fraction of a full chunk's compute time."""
+    """Contiguous [lo, hi) unit ranges of at most ``units_per_chunk`` units (the push granularity).  ``ramp``: the first chunks
+    hold 1, 2, 4 units, so the exchange starts after a fraction of a full chunk's compute time, and the last ones 2 and 1, so
+    little is left to push when the compute ends."""
     if units_per_chunk < 1:
         raise ValueError("units_per_chunk must be >= 1")
-    out, lo, k = [], 0, 0
-    while lo < n_units:
-        size = min(units_per_chunk, 1 << k) if ramp else units_per_chunk
-        out.append((lo, min(n_units, lo + size)))
+    sizes: List[int] = []
+    left = n_units
+    if ramp:
+        tail = [s for s in (2, 1) if s < units_per_chunk]
+        k = 0
+        while left > sum(tail) and (1 << k) < units_per_chunk:
+            size = min(1 << k, left - sum(tail))
+            sizes.append(size)
+            left -= size
+            k += 1
+        while left > sum(tail):
+            size = min(units_per_chunk, left - sum(tail))
+            sizes.append(size)
+            left -= size
+        for s_ in tail:
+            if left > 0:
+                size = min(s_, left)
+                sizes.append(size)
+                left -= size
+    while left > 0:
+        size = min(units_per_chunk, left)
+        sizes.append(size)
+        left -= size
+    out, lo = [], 0
+    for size in sizes:
+        out.append((lo, lo + size))
         lo += size
-        k += 1
     return out
 
 

@@ -69,7 +69,12 @@ assert out2.shape == (8, 3) and out2[:4].eq(0).all() and out2[4:].eq(1).all()
 assert sharding.window_layout([5, 4, 0, 3]) == [0, 5, 9, 9]
 assert sharding.chunk_ranges(24, 5) == [(0, 5), (5, 10), (10, 15), (15, 20), (20, 24)]
 assert sharding.chunk_ranges(0, 5) == []
-assert sharding.chunk_ranges(24, 5, ramp=True) == [(0, 1), (1, 3), (3, 7), (7, 12), (12, 17), (17, 22), (22, 24)]
+assert sharding.chunk_ranges(24, 5, ramp=True) == [(0, 1), (1, 3), (3, 7), (7, 12), (12, 17), (17, 21), (21, 23), (23, 24)]
+for n_u in range(0, 40):
+    for upc in (1, 2, 5):
+        cr = sharding.chunk_ranges(n_u, upc, ramp=True)
+        assert [a for a, _ in cr] == [0] * (n_u > 0) + [b for _, b in cr][:-1] and (not cr or cr[-1][1] == n_u)
+        assert all(0 < b - a <= upc for a, b in cr)
 # cfg3: 64 dyads x 3 tasks split evenly over 1/2/4/8 ranks, whole dyads per rank
 u3 = sharding.unit_table(64, ["SECORE", "MOVIE", "TALK"])
 for wsz in (1, 2, 4, 8):

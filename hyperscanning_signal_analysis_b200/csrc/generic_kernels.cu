@@ -390,10 +390,286 @@ __global__ void __launch_bounds__(256) transfer_generic_kernel(const K5Params P,
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Blocked generic A(f)^-1 (40 < m <= 160; cfg5: m = 128): Gauss-Jordan with PARTIAL PIVOTING in blocks of 16 pivots, the
+// rank-16 updates on the FP64 tensor pipe.  One CTA of 16 warps per matrix (persistent over matrices); the matrix lives in a
+// private global scratch slot (256 KB at m = 128: L2 resident, too large for shared memory next to the panels).
+// Per block of columns K = {k0 .. k0+15}:
+//   1. the column panel C = S[:, K] is copied to shared memory (twice: one copy is destroyed by the pivot search);
+//   2. pivot rows r_0 .. r_15 by LU-style elimination with partial pivoting INSIDE the panel (the panel holds every row, so these are
+//      the pivots unblocked partial pivoting would choose: the Gauss-Jordan updates of already used rows do not touch unused rows);
+//   3. D = C[R, :], P = D^-1 (16 x 16, elimination in pivot order), L = C P for the other rows, L[r_t, :] = e_t - P[t, :];
+//   4. the panel columns of S get the identity pattern (1 at (r_t, k0 + t)), U = S[R, :] is gathered;
+//   5. S <- S - L U for ALL rows: 4 DMMA m8n8k4 per (8 x 8 tile, 4 pivots) -- afterwards the pivot rows hold P U, the panel columns -L.
+// The matrix is read and written once per 16 pivots instead of once per pivot (round 1's kernel: 64 MB of L2 traffic per matrix).
+// Same result mapping as the unblocked kernel: inverse[rowmap[i]][colmap[j]] = a[i][j].
+// ------------------------------------------------------------------------------------------------
+constexpr int kNB = 16;
+constexpr int kLLd = kNB + 4;           // row stride of the L panel in doubles (= 4 mod 16: conflict-free A fragments)
+constexpr int kBlkThreads = 512;
+
+__device__ __forceinline__ void dmma884_g(double& c0, double& c1, const double a, const double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double2 cmul_g(const double2 a, const double2 b) { return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x)); }
+
+struct BlkSmem {
+    static __host__ __device__ int mp(int m) { return (m + kNB - 1) / kNB * kNB; }
+    static __host__ __device__ int ldu(int m) { return mp(m) + 4; }
+    static __host__ __device__ size_t bytes(int m) {
+        const size_t Mp = mp(m);
+        return 2 * Mp * kNB * sizeof(double2)            // Cp, C0
+               + 2 * Mp * kLLd * sizeof(double)          // Lre, Lim
+               + 2 * (size_t)kNB * ldu(m) * sizeof(double)   // Ure, Uim
+               + 2 * kNB * kNB * sizeof(double2)         // D, P
+               + (3 * Mp + kNB) * sizeof(int) + 64;
+    }
+};
+
+__global__ void __launch_bounds__(kBlkThreads, 1) transfer_blocked_kernel(const K5Params P, double2* __restrict__ scratch) {
+    extern __shared__ __align__(16) unsigned char smb[];
+    const int m = P.m, p = P.p, F = P.F;
+    const int Mp = BlkSmem::mp(m), ldu = BlkSmem::ldu(m);
+    double2* Cp = reinterpret_cast<double2*>(smb);                       // [Mp][16]
+    double2* C0 = Cp + (size_t)Mp * kNB;                                 // [Mp][16]
+    double* Lre = reinterpret_cast<double*>(C0 + (size_t)Mp * kNB);      // [Mp][kLLd]
+    double* Lim = Lre + (size_t)Mp * kLLd;
+    double* Ure = Lim + (size_t)Mp * kLLd;                               // [16][ldu]
+    double* Uim = Ure + (size_t)kNB * ldu;
+    double2* Dm = reinterpret_cast<double2*>(Uim + (size_t)kNB * ldu);   // [16][16]
+    double2* Pm = Dm + kNB * kNB;
+    int* rowmap = reinterpret_cast<int*>(Pm + kNB * kNB);                // [Mp]
+    int* colmap = rowmap + Mp;
+    int* used = colmap + Mp;
+    int* piv = used + Mp;                                                // [16] pivot rows of the current block
+    __shared__ double s_red[kBlkThreads / 32];
+    __shared__ int s_idx[kBlkThreads / 32];
+    double2* a = scratch + (size_t)blockIdx.x * Mp * Mp;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g4 = lane >> 2, t4 = lane & 3;
+    const long long n_mat = (long long)P.n_win * F;
+    for (long long mat = blockIdx.x; mat < n_mat; mat += gridDim.x) {
+        const int w = (int)(mat / F), f = (int)(mat % F);
+        const double* Aw = P.A + (size_t)w * m * m * p;
+        __syncthreads();
+        // z_k(f) of this bin: the D block is free until step 3 of the first panel
+        double2* zf = Dm;
+        for (int k = tid; k < p && k < kNB * kNB; k += kBlkThreads) zf[k] = __ldg(&P.z[(size_t)k * F + f]);
+        __syncthreads();
+        // ---- A(f) = I - sum_k A_k z_k(f), padded to Mp x Mp with the identity
+        for (int e = tid; e < Mp * Mp; e += kBlkThreads) {
+            const int i = e / Mp, j = e - i * Mp;
+            double re = (i == j) ? 1.0 : 0.0, im = 0.0;
+            if (i < m && j < m) {
+                const double* cp = Aw + ((size_t)i * m + j) * p;
+                for (int k = 0; k < p; ++k) {
+                    const double2 z = (p <= kNB * kNB) ? zf[k] : __ldg(&P.z[(size_t)k * F + f]);
+                    const double c = cp[k];
+                    re = fma(-c, z.x, re);
+                    im = fma(-c, z.y, im);
+                }
+                if (P.Af) P.Af[((size_t)w * m * m + (size_t)i * m + j) * F + f] = make_double2(re, im);
+            }
+            a[e] = make_double2(re, im);
+        }
+        for (int e = tid; e < Mp; e += kBlkThreads) used[e] = 0;
+        __syncthreads();
+        for (int k0 = 0; k0 < Mp; k0 += kNB) {
+            // ---- 1. column panel -> shared memory
+            for (int e = tid; e < Mp * kNB; e += kBlkThreads) {
+                const int i = e / kNB, q = e - i * kNB;
+                const double2 v = a[(size_t)i * Mp + k0 + q];
+                Cp[e] = v;
+                C0[e] = v;
+            }
+            __syncthreads();
+            // ---- 2. pivot rows by partial pivoting inside the panel
+            for (int q = 0; q < kNB; ++q) {
+                double best = -1.0;
+                int bi = 1 << 20;
+                for (int i = tid; i < Mp; i += kBlkThreads) {
+                    if (!used[i]) {
+                        const double2 v = Cp[i * kNB + q];
+                        const double mag = fma(v.x, v.x, v.y * v.y);
+                        if (mag > best || bi == (1 << 20)) { if (mag > best) best = mag; bi = i; }
+                    }
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                }
+                if (lane == 0) { s_red[warp] = best; s_idx[warp] = bi; }
+                __syncthreads();
+                if (tid == 0) {
+                    double bb = s_red[0];
+                    int ii = s_idx[0];
+                    for (int u = 1; u < kBlkThreads / 32; ++u)
+                        if (s_red[u] > bb || (s_red[u] == bb && s_idx[u] < ii)) { bb = s_red[u]; ii = s_idx[u]; }
+                    piv[q] = ii;
+                    used[ii] = 1;
+                    rowmap[ii] = k0 + q;
+                    colmap[k0 + q] = ii;
+                    if (!(bb > 0.0)) atomicOr(&P.status[w], 1);
+                }
+                __syncthreads();
+                const int r = piv[q];
+                const double2 pv = Cp[r * kNB + q];
+                const double d = 1.0 / fma(pv.x, pv.x, pv.y * pv.y);
+                const double2 iv = make_double2(pv.x * d, -pv.y * d);
+                const int rem = kNB - 1 - q;
+                for (int e = tid; e < Mp * rem; e += kBlkThreads) {
+                    const int i = e / rem, c = q + 1 + e % rem;
+                    if (!used[i]) {
+                        const double2 l = cmul_g(Cp[i * kNB + q], iv);
+                        const double2 rv = Cp[r * kNB + c];
+                        double2 x = Cp[i * kNB + c];
+                        x.x = fma(-l.x, rv.x, fma(l.y, rv.y, x.x));
+                        x.y = fma(-l.x, rv.y, fma(-l.y, rv.x, x.y));
+                        Cp[i * kNB + c] = x;
+                    }
+                }
+                __syncthreads();
+            }
+            // ---- 3. D = C0[R, :] and P = D^-1 (Gauss-Jordan in pivot order, one thread per entry of the 16 x 16 block)
+            if (tid < kNB * kNB) {
+                const int t = tid / kNB, sidx = tid % kNB;
+                Dm[tid] = C0[piv[t] * kNB + sidx];
+                Pm[tid] = make_double2(t == sidx ? 1.0 : 0.0, 0.0);
+            }
+            __syncthreads();
+            for (int sidx = 0; sidx < kNB; ++sidx) {
+                double2 dnew = make_double2(0.0, 0.0), pnew = make_double2(0.0, 0.0);
+                if (tid < kNB * kNB) {
+                    const int t = tid / kNB, c = tid % kNB;
+                    const double2 pvt = Dm[sidx * kNB + sidx];
+                    const double dd = 1.0 / fma(pvt.x, pvt.x, pvt.y * pvt.y);
+                    const double2 iv = make_double2(pvt.x * dd, -pvt.y * dd);
+                    const double2 rd = cmul_g(Dm[sidx * kNB + c], iv), rp = cmul_g(Pm[sidx * kNB + c], iv);      // scaled pivot row
+                    if (t == sidx) {
+                        dnew = rd;
+                        pnew = rp;
+                    } else {
+                        const double2 l = Dm[t * kNB + sidx];
+                        const double2 d0 = Dm[t * kNB + c], p0 = Pm[t * kNB + c];
+                        dnew = make_double2(fma(-l.x, rd.x, fma(l.y, rd.y, d0.x)), fma(-l.x, rd.y, fma(-l.y, rd.x, d0.y)));
+                        pnew = make_double2(fma(-l.x, rp.x, fma(l.y, rp.y, p0.x)), fma(-l.x, rp.y, fma(-l.y, rp.x, p0.y)));
+                    }
+                }
+                __syncthreads();
+                if (tid < kNB * kNB) { Dm[tid] = dnew; Pm[tid] = pnew; }
+                __syncthreads();
+            }
+            // ---- 3b. L = C0 P (rows outside R), L[r_t, :] = e_t - P[t, :]
+            for (int e = tid; e < Mp * kNB; e += kBlkThreads) {
+                const int i = e / kNB, q = e - i * kNB;
+                double2 acc = make_double2(0.0, 0.0);
+                const int rm = rowmap[i] - k0;               // 0..15 when row i is one of this block's pivot rows
+                if (used[i] && rm >= 0 && rm < kNB && piv[rm] == i) {
+                    const double2 pq = Pm[rm * kNB + q];
+                    acc = make_double2((rm == q ? 1.0 : 0.0) - pq.x, -pq.y);
+                } else {
+#pragma unroll
+                    for (int sidx = 0; sidx < kNB; ++sidx) {
+                        const double2 c = C0[i * kNB + sidx], pq = Pm[sidx * kNB + q];
+                        acc.x = fma(c.x, pq.x, fma(-c.y, pq.y, acc.x));
+                        acc.y = fma(c.x, pq.y, fma(c.y, pq.x, acc.y));
+                    }
+                }
+                Lre[i * kLLd + q] = acc.x;
+                Lim[i * kLLd + q] = acc.y;
+                // ---- 4a. identity pattern into the panel columns of S
+                a[(size_t)i * Mp + k0 + q] = make_double2((used[i] && rm == q && piv[q] == i) ? 1.0 : 0.0, 0.0);
+            }
+            __syncthreads();
+            // ---- 4b. U = S[R, :]
+            for (int e = tid; e < kNB * Mp; e += kBlkThreads) {
+                const int t = e / Mp, j = e - t * Mp;
+                const double2 v = a[(size_t)piv[t] * Mp + j];
+                Ure[t * ldu + j] = v.x;
+                Uim[t * ldu + j] = v.y;
+            }
+            __syncthreads();
+            // ---- 5. S <- S - L U on the tensor pipe: warp = tile row(s), 16 DMMAs per 8 x 8 complex tile
+            const int n_t = Mp >> 3;
+            for (int ta = warp; ta < n_t; ta += kBlkThreads / 32) {
+                double nlr[4], pli[4], nli[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const double lr = Lre[(8 * ta + g4) * kLLd + 4 * kk + t4], li = Lim[(8 * ta + g4) * kLLd + 4 * kk + t4];
+                    nlr[kk] = -lr;
+                    pli[kk] = li;
+                    nli[kk] = -li;
+                }
+                double2* rowp = a + (size_t)(8 * ta + g4) * Mp + 2 * t4;
+                double2 c0 = rowp[0], c1 = rowp[1];
+                for (int tb = 0; tb < n_t; ++tb) {
+                    double2 n0 = c0, n1 = c1;
+                    if (tb + 1 < n_t) { n0 = rowp[8 * (tb + 1)]; n1 = rowp[8 * (tb + 1) + 1]; }      // next tile's entries in flight
+                    double cr0 = c0.x, cr1 = c1.x, ci0 = c0.y, ci1 = c1.y;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const double ur = Ure[(4 * kk + t4) * ldu + 8 * tb + g4], ui = Uim[(4 * kk + t4) * ldu + 8 * tb + g4];
+                        dmma884_g(cr0, cr1, nlr[kk], ur);
+                        dmma884_g(cr0, cr1, pli[kk], ui);
+                        dmma884_g(ci0, ci1, nlr[kk], ui);
+                        dmma884_g(ci0, ci1, nli[kk], ur);
+                    }
+                    rowp[8 * tb] = make_double2(cr0, ci0);
+                    rowp[8 * tb + 1] = make_double2(cr1, ci1);
+                    c0 = n0;
+                    c1 = n1;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- outputs: inverse[rowmap[i]][colmap[j]] = a[i][j]
+        for (int e = tid; e < Mp * Mp; e += kBlkThreads) {
+            const int i = e / Mp, j = e - i * Mp;
+            const int oi = rowmap[i], oj = colmap[j];
+            if (oi < m && oj < m) {
+                const double2 v = a[e];
+                const size_t o = ((size_t)w * m * m + (size_t)oi * m + oj) * F + f;
+                if (P.dtf) P.dtf[o] = fma(v.x, v.x, v.y * v.y);
+                if (P.H) P.H[o] = v;
+            }
+        }
+        if (P.rowpart) {
+            for (int i = tid; i < Mp; i += kBlkThreads) {
+                const int oi = rowmap[i];
+                if (oi < m) {
+                    double acc = 0.0;
+                    for (int j = 0; j < Mp; ++j) {
+                        if (colmap[j] < m) {
+                            const double2 v = a[(size_t)i * Mp + j];
+                            acc += fma(v.x, v.x, v.y * v.y);
+                        }
+                    }
+                    P.rowpart[((size_t)w * F + f) * m + oi] = acc;
+                }
+            }
+        }
+    }
+}
+
 int transfer_generic_grid() { return device_sm_count() * 2; }
-size_t transfer_generic_scratch_bytes(int m) { return (size_t)transfer_generic_grid() * m * m * sizeof(double2); }
+size_t transfer_generic_scratch_bytes(int m) {
+    const size_t Mp = BlkSmem::mp(m);
+    return (size_t)transfer_generic_grid() * Mp * Mp * sizeof(double2);       // covers both kernels (Mp >= m)
+}
 
 int launch_transfer_generic(const K5Params& P, void* scratch, cudaStream_t st) {
+    const size_t smem_blk = BlkSmem::bytes(P.m);
+    if (smem_blk <= 220 * 1024 && exp_env_int("HS_K5_GENERIC_UNBLOCKED", 0) == 0) {
+        cudaError_t e = cudaFuncSetAttribute(transfer_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_blk);
+        if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "transfer_blocked: %s", cudaGetErrorString(e));
+        long long n_mat = (long long)P.n_win * P.F;
+        int grid = device_sm_count();
+        if (n_mat < grid) grid = (int)n_mat;
+        transfer_blocked_kernel<<<grid, kBlkThreads, smem_blk, st>>>(P, reinterpret_cast<double2*>(scratch));
+        return check_launch("transfer_blocked_kernel");
+    }
     const size_t smem = (size_t)2 * P.m * sizeof(double2) + 3 * P.m * sizeof(int) + 16;
     long long n_mat = (long long)P.n_win * P.F;
     int grid = transfer_generic_grid();

@@ -142,6 +142,91 @@ __global__ void __launch_bounds__(256) binv_kernel(const double* __restrict__ V,
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Inverse of symmetric positive definite m x m matrices (the residual covariances Vf / Vb of the LWR recursion), m <= 128:
+// in-place Gauss-Jordan WITHOUT pivoting (stable for SPD matrices; the m <= 40 path does the same) with the matrix in REGISTERS:
+// 32 x 32 threads, thread (ty, tx) owns the cyclic 4 x 4 sub-matrix rows ty + 32 a, columns tx + 32 b.  Per pivot the owners of
+// column k and row k publish them to a double-buffered shared-memory pair, ONE barrier, then every thread updates its 16
+// entries: 128 barriers per inverse (binv_kernel: pivot search + index arithmetic, ~1.2 ms per 128 x 128 matrix; this: ~15 us).
+// ------------------------------------------------------------------------------------------------
+constexpr int kSpdE = 4;
+__global__ void __launch_bounds__(1024, 1) binv_spd_kernel(const double* __restrict__ V, double* __restrict__ X, const int m, int* status, const int flag) {
+    __shared__ double colb[2][32 * kSpdE], rowb[2][32 * kSpdE];
+    __shared__ int bad;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const double* v = V + (size_t)blockIdx.x * m * m;
+    double a[kSpdE][kSpdE];
+#pragma unroll
+    for (int ia = 0; ia < kSpdE; ++ia)
+#pragma unroll
+        for (int ib = 0; ib < kSpdE; ++ib) {
+            const int i = ty + 32 * ia, j = tx + 32 * ib;
+            a[ia][ib] = (i < m && j < m) ? v[(size_t)i * m + j] : (i == j ? 1.0 : 0.0);       // identity padding
+        }
+    if (threadIdx.x == 0) bad = 0;
+    for (int k = 0; k < m; ++k) {
+        const int buf = k & 1, ka = k >> 5, kt = k & 31;
+        if (tx == kt) {
+#pragma unroll
+            for (int ia = 0; ia < kSpdE; ++ia)
+#pragma unroll
+                for (int ib = 0; ib < kSpdE; ++ib)
+                    if (ib == ka) colb[buf][ty + 32 * ia] = a[ia][ib];
+        }
+        if (ty == kt) {
+#pragma unroll
+            for (int ia = 0; ia < kSpdE; ++ia)
+#pragma unroll
+                for (int ib = 0; ib < kSpdE; ++ib)
+                    if (ia == ka) rowb[buf][tx + 32 * ib] = a[ia][ib];
+        }
+        __syncthreads();
+        const double pv = rowb[buf][k];
+        if (threadIdx.x == 0 && !(pv > 0.0)) bad = 1;          // not positive definite (or NaN)
+        const double inv = 1.0 / pv;
+        double cv[kSpdE], rv[kSpdE];
+#pragma unroll
+        for (int q = 0; q < kSpdE; ++q) {
+            cv[q] = colb[buf][ty + 32 * q];
+            rv[q] = rowb[buf][tx + 32 * q] * inv;
+        }
+#pragma unroll
+        for (int ia = 0; ia < kSpdE; ++ia) {
+            const int i = ty + 32 * ia;
+#pragma unroll
+            for (int ib = 0; ib < kSpdE; ++ib) {
+                const int j = tx + 32 * ib;
+                double x;
+                if (i == k) x = (j == k) ? inv : rv[ib];
+                else if (j == k) x = -cv[ia] * inv;
+                else x = fma(-cv[ia], rv[ib], a[ia][ib]);
+                a[ia][ib] = x;
+            }
+        }
+        // no second barrier: the next pivot publishes into the other buffer
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && bad) atomicOr(status + blockIdx.x, flag);
+    double* x = X + (size_t)blockIdx.x * m * m;
+#pragma unroll
+    for (int ia = 0; ia < kSpdE; ++ia)
+#pragma unroll
+        for (int ib = 0; ib < kSpdE; ++ib) {
+            const int i = ty + 32 * ia, j = tx + 32 * ib;
+            if (i < m && j < m) x[(size_t)i * m + j] = a[ia][ib];
+        }
+}
+
+static int launch_binv(const double* V, double* X, int m, int n, int* status, size_t inv_smem, cudaStream_t st) {
+    if (m <= 32 * kSpdE) {
+        binv_spd_kernel<<<n, 1024, 0, st>>>(V, X, m, status, HS_STATUS_SINGULAR_YW);
+        return check_launch("binv_spd_kernel");
+    }
+    binv_kernel<<<n, 256, inv_smem, st>>>(V, X, m, status, HS_STATUS_SINGULAR_YW);
+    return check_launch("binv_kernel");
+}
+
 __global__ void transpose_stack_kernel(const double* __restrict__ R, int m, int p, double* __restrict__ Grev, double* __restrict__ Vf,
                                        double* __restrict__ Vb) {
     // Grev[w] = [Gamma(p); ...; Gamma(1)] (p m x m), Gamma(l) = R(l)^T;  Vf = Vb = Gamma(0)
@@ -224,11 +309,9 @@ int launch_lwr_generic(const K4Params& P, cudaStream_t st) {
             if ((rc = bgemm(g, nw, st))) return rc;
         }
         // inverses
-        binv_kernel<<<nw, 256, inv_smem, st>>>(Vb, Xb, m, P.status, HS_STATUS_SINGULAR_YW);
-        if ((rc = check_launch("binv_kernel"))) return rc;
+        if ((rc = launch_binv(Vb, Xb, m, nw, P.status, inv_smem, st))) return rc;
         if (!last) {
-            binv_kernel<<<nw, 256, inv_smem, st>>>(Vf, Xf, m, P.status, HS_STATUS_SINGULAR_YW);
-            if ((rc = check_launch("binv_kernel"))) return rc;
+            if ((rc = launch_binv(Vf, Xf, m, nw, P.status, inv_smem, st))) return rc;
         }
         {   // Kf = D * Xb
             GemmArgs g{D, Xb, Kf, (long long)mm, (long long)mm, (long long)mm, m, m, m, m, m, m, 0, 0, 1.0, 0.0};

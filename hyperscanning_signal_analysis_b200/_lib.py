@@ -40,6 +40,7 @@ SIGNATURES = {
     "hs_transfer_set_kernel": (c_int, [c_int]),
     "hs_transfer_dtf_f64": (c_int, [c_dp, c_dp, c_int, c_dbl, c_int, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "hs_spectra_f64": (c_int, [c_dp, c_dp, c_int, c_int, c_int, c_dp, c_dp]),
+    "hs_gpdc_f64": (c_int, [c_dp, c_dp, c_int, c_int, c_int, c_dp, c_dp]),
     "hs_partial_coherence_f64": (c_int, [c_dp, c_int, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "hs_mvar_ffdtf_ws_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
     "hs_mvar_ffdtf_f64": (c_int, [c_dp, c_dp, c_i64, c_int, c_int, c_int, c_int, c_dp, c_int, c_dbl, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),

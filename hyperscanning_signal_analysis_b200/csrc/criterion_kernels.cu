@@ -60,9 +60,42 @@ __global__ void argmin_kernel(const double* __restrict__ crit, const int n_win, 
     popt[w] = best + 1;                            // model_order_range starts at 1 (mtmvar.py:573)
 }
 
+// Generalised partial directed coherence (reference gen_partial_directed_coherence, src/mtmvar.py:449-468):
+//   gpdc[i][j][f] = (|A_ij(f)| / sigma_i) / sqrt(sum_k |A_kj(f)|^2 / sigma_k^2),  sigma_k^2 = V_kk;  0 where the denominator is 0.
+// One thread per (window, target j, bin f): bins are the fastest index, so the column walks are coalesced.
+__global__ void __launch_bounds__(256) gpdc_kernel(const double2* __restrict__ Af, const double* __restrict__ V, const int m, const int F,
+                                                   double* __restrict__ out) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y, w = blockIdx.z;
+    if (f >= F) return;
+    const size_t base = (size_t)w * m * m * F;
+    const double* Vw = V + (size_t)w * m * m;
+    double den = 0.0;
+    for (int k = 0; k < m; ++k) {
+        const double2 a = Af[base + ((size_t)k * m + j) * F + f];
+        const double mag = hypot(a.x, a.y);                   // np.abs
+        den += (mag * mag) / Vw[(size_t)k * m + k];
+    }
+    den = sqrt(den);
+    for (int i = 0; i < m; ++i) {
+        const double2 a = Af[base + ((size_t)i * m + j) * F + f];
+        const double num = hypot(a.x, a.y) / sqrt(Vw[(size_t)i * m + i]);
+        out[base + ((size_t)i * m + j) * F + f] = (den != 0.0) ? num / den : 0.0;
+    }
+}
+
 }  // namespace hs
 
 using namespace hs;
+
+extern "C" int hs_gpdc_f64(const void* d_Af, const double* d_V, int n_win, int m, int F, double* d_gpdc, void* stream) {
+    if (n_win <= 0) return HS_OK;
+    if (!d_Af || !d_V || !d_gpdc) return set_error(HS_ERR_INVALID, "hs_gpdc_f64: null pointer");
+    if (m < 1 || F < 1 || n_win > 65535 || m > 65535) return set_error(HS_ERR_INVALID, "hs_gpdc_f64: bad sizes");
+    dim3 grid((F + 255) / 256, m, n_win);
+    gpdc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double2*>(d_Af), d_V, m, F, d_gpdc);
+    return check_launch("gpdc_kernel");
+}
 
 extern "C" int hs_mvar_criterion_f64(const double* d_Vall, int n_win, int P, int m, int n_samples, int crit_type, double* d_crit,
                                      double* d_logdet, int32_t* d_popt, void* stream) {

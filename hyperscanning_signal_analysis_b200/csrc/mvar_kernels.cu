@@ -1480,6 +1480,25 @@ __global__ void __launch_bounds__(256) pcoh_kernel(const double2* __restrict__ S
     const int w = active ? q / F : 0, f = active ? q - w * F : 0;
     const size_t sF = (size_t)F;
     const double2* Sw = S + (size_t)w * m * m * sF + f;
+    // Diagonal pre-scaling S' = D S D with D_ii = 2^-round(log2 sqrt|S_ii|): the partial coherence is invariant under it (every minor
+    // picks up the same factors in numerator and denominator), powers of two make it exact, and det S' stays representable where
+    // det S of unscaled data (volts: |S_ii| ~ 1e-12, m = 38) would underflow.
+    int ex_r[T], ex_c[T];
+#pragma unroll
+    for (int a = 0; a < T; ++a) {
+        const int i = g.tr + 8 * a, j = g.tc + 8 * a;
+        ex_r[a] = ex_c[a] = 0;
+        if (active && i < m) {
+            const double2 d = Sw[((size_t)i * m + i) * sF];
+            const double mag = hypot(d.x, d.y);
+            if (mag > 0.0 && mag < 1e300) ex_r[a] = -(ilogb(mag) / 2);
+        }
+        if (active && j < m) {
+            const double2 d = Sw[((size_t)j * m + j) * sF];
+            const double mag = hypot(d.x, d.y);
+            if (mag > 0.0 && mag < 1e300) ex_c[a] = -(ilogb(mag) / 2);
+        }
+    }
     double ar[T][T], ai[T][T];
 #pragma unroll
     for (int a = 0; a < T; ++a)
@@ -1487,7 +1506,11 @@ __global__ void __launch_bounds__(256) pcoh_kernel(const double2* __restrict__ S
         for (int b = 0; b < T; ++b) {
             const int i = g.tr + 8 * a, j = g.tc + 8 * b;
             double2 v = make_double2((i == j) ? 1.0 : 0.0, 0.0);
-            if (active && i < m && j < m) v = Sw[((size_t)i * m + j) * sF];
+            if (active && i < m && j < m) {
+                v = Sw[((size_t)i * m + j) * sF];
+                v.x = scalbn(v.x, ex_r[a] + ex_c[b]);
+                v.y = scalbn(v.y, ex_r[a] + ex_c[b]);
+            }
             ar[a][b] = v.x;
             ai[a][b] = v.y;
         }

@@ -23,7 +23,7 @@ from . import _lib
 __all__ = [
     "count_corr", "ar_coeff", "mvar_transfer_function", "multivariate_spectra", "dtf_multivariate",
     "full_freq_dtf", "mvar_criterion", "gen_partial_directed_coherence", "partial_coherence", "direct_dtf",
-    "batched_partial_coherence", "batched_mvar_criterion", "batched_lagcov", "batched_ar_coeff", "batched_transfer", "windowed_ffdtf", "FfdtfPlan",
+    "batched_partial_coherence", "batched_gpdc", "batched_mvar_criterion", "batched_lagcov", "batched_ar_coeff", "batched_transfer", "windowed_ffdtf", "FfdtfPlan",
 ]
 
 
@@ -377,13 +377,19 @@ def gen_partial_directed_coherence(signals, freqs, fs, max_model_order=20, optim
         print('Using provided model order: p = ', str(optimal_model_order))
     A, V, _ = _fit(signals, optimal_model_order)
     res = batched_transfer(A, freqs, fs, want=("Af",))
-    Af = res["Af"][0]
-    s2 = torch.diagonal(V[0])
-    absA = Af.abs()
-    denom = torch.sqrt(torch.sum(absA ** 2 / s2[:, None, None], dim=0))
-    num = absA / torch.sqrt(s2)[:, None, None]
-    g = torch.where(denom[None] != 0, num / denom[None], torch.zeros_like(num))
-    return g.cpu().numpy()
+    return batched_gpdc(res["Af"], V)[0].cpu().numpy()
+
+
+def batched_gpdc(Af, V):
+    """GPDC of every window: Af (n_win, m, m, F) complex128 and V (n_win, m, m) on the device -> (n_win, m, m, F) float64."""
+    torch = _torch()
+    lib = _lib.load()
+    Af = Af.contiguous()
+    V = V.contiguous()
+    n_win, m, _, F = Af.shape
+    out = torch.empty((n_win, m, m, F), dtype=torch.float64, device="cuda")
+    _lib.check(lib.hs_gpdc_f64(Af.data_ptr(), V.data_ptr(), n_win, m, F, out.data_ptr(), _stream()), "hs_gpdc_f64")
+    return out
 
 
 def batched_partial_coherence(S, ffdtf=None, want_kappa=True):

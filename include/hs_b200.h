@@ -115,6 +115,10 @@ int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double 
 /* S(f) = H(f) V H(f)^T with a plain transpose, src/mtmvar.py:197-199.  d_S (n_win, m, m, F) complex128. */
 int hs_spectra_f64(const void* d_H, const double* d_V, int n_win, int m, int F, void* d_S, void* stream);
 
+/* Generalised partial directed coherence from A(f) and diag(V).  Replaces the double loop of gen_partial_directed_coherence,
+ * src/mtmvar.py:449-468.  d_Af (n_win, m, m, F) complex128 (hs_transfer_dtf_f64's d_Af), d_V (n_win, m, m), d_gpdc (n_win, m, m, F).  */
+int hs_gpdc_f64(const void* d_Af, const double* d_V, int n_win, int m, int F, double* d_gpdc, void* stream);
+
 /* Partial coherence of a spectral matrix and the direct DTF.
  * Replaces partial_coherence (src/mtmvar.py:287-338: determinant of every minor of S(f)) by one pivoted complex
  * inverse per bin (minor_ij = (-1)^(i+j) det S (S^-1)_ji), and the product of direct_dtf (:379-383).

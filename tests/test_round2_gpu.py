@@ -223,3 +223,19 @@ def test_both_transfer_kernels_against_reference(mv, which):
     finally:
         lib.hs_transfer_set_kernel(0)
     assert lib.hs_transfer_set_kernel(7) != 0 and lib.hs_transfer_set_kernel(-1) != 0
+
+
+def test_partial_coherence_is_scale_invariant(mv):
+    """Unscaled data (volts): det S underflows (|S_ii| ~ 1e-12, m = 38) unless S is pre-scaled by its diagonal; kappa must not change."""
+    g = golden("mvar_pcoh.npz")
+    S = g["w0_S"]
+    k1 = mv.partial_coherence(S)
+    assert relerr(k1, g["w0_kappa"]) < TOL_MODEL
+    for scale in (1e-12, 1e+9):
+        ks = mv.partial_coherence(S * scale)
+        assert np.isfinite(ks).all()
+        assert relerr(ks, k1) < 1e-12, scale
+    # channel-wise scaling (different units per channel) leaves kappa unchanged as well
+    d = np.logspace(-8, 6, S.shape[0])
+    kd = mv.partial_coherence(S * d[:, None, None] * d[None, :, None])
+    assert relerr(kd, k1) < 1e-9

@@ -215,7 +215,15 @@ __device__ __forceinline__ void mv2(const double* __restrict__ Pm, const double 
     }
 }
 
-template <int D>
+// barrier of the 256 compute threads: the whole CTA in the two-kernel path, a named barrier in the fused kernel (whose CTA has a
+// ninth warp that only does the look-back)
+template <bool NAMED>
+__device__ __forceinline__ void tile_sync() {
+    if (NAMED) asm volatile("bar.sync 1, 256;" ::: "memory");
+    else __syncthreads();
+}
+
+template <int D, bool NAMED = false>
 __device__ __forceinline__ void tile_stage_and_local(const IirPass& P, const IirCoef& c, double* sm, const int s, const long long tile,
                                                      double (&z)[D]) {
     const double* base = P.in + (long long)s * P.in_sig_stride;
@@ -240,7 +248,7 @@ __device__ __forceinline__ void tile_stage_and_local(const IirPass& P, const Iir
             sm[(idx & (kTilePer - 1)) * kTileLd + (idx >> kTilePerLog2)] = (u < P.L) ? sweep_read(P, base, dc, u) : 0.0;
         }
     }
-    __syncthreads();
+    tile_sync<NAMED>();
 #pragma unroll
     for (int k = 0; k < D; ++k) z[k] = 0.0;
 #pragma unroll 8
@@ -368,60 +376,27 @@ __device__ __forceinline__ int ld_flag(const int* p) {
 }
 __device__ __forceinline__ void st_flag(int* p, const int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
+constexpr int kFusedThreads = kTileThreads + 32;      // 8 compute warps + the look-back warp
+
 template <int D>
-__global__ void __launch_bounds__(kTileThreads, 3) iir_tile_fused_kernel(const IirPass P, const IirCoef c, const IirCoef ct, const double* __restrict__ ppow,
-                                                                       const IirLookback S) {
+__global__ void __launch_bounds__(kFusedThreads, 3) iir_tile_fused_kernel(const IirPass P, const IirCoef c, const IirCoef ct, const double* __restrict__ ppow,
+                                                                        const IirLookback S) {
     extern __shared__ double tile_sm[];
     __shared__ double red[kTileThreads / 32][2];
     __shared__ double wtot[kTileThreads / 32][2];
     __shared__ double e_sh[2], sin_sh[2];
-    __shared__ unsigned tk_sh;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // Tile id = linear CTA index: CTAs are dispatched in index order, so every predecessor of a running CTA is running or done
-    // (the assumption cub::DeviceScan's decoupled look-back makes); HS_EXPERIMENT builds can switch to an atomic ticket.
-    unsigned tk = blockIdx.x;
-#ifdef HS_EXPERIMENT
-    if (S.ticket) {
-        if (threadIdx.x == 0) tk_sh = atomicAdd(S.ticket, 1u);
-        __syncthreads();
-        tk = tk_sh;
-    }
-#endif
+    // (the assumption cub::DeviceScan's decoupled look-back makes).
+    const unsigned tk = blockIdx.x;
     const long long n_tiles = P.n_chunks;
     const int s = (int)(tk / n_tiles);
     const long long tile = tk - (long long)s * n_tiles;
-    double z[D];
-    tile_stage_and_local<D>(P, c, tile_sm, s, tile, z);
-    // ---- aggregate of the tile: e = sum_t P^(255-t) z_t (fixed-order block reduction)
-    {
-        double w[D];
-        mv2<D>(ppow + (size_t)(kTileThreads - 1 - threadIdx.x) * 4, z, w);
-#pragma unroll
-        for (int k = 0; k < D; ++k) {
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) w[k] += __shfl_xor_sync(0xffffffffu, w[k], off);
-            if (lane == 0) red[warp][k] = w[k];
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < D) {
-        double acc = 0.0;
-        for (int q = 0; q < kTileThreads / 32; ++q) acc += red[q][threadIdx.x];
-        e_sh[threadIdx.x] = acc;
-    }
-    __syncthreads();
-    // ---- look-back (warp 0): publish the aggregate, combine the predecessors' records, publish the inclusive state
-    if (warp == 0) {
-        const long long rec0 = (long long)s * n_tiles;
-        const int f_agg = 2 * S.sweep + 1, f_incl = 2 * S.sweep + 2;
-        double e[D];
-#pragma unroll
-        for (int q = 0; q < D; ++q) e[q] = e_sh[q];
-        if (lane == 0) {
-#pragma unroll
-            for (int q = 0; q < D; ++q) S.agg[(rec0 + tile) * 2 + q] = e[q];
-            st_flag(S.flags + rec0 + tile, f_agg);
-        }
+    const long long rec0 = (long long)s * n_tiles;
+    const int f_agg = 2 * S.sweep + 1, f_incl = 2 * S.sweep + 2;
+    if (warp == kTileThreads / 32) {
+        // ---- look-back warp: the start state of this tile from the predecessors' records.  It needs nothing of this tile, so it
+        //      runs WHILE the compute warps stage and scan their samples: its two or three L2 round trips are off the critical path.
         const double* base = P.in + (long long)s * P.in_sig_stride;
         const double dc = P.mean ? P.mean[s] : 0.0;
         double acc[D], Pw[D][D];
@@ -505,15 +480,46 @@ __global__ void __launch_bounds__(kTileThreads, 3) iir_tile_fused_kernel(const I
         }
         if (lane == 0) {
 #pragma unroll
+            for (int i = 0; i < D; ++i) sin_sh[i] = acc[i];
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(kFusedThreads) : "memory");      // rendezvous: e_sh (compute warps) and sin_sh are both in place
+        if (lane == 0) {
+#pragma unroll
             for (int i = 0; i < D; ++i) {
-                double v = e[i];
+                double v = e_sh[i];
 #pragma unroll
                 for (int q = 0; q < D; ++q) v = fma(ct.pw[0][i * D + q], acc[q], v);
                 S.incl[(rec0 + tile) * 2 + i] = v;
-                sin_sh[i] = acc[i];
             }
             st_flag(S.flags + rec0 + tile, f_incl);
         }
+        return;
+    }
+    double z[D];
+    tile_stage_and_local<D, true>(P, c, tile_sm, s, tile, z);
+    // ---- aggregate of the tile: e = sum_t P^(255-t) z_t (fixed-order block reduction), published at once
+    {
+        double w[D];
+        mv2<D>(ppow + (size_t)(kTileThreads - 1 - threadIdx.x) * 4, z, w);
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) w[k] += __shfl_xor_sync(0xffffffffu, w[k], off);
+            if (lane == 0) red[warp][k] = w[k];
+        }
+    }
+    tile_sync<true>();
+    if (threadIdx.x == 0) {
+        double e[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            double acc = 0.0;
+            for (int q = 0; q < kTileThreads / 32; ++q) acc += red[q][k];
+            e[k] = acc;
+            e_sh[k] = acc;
+            S.agg[(rec0 + tile) * 2 + k] = acc;
+        }
+        st_flag(S.flags + rec0 + tile, f_agg);
     }
     // ---- inclusive scan of the zero-state pieces inside the warp:  v_l = sum_{l' <= l} P^(l-l') z_l'
     double v[D];
@@ -534,7 +540,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) iir_tile_fused_kernel(const I
 #pragma unroll
         for (int q = 0; q < D; ++q) wtot[warp][q] = v[q];
     }
-    __syncthreads();
+    asm volatile("bar.sync 2, %0;" ::"n"(kFusedThreads) : "memory");      // rendezvous with the look-back warp: sin_sh is known
     double W[D];
 #pragma unroll
     for (int q = 0; q < D; ++q) W[q] = 0.0;
@@ -559,7 +565,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) iir_tile_fused_kernel(const I
         double* slot = tile_sm + i * kTileLd + threadIdx.x;
         *slot = df2t_step<D>(c, st, *slot);
     }
-    __syncthreads();
+    tile_sync<true>();
     double* ob = P.out + (long long)s * P.out_sig_stride;
     const long long u0 = tile * kTile;
     const long long n = P.L - 2 * (long long)P.e;
@@ -759,7 +765,7 @@ static int run_sweep_fused(IirPass P, const IirCoef& c, const IirCoef& ct, const
     }
     const long long ctas = n_tiles * P.n_sig;
     if (ctas > 0x7fffffffLL) return set_error(HS_ERR_UNSUPPORTED, "filtfilt: too many tiles");
-    iir_tile_fused_kernel<D><<<(unsigned)ctas, kTileThreads, smem, st>>>(P, c, ct, d_ppow, S);
+    iir_tile_fused_kernel<D><<<(unsigned)ctas, kFusedThreads, smem, st>>>(P, c, ct, d_ppow, S);
     return check_launch("iir_tile_fused_kernel");
 }
 

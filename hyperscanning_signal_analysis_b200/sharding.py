@@ -98,16 +98,17 @@ def window_layout(counts: Sequence[int]) -> List[int]:
     return out
 
 
-def chunk_ranges(n_units: int, units_per_chunk: int, ramp: bool = False) -> List[Tuple[int, int]]:
+def chunk_ranges(n_units: int, units_per_chunk: int, ramp: bool = False, ramp_down: bool = True) -> List[Tuple[int, int]]:
     """Contiguous [lo, hi) unit ranges of at most ``units_per_chunk`` units (the push granularity).  ``ramp``: the first chunks
-    hold 1, 2, 4 units, so the exchange starts after a fraction of a full chunk's compute time, and the last ones 2 and 1, so
-    little is left to push when the compute ends."""
+    hold 1, 2, 4 units, so the exchange starts after a fraction of a full chunk's compute time, and (``ramp_down``) the last ones
+    2 and 1, so little is left to push when the compute ends -- useful while the step is compute-bound (N <= 4); when the NVLink
+    receive side bounds it (N = 8) the pushes queue up anyway and small last chunks only add copies."""
     if units_per_chunk < 1:
         raise ValueError("units_per_chunk must be >= 1")
     sizes: List[int] = []
     left = n_units
     if ramp:
-        tail = [s for s in (2, 1) if s < units_per_chunk]
+        tail = [s for s in (2, 1) if s < units_per_chunk] if ramp_down else []
         k = 0
         while left > sum(tail) and (1 << k) < units_per_chunk:
             size = min(1 << k, left - sum(tail))
@@ -271,7 +272,7 @@ class ShardedFfdtf:
         self.win_local = self.n_units * self.n_win
         self.total_windows = self.win_local * self.world
         self.rank_offset = self.rank * self.win_local
-        self.chunks = chunk_ranges(self.n_units, units_per_chunk, ramp=ramp and self.world > 1)
+        self.chunks = chunk_ranges(self.n_units, units_per_chunk, ramp=ramp and self.world > 1, ramp_down=self.world <= 4)
         self.push = push
         self.push_ctas = int(push_ctas)
         dev = torch.device("cuda", torch.cuda.current_device())

@@ -70,6 +70,7 @@ assert sharding.window_layout([5, 4, 0, 3]) == [0, 5, 9, 9]
 assert sharding.chunk_ranges(24, 5) == [(0, 5), (5, 10), (10, 15), (15, 20), (20, 24)]
 assert sharding.chunk_ranges(0, 5) == []
 assert sharding.chunk_ranges(24, 5, ramp=True) == [(0, 1), (1, 3), (3, 7), (7, 12), (12, 17), (17, 21), (21, 23), (23, 24)]
+assert sharding.chunk_ranges(24, 5, ramp=True, ramp_down=False) == [(0, 1), (1, 3), (3, 7), (7, 12), (12, 17), (17, 22), (22, 24)]
 for n_u in range(0, 40):
     for upc in (1, 2, 5):
         cr = sharding.chunk_ranges(n_u, upc, ramp=True)

@@ -31,6 +31,7 @@ struct GemmArgs {
     double alpha, beta;
 };
 
+#ifdef HS_EXPERIMENT      // round 1's register-tile DFMA version (HS_BGEMM_DFMA=1): 10.5 ms of GEMMs per cfg5 fit
 __global__ void __launch_bounds__(64) bgemm_kernel(const GemmArgs g) {
     __shared__ double pa[kPadMax * kPadMax], pb[kPadMax * kPadMax];
     const Group grp = make_group();
@@ -74,10 +75,90 @@ __global__ void __launch_bounds__(64) bgemm_kernel(const GemmArgs g) {
     }
 }
 
+#endif
+
+// The same batched GEMM on the FP64 tensor pipe: 64 x 64 block of C per CTA, 4 warps (2 x 2, 32 x 32 outputs = 16 accumulator tiles
+// each), K in chunks of 32 staged as As[i][k] / Bs[j][k] (row stride 36 = 4 mod 16 doubles: conflict-free m8n8k4 fragments for both).
+constexpr int kGB = 64, kGK = 32, kGLd = kGK + 4;
+__device__ __forceinline__ void dmma884_b(double& c0, double& c1, const double a, const double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(128) bgemm_mma_kernel(const GemmArgs g) {
+    __shared__ double As[kGB * kGLd], Bs[kGB * kGLd];
+    const int tiles_n = (g.N + kGB - 1) / kGB;
+    const int i0 = (blockIdx.x / tiles_n) * kGB, j0 = (blockIdx.x % tiles_n) * kGB;
+    const double* A = g.A + (long long)blockIdx.y * g.sA;
+    const double* B = g.B + (long long)blockIdx.y * g.sB;
+    double* C = g.C + (long long)blockIdx.y * g.sC;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g4 = lane >> 2, t4 = lane & 3;
+    const int wr = warp >> 1, wc = warp & 1;
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    for (int k0 = 0; k0 < g.K; k0 += kGK) {
+        __syncthreads();
+        // stage along the contiguous direction of each operand
+        for (int e = threadIdx.x; e < kGB * kGK; e += 128) {
+            int i, k;
+            if (g.tA) { i = e % kGB; k = e / kGB; } else { k = e % kGK; i = e / kGK; }
+            double v = 0.0;
+            if (i0 + i < g.M && k0 + k < g.K) v = g.tA ? A[(long long)(k0 + k) * g.lda + i0 + i] : A[(long long)(i0 + i) * g.lda + k0 + k];
+            As[i * kGLd + k] = v;
+        }
+        for (int e = threadIdx.x; e < kGB * kGK; e += 128) {
+            int j, k;
+            if (g.tB) { k = e % kGK; j = e / kGK; } else { j = e % kGB; k = e / kGB; }
+            double v = 0.0;
+            if (j0 + j < g.N && k0 + k < g.K) v = g.tB ? B[(long long)(j0 + j) * g.ldb + k0 + k] : B[(long long)(k0 + k) * g.ldb + j0 + j];
+            Bs[j * kGLd + k] = v;
+        }
+        __syncthreads();
+        const double* pa = As + (32 * wr + g4) * kGLd + t4;
+        const double* pb = Bs + (32 * wc + g4) * kGLd + t4;
+#pragma unroll
+        for (int kk = 0; kk < kGK; kk += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                a[q] = pa[q * 8 * kGLd + kk];
+                b[q] = pb[q * 8 * kGLd + kk];
+            }
+#pragma unroll
+            for (int qa = 0; qa < 4; ++qa)
+#pragma unroll
+                for (int qb = 0; qb < 4; ++qb) dmma884_b(acc[qa][qb][0], acc[qa][qb][1], a[qa], b[qb]);
+        }
+    }
+#pragma unroll
+    for (int qa = 0; qa < 4; ++qa) {
+        const int i = i0 + 32 * wr + 8 * qa + g4;
+#pragma unroll
+        for (int qb = 0; qb < 4; ++qb) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = j0 + 32 * wc + 8 * qb + 2 * t4 + h;
+                if (i < g.M && j < g.N) {
+                    double* c = C + (long long)i * g.ldc + j;
+                    *c = (g.beta == 0.0 ? 0.0 : g.beta * *c) + g.alpha * acc[qa][qb][h];
+                }
+            }
+        }
+    }
+}
+
 static int bgemm(const GemmArgs& g, int batch, cudaStream_t st) {
-    dim3 grid(((g.M + kPadMax - 1) / kPadMax) * ((g.N + kPadMax - 1) / kPadMax), batch);
-    bgemm_kernel<<<grid, 64, 0, st>>>(g);
-    return check_launch("bgemm_kernel");
+#ifdef HS_EXPERIMENT
+    if (exp_env_int("HS_BGEMM_DFMA", 0) == 1) {
+        dim3 grid0(((g.M + kPadMax - 1) / kPadMax) * ((g.N + kPadMax - 1) / kPadMax), batch);
+        bgemm_kernel<<<grid0, 64, 0, st>>>(g);
+        return check_launch("bgemm_kernel");
+    }
+#endif
+    dim3 grid(((g.M + kGB - 1) / kGB) * ((g.N + kGB - 1) / kGB), batch);
+    bgemm_mma_kernel<<<grid, 128, 0, st>>>(g);
+    return check_launch("bgemm_mma_kernel");
 }
 
 // ------------------------------------------------------------------------------------------------

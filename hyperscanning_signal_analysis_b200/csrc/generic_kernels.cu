@@ -647,55 +647,59 @@ __global__ void __launch_bounds__(kBlkThreads, 1) transfer_blocked_kernel(const 
                 C0[e] = v;
             }
             __syncthreads();
-            // ---- 2. pivot rows by partial pivoting inside the panel
-            for (int q = 0; q < kNB; ++q) {
-                double best = -1.0;
-                int bi = 1 << 20;
-                for (int i = tid; i < Mp; i += kBlkThreads) {
-                    if (!used[i]) {
-                        const double2 v = Cp[i * kNB + q];
-                        const double mag = fma(v.x, v.x, v.y * v.y);
-                        if (mag > best || bi == (1 << 20)) { if (mag > best) best = mag; bi = i; }
-                    }
-                }
+            // ---- 2. pivot rows by partial pivoting inside the panel: thread i < Mp keeps row i of the panel in registers, the first
+            //         ceil(Mp / 32) warps run the 16 elimination steps with two named barriers each (the other warps wait below)
+            const int n_pw = (Mp + 31) >> 5;                      // panel warps
+            if (warp < n_pw) {
+                const bool has_row = tid < Mp;
+                double2 r[kNB];
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const double ob = __shfl_xor_sync(0xffffffffu, best, off);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-                }
-                if (lane == 0) { s_red[warp] = best; s_idx[warp] = bi; }
-                __syncthreads();
-                if (tid == 0) {
-                    double bb = s_red[0];
-                    int ii = s_idx[0];
-                    for (int u = 1; u < kBlkThreads / 32; ++u)
-                        if (s_red[u] > bb || (s_red[u] == bb && s_idx[u] < ii)) { bb = s_red[u]; ii = s_idx[u]; }
-                    piv[q] = ii;
-                    used[ii] = 1;
-                    rowmap[ii] = k0 + q;
-                    colmap[k0 + q] = ii;
-                    if (!(bb > 0.0)) atomicOr(&P.status[w], 1);
-                }
-                __syncthreads();
-                const int r = piv[q];
-                const double2 pv = Cp[r * kNB + q];
-                const double d = 1.0 / fma(pv.x, pv.x, pv.y * pv.y);
-                const double2 iv = make_double2(pv.x * d, -pv.y * d);
-                const int rem = kNB - 1 - q;
-                for (int e = tid; e < Mp * rem; e += kBlkThreads) {
-                    const int i = e / rem, c = q + 1 + e % rem;
-                    if (!used[i]) {
-                        const double2 l = cmul_g(Cp[i * kNB + q], iv);
-                        const double2 rv = Cp[r * kNB + c];
-                        double2 x = Cp[i * kNB + c];
-                        x.x = fma(-l.x, rv.x, fma(l.y, rv.y, x.x));
-                        x.y = fma(-l.x, rv.y, fma(-l.y, rv.x, x.y));
-                        Cp[i * kNB + c] = x;
+                for (int c = 0; c < kNB; ++c) r[c] = has_row ? Cp[tid * kNB + c] : make_double2(0.0, 0.0);
+                bool mine_used = has_row ? (used[tid] != 0) : true;
+#pragma unroll
+                for (int q = 0; q < kNB; ++q) {
+                    double best = mine_used ? -1.0 : fma(r[q].x, r[q].x, r[q].y * r[q].y);
+                    int bi = mine_used ? (1 << 20) : tid;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
                     }
+                    if (lane == 0) { s_red[warp] = best; s_idx[warp] = bi; }
+                    asm volatile("bar.sync 3, %0;" ::"r"(n_pw * 32) : "memory");
+                    double bb = s_red[0];
+                    int pr = s_idx[0];
+                    for (int u = 1; u < n_pw; ++u)
+                        if (s_red[u] > bb || (s_red[u] == bb && s_idx[u] < pr)) { bb = s_red[u]; pr = s_idx[u]; }
+                    if (tid == pr) {                               // the pivot row publishes itself
+                        mine_used = true;
+                        used[tid] = 1;
+                        piv[q] = tid;
+                        rowmap[tid] = k0 + q;
+                        colmap[k0 + q] = tid;
+                        if (!(bb > 0.0)) atomicOr(&P.status[w], 1);
+#pragma unroll
+                        for (int c = 0; c < kNB; ++c) Dm[c] = r[c];      // row buffer (D is rebuilt in step 3)
+                    }
+                    asm volatile("bar.sync 3, %0;" ::"r"(n_pw * 32) : "memory");
+                    if (!mine_used) {
+                        const double2 pv = Dm[q];
+                        const double d = 1.0 / fma(pv.x, pv.x, pv.y * pv.y);
+                        const double2 l = cmul_g(r[q], make_double2(pv.x * d, -pv.y * d));
+#pragma unroll
+                        for (int c = 0; c < kNB; ++c) {
+                            if (c > q) {
+                                const double2 rv = Dm[c];
+                                r[c].x = fma(-l.x, rv.x, fma(l.y, rv.y, r[c].x));
+                                r[c].y = fma(-l.x, rv.y, fma(-l.y, rv.x, r[c].y));
+                            }
+                        }
+                    }
+                    // the next step's publication of Dm happens after the next first barrier: everyone has read this one by then
                 }
-                __syncthreads();
             }
+            __syncthreads();
             // ---- 3. D = C0[R, :] and P = D^-1 (Gauss-Jordan in pivot order, one thread per entry of the 16 x 16 block)
             if (tid < kNB * kNB) {
                 const int t = tid / kNB, sidx = tid % kNB;

@@ -216,6 +216,57 @@ __device__ __forceinline__ void mma_inverse4_adj(const MmaCtx& x, const int K0, 
     __syncwarp();
 }
 
+// ---- P = D^-1 by cofactors with the Re / Im parts of every entry split over the two half-warps: lane (s, i, j) produces the
+//      component s (0: Re, 1: Im) of P[i][j].  A scalar FP64 instruction costs the warp a turn of the FP64 pipe no matter how many
+//      lanes are live, and while the other warps of the sub-partition stream 16-cycle DMMAs such a turn comes up about once per
+//      DMMA: what the inverse costs is its NUMBER of FP64 instructions, and mirrored lanes are wasted turns.  With
+//      (q1, q2) = (Re q, -Im q) in the Re lanes and (Im q, Re q) in the Im lanes, the lane's component of a complex product p q
+//      is p.re q1 + p.im q2: 2 instructions instead of 4, the same code in both halves.  Operands that come from the panel are
+//      loaded in that form straight from the Re / Im planes; computed operands take their other component from lane ^ 16.
+//      det = (D adj)[j][j] = sum_i D[j][i] adj[i][j]: one term per lane, summed over i by two butterfly rounds.
+//      31 FP64 instructions + 14 shuffles per block step against 84 + 16 for mma_inverse4_adj.
+__device__ __forceinline__ void mma_inverse4_split(const MmaCtx& x, const int K0, const int buf) {
+    MmaGroupSmem* gs = x.gs;
+    const int s = x.lane >> 4, i = (x.lane >> 2) & 3, j = x.lane & 3;
+    const double* Dr = gs->u.p.Craw[buf][0] + K0 * 4;
+    const double* Di = gs->u.p.Craw[buf][1] + K0 * 4;
+    const double* D1 = s ? Di : Dr;                    // plane of the component this lane produces
+    const double* D2 = s ? Dr : Di;
+    const int neg = s ? 0 : (int)0x80000000;           // the Re lanes take -Im of a second operand
+    const int r0 = (0 >= j) ? 1 : 0, r1 = (1 >= j) ? 2 : 1, r2 = (2 >= j) ? 3 : 2;
+    const int c0 = (0 >= i) ? 1 : 0, c1 = (1 >= i) ? 2 : 1, c2 = (2 >= i) ? 3 : 2;
+#define HS_LD1(R, C, vr, vi) const double vr = Dr[(R) * 4 + (C)], vi = Di[(R) * 4 + (C)]                              /* first operand: (re, im) */
+#define HS_LD2(R, C, v1, v2) const double v1 = D1[(R) * 4 + (C)], v2 = flip_sign(D2[(R) * 4 + (C)], neg)             /* second operand form */
+    HS_LD1(r1, c0, a10r, a10i); HS_LD1(r1, c1, a11r, a11i); HS_LD1(r1, c2, a12r, a12i);
+    HS_LD2(r2, c0, a20p, a20q); HS_LD2(r2, c1, a21p, a21q); HS_LD2(r2, c2, a22p, a22q);
+    HS_LD1(r0, c0, a00r, a00i); HS_LD1(r0, c1, a01r, a01i); HS_LD1(r0, c2, a02r, a02i);
+    HS_LD1(j, i, djr, dji);
+#undef HS_LD1
+#undef HS_LD2
+    // own component of the 2 x 2 minors of rows r1, r2
+    const double m0 = fma(-a12i, a21q, fma(-a12r, a21p, fma(a11i, a22q, a11r * a22p)));
+    const double m1 = fma(-a12i, a20q, fma(-a12r, a20p, fma(a10i, a22q, a10r * a22p)));
+    const double m2 = fma(-a11i, a20q, fma(-a11r, a20p, fma(a10i, a21q, a10r * a21p)));
+    const double m0o = flip_sign(__shfl_xor_sync(0xffffffffu, m0, 16), neg);
+    const double m1o = flip_sign(__shfl_xor_sync(0xffffffffu, m1, 16), neg);
+    const double m2o = flip_sign(__shfl_xor_sync(0xffffffffu, m2, 16), neg);
+    // own component of the signed cofactor  a00 m0 - a01 m1 + a02 m2
+    double cf = fma(a02i, m2o, fma(a02r, m2, fma(-a01i, m1o, fma(-a01r, m1, fma(a00i, m0o, a00r * m0)))));
+    cf = flip_sign(cf, ((i + j) & 1) ? (int)0x80000000 : 0);
+    const double cfo = __shfl_xor_sync(0xffffffffu, cf, 16);           // the other component of the own cofactor
+    // det = sum_i D[j][i] adj[i][j]
+    double dt = fma(dji, flip_sign(cfo, neg), djr * cf);
+    dt += __shfl_xor_sync(0xffffffffu, dt, 4);
+    dt += __shfl_xor_sync(0xffffffffu, dt, 8);
+    const double dto = __shfl_xor_sync(0xffffffffu, dt, 16);
+    const double y = rcp_newton2(fma(dt, dt, dto * dto));
+    // P = adj conj(det) / |det|^2:  Re = cr dr + ci di,  Im = ci dr - cr di
+    const double u1 = s ? dto : dt, u2 = s ? -dt : dto;
+    const double pv = fma(cfo, u2, cf * u1) * y;
+    reinterpret_cast<double*>(gs->u.p.P[x.part])[2 * (x.lane & 15) + s] = pv;
+    __syncwarp();
+}
+
 // ---- the two block steps of tile t (h = 0, 1): hand-over of the panel, 4 x 4 inverse, L panel by DMMA, rank-4 update
 template <int T, int t, int ADJ>
 __device__ __forceinline__ void mma_tile_steps(double (&c)[T][T][2], const int m, const MmaCtx& x) {
@@ -235,7 +286,8 @@ __device__ __forceinline__ void mma_tile_steps(double (&c)[T][T][2], const int m
             __syncwarp();
         } else
 #endif
-        if (ADJ == 2) mma_inverse4_adj<false>(x, K0, h, det);
+        if (ADJ == 3) mma_inverse4_split(x, K0, h);
+        else if (ADJ == 2) mma_inverse4_adj<false>(x, K0, h, det);
         else if (ADJ == 1) mma_inverse4_adj<true>(x, K0, h, det);
         else mma_inverse4(x, K0, h);
         // B fragments of -P with Re/Im interleaved by output column:  n = 2j -> Re, n = 2j+1 -> Im
@@ -1103,15 +1155,15 @@ template <int T, int NG>
 int launch_mma_t(const K5Params& P, int sm_count, cudaStream_t stream) {
     const size_t smem = MmaSmem<T>::total(P.p, NG, P.seg_len);
     if (smem > 227 * 1024) return set_error(HS_ERR_UNSUPPORTED, "transfer_mma: model order %d needs %zu B shared memory", P.p, smem);
-    // 4 x 4 pivot-block inverse: 1 (default) cofactors; 2 cofactors with the division by det deferred to the U panel (measured
+    // 4 x 4 pivot-block inverse: 3 (default) cofactors with Re / Im split over the half-warps; 1 cofactors, every lane a whole entry; 2 cofactors with the division by det deferred to the U panel (measured
     // slower: 5.49 vs 5.24 ms, the 20 extra FP64 instructions per lane and step sit in front of the 50 update DMMAs); 0 in-place elimination
 #ifdef HS_EXPERIMENT
-    static const int adj = exp_env_int("HS_K5_ADJ", 1);
+    static const int adj = exp_env_int("HS_K5_ADJ", 3);
     constexpr bool kMain = (T == 5 && NG == 6);
-    auto kern = (adj == 2 && kMain) ? transfer_mma_kernel<T, NG, kMain ? 2 : 0>
+    auto kern = (adj == 3) ? transfer_mma_kernel<T, NG, 3> : (adj == 2 && kMain) ? transfer_mma_kernel<T, NG, kMain ? 2 : 0>
               : (adj == 1 && kMain) ? transfer_mma_kernel<T, NG, kMain ? 1 : 0> : transfer_mma_kernel<T, NG, 0>;
 #else
-    auto kern = transfer_mma_kernel<T, NG, 1>;       // cofactor pivot-block inverse for every tile count
+    auto kern = transfer_mma_kernel<T, NG, 3>;       // cofactor pivot-block inverse, Re / Im split over the half-warps, for every tile count
 #endif
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "transfer_mma: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));

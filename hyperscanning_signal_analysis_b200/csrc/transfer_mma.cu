@@ -651,8 +651,9 @@ struct MmaSmem {
     static __host__ __device__ size_t coef_bytes(int p) { return (size_t)planes(p) * kPlaneD * sizeof(double); }
     static __host__ __device__ size_t probe_bytes(int p) { return (size_t)kMP * p * sizeof(double2); }
     static __host__ __device__ size_t z_bytes(int p, int seg_len) { return (size_t)seg_len * 2 * planes(p) * sizeof(double2); }    // z of the unit's bins
+    static __host__ __device__ size_t chk_bytes() { return (size_t)2 * kMP * sizeof(double2); }      // [part][row] {expected pad-column value, limit}
     static __host__ __device__ size_t total(int p, int ng, int seg_len) {
-        return coef_bytes(p) + probe_bytes(p) + z_bytes(p, seg_len) + (size_t)ng * sizeof(MmaGroupSmem) + 64;
+        return coef_bytes(p) + probe_bytes(p) + z_bytes(p, seg_len) + chk_bytes() + (size_t)ng * sizeof(MmaGroupSmem) + 64;
     }
 };
 
@@ -663,7 +664,9 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
     double* coef = reinterpret_cast<double*>(smem_raw);
     double2* probe = reinterpret_cast<double2*>(smem_raw + MmaSmem<T>::coef_bytes(p));
     double2* zs = reinterpret_cast<double2*>(smem_raw + MmaSmem<T>::coef_bytes(p) + MmaSmem<T>::probe_bytes(p));      // [bin of the unit][2 * n_planes]
-    MmaGroupSmem* groups = reinterpret_cast<MmaGroupSmem*>(smem_raw + MmaSmem<T>::coef_bytes(p) + MmaSmem<T>::probe_bytes(p) + MmaSmem<T>::z_bytes(p, P.seg_len));
+    double2* chk = reinterpret_cast<double2*>(smem_raw + MmaSmem<T>::coef_bytes(p) + MmaSmem<T>::probe_bytes(p) + MmaSmem<T>::z_bytes(p, P.seg_len));
+    MmaGroupSmem* groups = reinterpret_cast<MmaGroupSmem*>(smem_raw + MmaSmem<T>::coef_bytes(p) + MmaSmem<T>::probe_bytes(p) + MmaSmem<T>::z_bytes(p, P.seg_len) +
+                                                           MmaSmem<T>::chk_bytes());
     const int warp = threadIdx.x >> 5;
     MmaCtx x;
     x.lane = threadIdx.x & 31;
@@ -687,6 +690,16 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
 
     // zero the coefficient planes once: padding rows / columns / the odd lag stay zero for every unit
     for (int e = threadIdx.x; e < n_planes * kPlaneD; e += NG * 64) coef[e] = 0.0;
+    // A-posteriori check through the padding: when the last column of the padded matrix is free (m < 8 T) it carries v = A(f) u
+    // through the elimination like a right-hand side ([[A, v], [0, 1]]^-1 = [[H, -H v], [0, 1]]), so H v comes out of the update DMMAs
+    // and only has to be compared with u: -u if the pad column lies inside the last eliminated block (8 T - 4 < m), else +u.
+    const bool padchk = (m < 8 * T);
+    if (threadIdx.x < 2 * kMP) {
+        const int part = threadIdx.x / kMP, row = threadIdx.x - part * kMP;
+        const double2 u = probe_u2(row);
+        const double want = part ? u.y : u.x;
+        chk[threadIdx.x] = make_double2((8 * T - 4 < m) ? -want : want, 0.5 * P.verify_tol2 * fma(u.x, u.x, u.y * u.y));
+    }
 
     // Balanced static partition: CTA c owns the matrices q = w * F + f in [c * per_cta, (c + 1) * per_cta): every CTA gets the
     // same count (+-1 round of NG), and a window's coefficients are loaded once per PIECE (= the part of a window inside the range).
@@ -783,10 +796,33 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
             if (n_planes == 4) mma_assemble<T, 4>(c, coef, zg, n_planes, x);
             else mma_assemble<T, 0>(c, coef, zg, n_planes, x);
             if (P.Af) mma_store_generic<T, false>(c, P, w, f, x);
+            if (padchk && x.t4 == 3) {       // v into the pad column (entry [1] of the last column tile in the lanes t4 == 3)
+#pragma unroll
+                for (int ta = 0; ta < T; ++ta) {
+                    const int row = 8 * ta + x.g4;
+                    if (row < m) {
+                        const double2 vv = gs->vfull[row];
+                        c[ta][T - 1][1] = x.part ? vv.y : vv.x;
+                    }
+                }
+            }
             // ---- blocked Gauss-Jordan on the tensor pipe
             mma_gauss_jordan<T, ADJ>(c, m, x);
             // ---- a-posteriori check:  S v == u ?   (v = A(f) u)
-            {
+            if (padchk) {
+                if (x.t4 == 3) {
+                    bool bad = false;
+#pragma unroll
+                    for (int ta = 0; ta < T; ++ta) {
+                        const int row = 8 * ta + x.g4;
+                        const double2 ck = chk[x.part * kMP + row];
+                        const double e = c[ta][T - 1][1] - ck.x;
+                        if (row < m && !(e * e <= ck.y)) bad = true;      // also catches NaN / Inf
+                    }
+                    if (bad) gs->flag = 1;
+                }
+                mma_group_sync(x);             // the partner is past its last fragment loads: the panel buffers may become the exchange buffer
+            } else {
                 double sr[T], si[T];
 #pragma unroll
                 for (int ta = 0; ta < T; ++ta) sr[ta] = si[ta] = 0.0;
@@ -810,16 +846,16 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
                         gs->wpart[x.part][1][8 * ta + x.g4] = si[ta];
                     }
                 }
-            }
-            mma_group_sync(x);
-            if (l64 < m) {
-                // S v = (Sr vr - Si vi) + i (Sr vi + Si vr)
-                const double wr = gs->wpart[0][0][l64] - gs->wpart[1][1][l64];
-                const double wi = gs->wpart[0][1][l64] + gs->wpart[1][0][l64];
-                const double2 u = probe_u2(l64);
-                const double er = wr - u.x, ei = wi - u.y;
-                const double err = fma(er, er, ei * ei), ref = fma(u.x, u.x, u.y * u.y);
-                if (!(err <= P.verify_tol2 * ref)) gs->flag = 1;      // also catches NaN / Inf
+                mma_group_sync(x);
+                if (l64 < m) {
+                    // S v = (Sr vr - Si vi) + i (Sr vi + Si vr)
+                    const double wr = gs->wpart[0][0][l64] - gs->wpart[1][1][l64];
+                    const double wi = gs->wpart[0][1][l64] + gs->wpart[1][0][l64];
+                    const double2 u = probe_u2(l64);
+                    const double er = wr - u.x, ei = wi - u.y;
+                    const double err = fma(er, er, ei * ei), ref = fma(u.x, u.x, u.y * u.y);
+                    if (!(err <= P.verify_tol2 * ref)) gs->flag = 1;      // also catches NaN / Inf
+                }
             }
             // ---- Re/Im exchange for |H|^2 (the panel buffers are free: the barrier above is past every fragment load).
             //      The Re warp finishes the entries in even columns, the Im warp those in odd columns.

@@ -65,6 +65,7 @@ struct __align__(16) MmaGroupSmem {
             double Craw[2][2][kMP * 4];    // [buf][part][row*4 + k]   panel columns  (A-fragment order)
             double Rraw[2][2][4 * kUS];    // [buf][part][k*52 + col]  panel rows with the identity pattern (B-fragment order)
             double2 P[2][16];              // [warp][i*4 + j]          D^-1, private copy per warp
+            float Df[2][32];               // [warp][part*16 + i*4 + j] pivot block rounded to FP32 (seed of mma_inverse4_newton)
         } p;
         double2 X[25][32];                 // Re/Im exchange of the epilogue (after the elimination)
     } u;
@@ -267,6 +268,91 @@ __device__ __forceinline__ void mma_inverse4_split(const MmaCtx& x, const int K0
     __syncwarp();
 }
 
+// ---- P = D^-1 with (almost) no scalar FP64 work: FP32 seed + two Newton-Schulz steps on the tensor pipe.
+//      While the other warps of the sub-partition stream DMMAs a dependent scalar FP64 instruction waits for the FP64 pipe
+//      about as long as two DMMAs take (ncu: math_pipe_throttle on every DFMA of the cofactor chain, 44 % of a block step), so the
+//      31-instruction chain of mma_inverse4_split is the most expensive part of the step.  Here the chain runs on the FP32 pipe,
+//      which nothing else uses: the pivot block is rounded to FP32 (one entry component per lane), inverted by the same split
+//      cofactor formula in FP32 (X0: relative error ~1e-7 cond(D)), and refined in FP64 by
+//          R = I - X D,   X <- X + R X          (error -> error^2 per step; two steps: ~1e-7^4 cond^4, i.e. rounding level)
+//      as four DMMAs per step: X lives in the accumulator layout with Re / Im interleaved by column, which IS the pair of A
+//      fragments (Re X, Im X) of the next product, exactly like the L panel below; the B-side copy of X (lane (g4, t4) <- X[t4][g4 >> 1])
+//      is one shuffle.  Rows 4..7 of the 8-row fragments mirror rows 0..3.  A block too ill-conditioned for the FP32 seed
+//      (cond(D) >~ 1e5) does not converge; the a-posteriori check then flags the matrix for the pivoted kernel like any other failure.
+//      Returns pk = P[g4 & 3][t4] (the lane's own accumulator) and pv = P[t4][g4 >> 1] without a round trip through shared memory.
+//      Measured (599 cfg2 windows): 4.85 ms against 4.81 ms for mma_inverse4_split, 36 instead of 49 matrices flagged -- inside the block
+//      steps the FP64 pipe is already ~85 % busy (ncu), so trading 31 scalar instructions for 8 DMMAs buys nothing; selected by
+//      HS_K5_ADJ=4 in HS_EXPERIMENT builds.
+__device__ __forceinline__ float flip_sign_f(const float v, const int mask) { return __int_as_float(__float_as_int(v) ^ mask); }
+
+__device__ __forceinline__ void mma_inverse4_newton(const MmaCtx& x, const int K0, const int buf, double2& pv, double2& pk) {
+    MmaGroupSmem* gs = x.gs;
+    const int s = x.lane >> 4, i = (x.lane >> 2) & 3, j = x.lane & 3;
+    const double* Dr = gs->u.p.Craw[buf][0] + K0 * 4;
+    const double* Di = gs->u.p.Craw[buf][1] + K0 * 4;
+    float* Df = gs->u.p.Df[x.part];
+    Df[x.lane] = (float)(s ? Di : Dr)[x.lane & 15];
+    // D as the B operand of X D:  column n = 2 j' + c of the product is the Re (c = 0) / Im (c = 1) part of complex column j'
+    const bool odd = x.g4 & 1;
+    const int bsel = x.t4 * 4 + (x.g4 >> 1);
+    const double dBr = Dr[bsel], dBi = Di[bsel];
+    const double dB1 = odd ? dBi : dBr;                                                     // multiplies Re X
+    const double dB2 = flip_sign(odd ? dBr : dBi, odd ? 0 : (int)0x80000000);                // multiplies Im X
+    __syncwarp();
+    // ---- FP32 seed: component s of adj(D)[i][j] / det D, same scheme as mma_inverse4_split
+    float x0;
+    {
+        const float* F1 = Df + 16 * s;
+        const float* F2 = Df + 16 * (s ^ 1);
+        const int neg = s ? 0 : (int)0x80000000;
+        const int r0 = (0 >= j) ? 1 : 0, r1 = (1 >= j) ? 2 : 1, r2 = (2 >= j) ? 3 : 2;
+        const int c0 = (0 >= i) ? 1 : 0, c1 = (1 >= i) ? 2 : 1, c2 = (2 >= i) ? 3 : 2;
+#define HS_LD1(R, C, vr, vi) const float vr = Df[(R) * 4 + (C)], vi = Df[16 + (R) * 4 + (C)]
+#define HS_LD2(R, C, v1, v2) const float v1 = F1[(R) * 4 + (C)], v2 = flip_sign_f(F2[(R) * 4 + (C)], neg)
+        HS_LD1(r1, c0, a10r, a10i); HS_LD1(r1, c1, a11r, a11i); HS_LD1(r1, c2, a12r, a12i);
+        HS_LD2(r2, c0, a20p, a20q); HS_LD2(r2, c1, a21p, a21q); HS_LD2(r2, c2, a22p, a22q);
+        HS_LD1(r0, c0, a00r, a00i); HS_LD1(r0, c1, a01r, a01i); HS_LD1(r0, c2, a02r, a02i);
+        HS_LD1(j, i, djr, dji);
+#undef HS_LD1
+#undef HS_LD2
+        const float m0 = fmaf(-a12i, a21q, fmaf(-a12r, a21p, fmaf(a11i, a22q, a11r * a22p)));
+        const float m1 = fmaf(-a12i, a20q, fmaf(-a12r, a20p, fmaf(a10i, a22q, a10r * a22p)));
+        const float m2 = fmaf(-a11i, a20q, fmaf(-a11r, a20p, fmaf(a10i, a21q, a10r * a21p)));
+        const float m0o = flip_sign_f(__shfl_xor_sync(0xffffffffu, m0, 16), neg);
+        const float m1o = flip_sign_f(__shfl_xor_sync(0xffffffffu, m1, 16), neg);
+        const float m2o = flip_sign_f(__shfl_xor_sync(0xffffffffu, m2, 16), neg);
+        float cf = fmaf(a02i, m2o, fmaf(a02r, m2, fmaf(-a01i, m1o, fmaf(-a01r, m1, fmaf(a00i, m0o, a00r * m0)))));
+        cf = flip_sign_f(cf, ((i + j) & 1) ? (int)0x80000000 : 0);
+        const float cfo = __shfl_xor_sync(0xffffffffu, cf, 16);
+        float dt = fmaf(dji, flip_sign_f(cfo, neg), djr * cf);
+        dt += __shfl_xor_sync(0xffffffffu, dt, 4);
+        dt += __shfl_xor_sync(0xffffffffu, dt, 8);
+        const float dto = __shfl_xor_sync(0xffffffffu, dt, 16);
+        const float y = __fdividef(1.0f, fmaf(dt, dt, dto * dto));
+        const float u1 = s ? dto : dt, u2 = s ? -dt : dto;
+        x0 = fmaf(cfo, u2, cf * u1) * y;
+    }
+    // ---- X0 into the accumulator layout: lane (g4, t4) <- X0[g4 & 3][t4] (Re, Im), from the lanes (s, i, j) = (0 | 1, g4 & 3, t4)
+    const int own = (x.g4 & 3) * 4 + x.t4;
+    double ar = (double)__shfl_sync(0xffffffffu, x0, own);
+    double ai = (double)__shfl_sync(0xffffffffu, x0, own + 16);
+    const double idr = ((x.g4 & 3) == x.t4) ? 1.0 : 0.0;
+    double b1, b2;      // X as the B operand of R X
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const double tr = __shfl_sync(0xffffffffu, ar, bsel), ti = __shfl_sync(0xffffffffu, ai, bsel);
+        b1 = odd ? ti : tr;
+        b2 = flip_sign(odd ? tr : ti, odd ? 0 : (int)0x80000000);
+        double q0 = idr, q1 = 0.0;
+        dmma884(q0, q1, ar, -dB1);              // R = I - X D
+        dmma884(q0, q1, ai, -dB2);
+        dmma884(ar, ai, q0, b1);                // X += R X
+        dmma884(ar, ai, q1, b2);
+    }
+    pk = make_double2(ar, ai);
+    pv = make_double2(__shfl_sync(0xffffffffu, ar, bsel), __shfl_sync(0xffffffffu, ai, bsel));
+}
+
 // ---- the two block steps of tile t (h = 0, 1): hand-over of the panel, 4 x 4 inverse, L panel by DMMA, rank-4 update
 template <int T, int t, int ADJ>
 __device__ __forceinline__ void mma_tile_steps(double (&c)[T][T][2], const int m, const MmaCtx& x) {
@@ -286,15 +372,21 @@ __device__ __forceinline__ void mma_tile_steps(double (&c)[T][T][2], const int m
             __syncwarp();
         } else
 #endif
-        if (ADJ == 3) mma_inverse4_split(x, K0, h);
-        else if (ADJ == 2) mma_inverse4_adj<false>(x, K0, h, det);
-        else if (ADJ == 1) mma_inverse4_adj<true>(x, K0, h, det);
-        else mma_inverse4(x, K0, h);
+        double2 pv, pk;       // P[t4][g4 >> 1] (B fragments of -P) and P[g4 & 3][t4] (rows K of the panel)
+        if (ADJ == 4) {
+            mma_inverse4_newton(x, K0, h, pv, pk);
+        } else {
+            if (ADJ == 3) mma_inverse4_split(x, K0, h);
+            else if (ADJ == 2) mma_inverse4_adj<false>(x, K0, h, det);
+            else if (ADJ == 1) mma_inverse4_adj<true>(x, K0, h, det);
+            else mma_inverse4(x, K0, h);
+            pv = gs->u.p.P[x.part][x.t4 * 4 + (x.g4 >> 1)];
+            pk = gs->u.p.P[x.part][(x.g4 & 3) * 4 + x.t4];
+        }
         // B fragments of -P with Re/Im interleaved by output column:  n = 2j -> Re, n = 2j+1 -> Im
         double a0[T], a1[T];
         pipe_lock(x);
         {
-            const double2 pv = gs->u.p.P[x.part][x.t4 * 4 + (x.g4 >> 1)];
             const bool odd = x.g4 & 1;
             const double bB1 = odd ? -pv.y : -pv.x;        // multiplies Re C
             const double bB2 = odd ? -pv.x : pv.y;         // multiplies Im C
@@ -309,7 +401,6 @@ __device__ __forceinline__ void mma_tile_steps(double (&c)[T][T][2], const int m
                 a1[ta] = l1;
             }
             // rows K of the panel: -L = P - I
-            const double2 pk = gs->u.p.P[x.part][(x.g4 & 3) * 4 + x.t4];
             if ((x.g4 >> 2) == h) {
                 const bool dg = (x.g4 & 3) == x.t4;
                 a0[t] = pk.x - (dg ? (ADJ == 2 ? det.x : 1.0) : 0.0);
@@ -1191,12 +1282,13 @@ template <int T, int NG>
 int launch_mma_t(const K5Params& P, int sm_count, cudaStream_t stream) {
     const size_t smem = MmaSmem<T>::total(P.p, NG, P.seg_len);
     if (smem > 227 * 1024) return set_error(HS_ERR_UNSUPPORTED, "transfer_mma: model order %d needs %zu B shared memory", P.p, smem);
-    // 4 x 4 pivot-block inverse: 3 (default) cofactors with Re / Im split over the half-warps; 1 cofactors, every lane a whole entry; 2 cofactors with the division by det deferred to the U panel (measured
+    // 4 x 4 pivot-block inverse: 3 (default) cofactors with Re / Im split over the half-warps; 4 FP32 seed + Newton-Schulz on the tensor pipe
+    // (measured the same: 4.85 vs 4.81 ms -- 8 more DMMAs per block step, see mma_inverse4_newton); 1 cofactors, every lane a whole entry; 2 cofactors with the division by det deferred to the U panel (measured
     // slower: 5.49 vs 5.24 ms, the 20 extra FP64 instructions per lane and step sit in front of the 50 update DMMAs); 0 in-place elimination
 #ifdef HS_EXPERIMENT
     static const int adj = exp_env_int("HS_K5_ADJ", 3);
     constexpr bool kMain = (T == 5 && NG == 6);
-    auto kern = (adj == 3) ? transfer_mma_kernel<T, NG, 3> : (adj == 2 && kMain) ? transfer_mma_kernel<T, NG, kMain ? 2 : 0>
+    auto kern = (adj == 4) ? transfer_mma_kernel<T, NG, 4> : (adj == 3) ? transfer_mma_kernel<T, NG, 3> : (adj == 2 && kMain) ? transfer_mma_kernel<T, NG, kMain ? 2 : 0>
               : (adj == 1 && kMain) ? transfer_mma_kernel<T, NG, kMain ? 1 : 0> : transfer_mma_kernel<T, NG, 0>;
 #else
     auto kern = transfer_mma_kernel<T, NG, 3>;       // cofactor pivot-block inverse, Re / Im split over the half-warps, for every tile count

@@ -1350,7 +1350,285 @@ __global__ void __launch_bounds__(64, kK4PerSM) lwr1_kernel(const K4Params P) {
 }
 
 
-size_t lwr_ws_doubles(int grid, int m, int p) { return (size_t)grid * (4 * p + 2) * m * m; }
+// -------------------------------------------------------------------------------------
+// K4 on the FP64 tensor pipe (the one that runs): same recursion, same panels and barriers as lwr1_kernel, but every
+// product is mma.sync.m8n8k4.f64.  lwr1_kernel issues 1000 DFMAs + 400 LDS per thread and product and is bound by instruction
+// issue / fixed latencies with 2.5 warps per scheduler (0.19 of the FP64 peak on LWR's own flops); a DMMA does the work of 8
+// DFMAs per lane from two fragment loads, so a product is 130 DMMAs + 80 LDS per lane.
+//   * the 25 accumulator tiles of a 40 x 40 product are split 13 / 12 between the two warps of the window (tile order row-major:
+//     warp 0 rows 0, 1 and three tiles of row 2; warp 1 the rest): per k-step 3 A fragments + 5 B fragments for 13 DMMAs;
+//   * panels keep their roles (P0 / P1 / P2 rotate through A_j, Gamma, Delta, V^-1, Kf, Kb) with a row stride of 44 doubles
+//     (= 12 mod 16): a fragment is read along a row or along a column of the panel -- (ld g4 + t4) or (ld t4 + g4) mod 16 distinct over
+//     a half-warp -- so no transposed copies exist, as before;
+//   * accumulators live in the m8n8k4 layout (lane (g4, t4): row 8a + g4, columns 8b + 2 t4, +1) and go to / come from the
+//     global scratch row-major; the SPD inverses stay on the register-tile Gauss-Jordan (gj_inverse_static) and exchange
+//     V_f / V_b with the products through that scratch (different thread -> element maps, hence the barriers around them).
+// -------------------------------------------------------------------------------------
+constexpr int kK4Ld2 = kPadMax + 4;             // 44
+constexpr int kK4Panel2 = kPadMax * kK4Ld2;
+
+template <int W>
+struct K4Split {
+    static constexpr int first = W ? 13 : 0, count = W ? 12 : 13, row0 = W ? 2 : 0;
+};
+
+// acc (tiles of warp W) +=/-= sum_k L[i][k] Rt[k][j];  TRA: Pa holds L row-major (else k-major);  TRB: Pb holds Rt^T
+template <int W, bool SUB, bool TRA, bool TRB>
+__device__ __forceinline__ void k4_mma(double (&acc)[13][2], const double* __restrict__ Pa, const double* __restrict__ Pb, const int ksteps,
+                                       const int g4, const int t4) {
+    using S = K4Split<W>;
+    const double* pa = TRA ? Pa + g4 * kK4Ld2 + t4 : Pa + t4 * kK4Ld2 + g4;
+    const double* pb = TRB ? Pb + g4 * kK4Ld2 + t4 : Pb + t4 * kK4Ld2 + g4;
+#pragma unroll 2
+    for (int s = 0; s < ksteps; ++s) {
+        double av[3], bv[5];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) av[r] = TRA ? pa[8 * (S::row0 + r) * kK4Ld2] : pa[8 * (S::row0 + r)];
+#pragma unroll
+        for (int b = 0; b < 5; ++b) bv[b] = TRB ? pb[8 * b * kK4Ld2] : pb[8 * b];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) av[r] = SUB ? -av[r] : av[r];
+#pragma unroll
+        for (int n = 0; n < S::count; ++n) dmma884_k3(acc[n][0], acc[n][1], av[(S::first + n) / 5 - S::row0], bv[(S::first + n) % 5]);
+        pa += TRA ? 4 : 4 * kK4Ld2;
+        pb += TRB ? 4 : 4 * kK4Ld2;
+    }
+}
+
+template <int W, bool TRANS>      // acc <- src (row-major m x m, leading dimension ld; TRANS: acc[i][j] = src[j][i]), zero outside m x m
+__device__ __forceinline__ void k4_load(double (&acc)[13][2], const double* __restrict__ src, const int ld, const int m, const int g4, const int t4) {
+    using S = K4Split<W>;
+#pragma unroll
+    for (int n = 0; n < S::count; ++n) {
+        const int i = 8 * ((S::first + n) / 5) + g4, j = 8 * ((S::first + n) % 5) + 2 * t4;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) acc[n][c] = (i < m && j + c < m) ? (TRANS ? src[(size_t)(j + c) * ld + i] : src[(size_t)i * ld + j + c]) : 0.0;
+    }
+}
+
+template <int W>                  // bounded store to a packed m x m array (the outputs V, Vall)
+__device__ __forceinline__ void k4_store(double* __restrict__ dst, const int ld, const double (&acc)[13][2], const int m, const int g4, const int t4) {
+    using S = K4Split<W>;
+#pragma unroll
+    for (int n = 0; n < S::count; ++n) {
+        const int i = 8 * ((S::first + n) / 5) + g4, j = 8 * ((S::first + n) % 5) + 2 * t4;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+            if (i < m && j + c < m) dst[(size_t)i * ld + j + c] = acc[n][c];
+    }
+}
+
+// Scratch matrices and panels are 40 x 40 with zero padding (every producer writes whole tiles, the padding of an accumulator is
+// exactly zero), so they move as unconditional 16-byte accesses: LD = 40 for the global scratch, 44 for a shared-memory panel.
+template <int W, int LD>
+__device__ __forceinline__ void k4_load_pad(double (&acc)[13][2], const double* __restrict__ src, const int g4, const int t4) {
+    using S = K4Split<W>;
+#pragma unroll
+    for (int n = 0; n < S::count; ++n) {
+        const double2 v = *reinterpret_cast<const double2*>(src + (8 * ((S::first + n) / 5) + g4) * LD + 8 * ((S::first + n) % 5) + 2 * t4);
+        acc[n][0] = v.x;
+        acc[n][1] = v.y;
+    }
+}
+template <int W, int LD>
+__device__ __forceinline__ void k4_store_pad(double* __restrict__ dst, const double (&acc)[13][2], const int g4, const int t4) {
+    using S = K4Split<W>;
+#pragma unroll
+    for (int n = 0; n < S::count; ++n)
+        *reinterpret_cast<double2*>(dst + (8 * ((S::first + n) / 5) + g4) * LD + 8 * ((S::first + n) % 5) + 2 * t4) = make_double2(acc[n][0], acc[n][1]);
+}
+// A[w][i][j][k] = A_{k+1}[i][j]: the final coefficient matrices go straight to the output (lag fastest, stride p)
+template <int W>
+__device__ __forceinline__ void k4_store_lag(double* __restrict__ Aw, const int p, const int k, const double (&acc)[13][2], const int m, const int g4, const int t4) {
+    using S = K4Split<W>;
+#pragma unroll
+    for (int n = 0; n < S::count; ++n) {
+        const int i = 8 * ((S::first + n) / 5) + g4, j = 8 * ((S::first + n) % 5) + 2 * t4;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+            if (i < m && j + c < m) Aw[((size_t)i * m + j + c) * p + k] = acc[n][c];
+    }
+}
+
+constexpr int kK4Sd = kPadMax * kPadMax;        // doubles per scratch matrix
+
+// global -> panel without a detour through registers: cp.async (L2 only, so stores of other threads of the CTA made visible by a
+// barrier are seen), CH doubles per copy.  src rows are `row_len` doubles long and contiguous (row_len = 40: a scratch matrix;
+// row_len = m: a packed R(l) from K3), panel rows are kK4Ld2 apart.  Caller: k4_async_wait(); __syncthreads().
+template <int CH>
+__device__ __forceinline__ void k4_async_rows(double* __restrict__ panel, const double* __restrict__ src, const int row_len, const int n_rows,
+                                              const int l64) {
+    const int rc = row_len / CH;                 // copies per row
+    const int total = rc * n_rows;
+    int r = l64 / rc, c = l64 - r * rc;
+    const int dr = 64 / rc, dc = 64 - dr * rc;
+    const unsigned base = (unsigned)__cvta_generic_to_shared(panel);
+    for (int e = l64; e < total; e += 64) {
+        const unsigned dst = base + (unsigned)((r * kK4Ld2 + c * CH) * 8);
+        const double* sp = src + (size_t)e * CH;
+        if (CH == 2) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(sp) : "memory");
+        else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(sp) : "memory");
+        r += dr;
+        c += dc;
+        if (c >= rc) { c -= rc; ++r; }
+    }
+}
+__device__ __forceinline__ void k4_async_wait() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+
+// one warp's share of the recursion of the windows w = blockIdx.x, + gridDim.x, ...
+template <int T, int W>
+__device__ __forceinline__ void lwr2_body(const K4Params& P, double* P0, double* P1, double* P2, GJScratch* sh, const Group& g) {
+    const int lane = threadIdx.x & 31, g4 = lane >> 2, t4 = lane & 3;
+    const int m = P.m, p = P.p;
+    const size_t mm = (size_t)m * m;
+    const int ksteps = (m + 3) >> 2;
+    const bool r16 = ((m & 1) == 0) && ((reinterpret_cast<size_t>(P.R) & 15) == 0);       // rows of R(l) are whole 16-byte chunks
+    double* ws = P.ws + (size_t)blockIdx.x * (4 * p + 2) * kK4Sd;       // [par][A|B][p] padded matrices, Vf, Vb
+    auto stA = [&](int par, int j) { return ws + ((size_t)(par * 2 + 0) * p + j) * kK4Sd; };   // j = 0-based index of A_{j+1}
+    auto stB = [&](int par, int j) { return ws + ((size_t)(par * 2 + 1) * p + j) * kK4Sd; };
+    double* gVf = ws + (size_t)4 * p * kK4Sd;
+    double* gVb = gVf + kK4Sd;
+
+    for (int w = blockIdx.x; w < P.n_win; w += gridDim.x) {
+        const double* Rw = P.R + (size_t)w * (p + 1) * mm;
+        double* Aw = P.A + (size_t)w * mm * p;
+        double dummy[T][T];
+        double acc[13][2];
+        k4_load<W, true>(acc, Rw, m, m, g4, t4);                                       // Gamma(0) = R(0)^T
+        k4_store_pad<W, kPadMax>(gVf, acc, g4, t4);
+        k4_store_pad<W, kPadMax>(gVb, acc, g4, t4);
+        __syncthreads();
+        for (int kk = 0; kk < p; ++kk) {
+            const int cur = kk & 1, nxt = cur ^ 1;
+            const bool last = (kk == p - 1);
+            // ---- phase 1: Delta = Gamma(kk+1) - sum_j A_{j+1} Gamma(kk-j)
+            k4_load<W, true>(acc, Rw + (size_t)(kk + 1) * mm, m, m, g4, t4);
+            for (int j = 0; j < kk; ++j) {
+                __syncthreads();                                                        // the previous product is done with P0 / P1
+                k4_async_rows<2>(P0, stA(cur, j), kPadMax, m, g.l64);                  // A_{j+1}[i][q]
+                if (r16) k4_async_rows<2>(P1, Rw + (size_t)(kk - j) * mm, m, m, g.l64);      // R(l)[c][q] = Gamma(l)[q][c]
+                else k4_async_rows<1>(P1, Rw + (size_t)(kk - j) * mm, m, m, g.l64);
+                k4_async_wait();
+                __syncthreads();
+                k4_mma<W, true, true, true>(acc, P0, P1, ksteps, g4, t4);
+            }
+            __syncthreads();
+            k4_store_pad<W, kK4Ld2>(P2, acc, g4, t4);                                   // Delta, row-major
+            // ---- phases 2+3: Kf = Delta Vb^-1, Kb = Delta^T Vf^-1, residual covariances
+            {
+                double iv[T][T];
+                bool finite = true;
+                load_tile<T>(iv, gVb, kPadMax, m, g);
+#pragma unroll
+                for (int a = 0; a < T; ++a)
+#pragma unroll
+                    for (int b = 0; b < T; ++b) {
+                        const int i = g.tr + 8 * a, j = g.tc + 8 * b;
+                        if (!(i < m && j < m)) iv[a][b] = (i == j) ? 1.0 : 0.0;
+                    }
+                // residual covariances are symmetric positive definite: unpivoted elimination is stable
+                gj_inverse_static<T, false>(iv, dummy, m, g, sh);
+#pragma unroll
+                for (int a = 0; a < T; ++a)
+#pragma unroll
+                    for (int b = 0; b < T; ++b) {
+                        const int i = g.tr + 8 * a, j = g.tc + 8 * b;
+                        if (i < m && j < m) {
+                            P1[i * kK4Ld2 + j] = iv[a][b];
+                            finite = finite && (fabs(iv[a][b]) <= 1.79e308);
+                        }
+                    }
+                __syncthreads();
+#pragma unroll
+                for (int n = 0; n < 13; ++n) acc[n][0] = acc[n][1] = 0.0;
+                k4_mma<W, false, true, false>(acc, P2, P1, ksteps, g4, t4);             // Kf = sum_q Delta[i][q] Vbinv[q][j]
+                k4_store_pad<W, kK4Ld2>(P0, acc, g4, t4);                               // (phase 1 is done with P0)
+                if (last) k4_store_lag<W>(Aw, p, kk, acc, m, g4, t4);                   // A_p = Kf
+                else k4_store_pad<W, kPadMax>(stA(nxt, kk), acc, g4, t4);
+                if (!last) {
+                    load_tile<T>(iv, gVf, kPadMax, m, g);
+#pragma unroll
+                    for (int a = 0; a < T; ++a)
+#pragma unroll
+                        for (int b = 0; b < T; ++b) {
+                            const int i = g.tr + 8 * a, j = g.tc + 8 * b;
+                            if (!(i < m && j < m)) iv[a][b] = (i == j) ? 1.0 : 0.0;
+                        }
+                    gj_inverse_static<T, false>(iv, dummy, m, g, sh);
+                    __syncthreads();                                                     // every thread is done reading Vb^-1
+#pragma unroll
+                    for (int a = 0; a < T; ++a)
+#pragma unroll
+                        for (int b = 0; b < T; ++b) {
+                            const int i = g.tr + 8 * a, j = g.tc + 8 * b;
+                            if (i < m && j < m) {
+                                P1[i * kK4Ld2 + j] = iv[a][b];
+                                finite = finite && (fabs(iv[a][b]) <= 1.79e308);
+                            }
+                        }
+                    __syncthreads();
+#pragma unroll
+                    for (int n = 0; n < 13; ++n) acc[n][0] = acc[n][1] = 0.0;
+                    k4_mma<W, false, false, false>(acc, P2, P1, ksteps, g4, t4);        // Kb = sum_q Delta[q][i] Vfinv[q][j]
+                    k4_store_pad<W, kPadMax>(stB(nxt, kk), acc, g4, t4);
+                    __syncthreads();                                                     // every thread is done reading Vf^-1
+                    k4_store_pad<W, kK4Ld2>(P1, acc, g4, t4);
+                    k4_load_pad<W, kPadMax>(acc, gVb, g4, t4);
+                    __syncthreads();
+                    k4_mma<W, true, true, false>(acc, P1, P2, ksteps, g4, t4);          // Vb -= Kb Delta
+                    k4_store_pad<W, kPadMax>(gVb, acc, g4, t4);
+                } else {
+                    __syncthreads();
+                }
+                k4_load_pad<W, kPadMax>(acc, gVf, g4, t4);
+                k4_mma<W, true, true, true>(acc, P0, P2, ksteps, g4, t4);               // Vf -= Kf Delta^T   (P0 written before the barriers above)
+                k4_store_pad<W, kPadMax>(gVf, acc, g4, t4);
+                if (!finite) atomicOr(&P.status[w], 2);      // singular (or not positive definite) residual covariance
+                if (P.Vall) k4_store<W>(P.Vall + ((size_t)w * p + kk) * mm, m, acc, m, g4, t4);
+                if (last) k4_store<W>(P.V + (size_t)w * mm, m, acc, m, g4, t4);
+            }
+            // ---- phase 4: order update  A_j -= Kf B_{kk-1-j}  (and  B_j -= Kb A_{kk-1-j}  unless this is the last order)
+            for (int it = 0; it < (last ? kk : 2 * kk); ++it) {
+                const bool isA = it < kk;
+                const int j = isA ? it : it - kk;
+                const double* own = isA ? stA(cur, j) : stB(cur, j);
+                const double* other = isA ? stB(cur, kk - 1 - j) : stA(cur, kk - 1 - j);
+                __syncthreads();                                                         // P2 (Delta / previous operand) is free
+                k4_async_rows<2>(P2, other, kPadMax, m, g.l64);
+                k4_load_pad<W, kPadMax>(acc, own, g4, t4);
+                k4_async_wait();
+                __syncthreads();
+                if (isA) k4_mma<W, true, true, false>(acc, P0, P2, ksteps, g4, t4);
+                else k4_mma<W, true, true, false>(acc, P1, P2, ksteps, g4, t4);
+                if (last) k4_store_lag<W>(Aw, p, j, acc, m, g4, t4);                    // final A_{j+1}
+                else k4_store_pad<W, kPadMax>(isA ? stA(nxt, j) : stB(nxt, j), acc, g4, t4);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <int T>
+__global__ void __launch_bounds__(64, kK4PerSM) lwr2_kernel(const K4Params P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* P0 = reinterpret_cast<double*>(smem_raw);
+    double* P1 = P0 + kK4Panel2;
+    double* P2 = P1 + kK4Panel2;
+    GJScratch* sh = reinterpret_cast<GJScratch*>(P2 + kK4Panel2);
+    Group g = make_group();
+    g.gid = 0;
+    g.bar = 1;
+    for (int e = threadIdx.x; e < 3 * kK4Panel2; e += 64) P0[e] = 0.0;      // padding rows / columns stay zero for good
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) lwr2_body<T, 0>(P, P0, P1, P2, sh, g);
+    else lwr2_body<T, 1>(P, P0, P1, P2, sh, g);
+}
+
+
+size_t lwr_ws_doubles(int grid, int m, int p) {       // lwr2_kernel keeps its scratch matrices padded to 40 x 40 (m <= 40 on this path)
+    const size_t mm = (size_t)(m > kPadMax ? m : kPadMax) * (m > kPadMax ? m : kPadMax);
+    return (size_t)grid * (4 * p + 2) * mm;
+}
 int lwr_grid(int n_win) { const int slots = device_sm_count() * kK4PerSM; return n_win < slots ? n_win : slots; }
 
 int launch_lwr(const K4Params& P, int grid, cudaStream_t stream) {
@@ -1364,20 +1642,30 @@ int launch_lwr(const K4Params& P, int grid, cudaStream_t stream) {
         return check_launch("lwr_kernel");
     }
 #endif
-    const size_t smem = (size_t)3 * kK4Panel * sizeof(double) + sizeof(GJScratch);
-    cudaError_t e = cudaFuncSetAttribute(lwr1_kernel<kTileMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#ifdef HS_EXPERIMENT
+    if (exp_env_int("HS_K4_LEGACY", 0) == 2) {      // register-tiled DFMA products
+        const size_t smem1 = (size_t)3 * kK4Panel * sizeof(double) + sizeof(GJScratch);
+        cudaError_t e1 = cudaFuncSetAttribute(lwr1_kernel<kTileMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+        if (e1 != cudaSuccess) return set_error(HS_ERR_CUDA, "lwr: %s", cudaGetErrorString(e1));
+        cudaFuncSetAttribute(lwr1_kernel<kTileMax>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        lwr1_kernel<kTileMax><<<grid, 64, smem1, stream>>>(P);
+        return check_launch("lwr1_kernel");
+    }
+#endif
+    const size_t smem = (size_t)3 * kK4Panel2 * sizeof(double) + sizeof(GJScratch);
+    cudaError_t e = cudaFuncSetAttribute(lwr2_kernel<kTileMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "lwr: %s", cudaGetErrorString(e));
-    // five 41 KB CTAs per SM need the large shared-memory carve-out (the default split may leave room for two only)
-    cudaFuncSetAttribute(lwr1_kernel<kTileMax>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    // five 43 KB CTAs per SM need the large shared-memory carve-out (the default split may leave room for two only)
+    cudaFuncSetAttribute(lwr2_kernel<kTileMax>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 #ifdef HS_EXPERIMENT
     if (exp_env_int("HS_DEBUG", 0)) {
         int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lwr1_kernel<kTileMax>, 64, smem);
-        fprintf(stderr, "[hs] lwr1_kernel: %d CTAs/SM, smem %zu, grid %d\n", nb, smem, grid);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lwr2_kernel<kTileMax>, 64, smem);
+        fprintf(stderr, "[hs] lwr2_kernel: %d CTAs/SM, smem %zu, grid %d\n", nb, smem, grid);
     }
 #endif
-    lwr1_kernel<kTileMax><<<grid, 64, smem, stream>>>(P);
-    return check_launch("lwr1_kernel");
+    lwr2_kernel<kTileMax><<<grid, 64, smem, stream>>>(P);
+    return check_launch("lwr2_kernel");
 }
 
 

@@ -16,7 +16,7 @@ for k in "$@"; do
   case $k in
     k3)   cap k3_lagcov_tma 'lagcov_mma_kernel'     python tools/prof_mvar.py 599 1 ;;
     k3g)  cap k3_gemm_cfg5  'lagcov_gemm_kernel'    python tools/prof_cfg5.py ;;
-    k4)   cap k4_lwr1       'lwr1_kernel'           python tools/prof_mvar.py 599 1 ;;
+    k4)   cap k4_lwr2       'lwr2_kernel'           python tools/prof_mvar.py 599 1 ;;
     k5)   cap k5_mma        'transfer_mma_kernel'   python tools/prof_mvar.py 599 1 ;;
     k5w)  cap k5_ws         'transfer_ws_kernel'    python tools/prof_mvar.py 599 1 ;;
     fin)  cap fin           'dtf_finalize_kernel'   python tools/prof_mvar.py 599 1 ;;

@@ -1475,10 +1475,121 @@ __device__ __forceinline__ void k4_async_rows(double* __restrict__ panel, const 
 }
 __device__ __forceinline__ void k4_async_wait() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 
+// ---- SPD inverse of a residual covariance by ONE warp: the 40 x 40 matrix lives in the warp's registers in the m8n8k4 accumulator
+//      layout (50 doubles per lane), in-place Gauss-Jordan with 1 x 1 pivots and no pivoting (residual covariances are symmetric
+//      positive definite, so this is backward stable -- same arithmetic as gj_inverse_static, which it replaces).  Per step the
+//      owners publish the pivot row and column to shared memory (double buffered by step parity: one __syncwarp per step, no CTA
+//      barrier), every lane takes its 5 multipliers and 10 row entries back and does its 50 DFMAs.  The two inverses of an order
+//      (V_b^-1 by warp 0, V_f^-1 by warp 1) run side by side.  Scratch: the start of the panel that receives the result.
+//      Measured and dropped: block Gauss-Jordan with 4 x 4 pivot blocks on the tensor pipe (explicit D^-1 by cofactors, L = C D^-1 and the
+//      rank-4 update as DMMAs, like transfer_mma.cu): 0.63 instead of 0.70 ms for the whole stage, but the explicit inverse of a pivot block puts
+//      cond(D) into the backward error -- A came out 30 x further from the reference (6e-9 .. 1e-8 instead of 3e-10 on the cfg2
+//      goldens, 8e-7 on the cond 1.7e9 stress fixture).  K5's complex A(f) blocks are well conditioned and verified; these are not.
+struct K4InvBuf {
+    double row[2][kPadMax];                     // [step parity][j]  pivot row
+    double col[2][kPadMax];                     // [step parity][i]  pivot column
+};
+static_assert(sizeof(K4InvBuf) <= kK4Panel2 * sizeof(double), "inverse scratch must fit the destination panel");
+
+template <int b>      // the pivots k = 8 b .. 8 b + 7
+__device__ __forceinline__ void k4_gj_steps(double (&c)[5][5][2], const int m, K4InvBuf* __restrict__ ib, int& step, const int g4, const int t4) {
+#pragma unroll 1
+    for (int kc = 0; kc < 8; ++kc) {
+        const int k = 8 * b + kc;
+        if (k >= m) break;
+        const int par = step & 1;
+        ++step;
+        const bool odd = kc & 1;
+        const bool own_row = (g4 == kc), own_col = (t4 == (kc >> 1));
+        double* row = ib->row[par];
+        double* col = ib->col[par];
+        if (own_row) {
+#pragma unroll
+            for (int tb = 0; tb < 5; ++tb) *reinterpret_cast<double2*>(&row[8 * tb + 2 * t4]) = make_double2(c[b][tb][0], c[b][tb][1]);
+        }
+        if (own_col) {
+#pragma unroll
+            for (int ta = 0; ta < 5; ++ta) col[8 * ta + g4] = odd ? c[ta][b][1] : c[ta][b][0];
+        }
+        __syncwarp();
+        const double ip = rcp_newton(row[k]);
+        double ci[5], cfix[5];
+        double2 r[5];
+#pragma unroll
+        for (int ta = 0; ta < 5; ++ta) cfix[ta] = ci[ta] = col[8 * ta + g4] * ip;
+#pragma unroll
+        for (int tb = 0; tb < 5; ++tb) r[tb] = *reinterpret_cast<const double2*>(&row[8 * tb + 2 * t4]);
+        if (own_col) {                               // the rank-1 term must not touch column k
+            if (odd) r[b].y = 0.0;
+            else r[b].x = 0.0;
+        }
+        if (own_row) ci[b] = 0.0;                    // ... nor row k
+#pragma unroll
+        for (int ta = 0; ta < 5; ++ta)
+#pragma unroll
+            for (int tb = 0; tb < 5; ++tb) {
+                c[ta][tb][0] = fma(-ci[ta], r[tb].x, c[ta][tb][0]);
+                c[ta][tb][1] = fma(-ci[ta], r[tb].y, c[ta][tb][1]);
+            }
+        if (own_row) {                               // row k := row k / p
+#pragma unroll
+            for (int tb = 0; tb < 5; ++tb) {
+                c[b][tb][0] = r[tb].x * ip;
+                c[b][tb][1] = r[tb].y * ip;
+            }
+        }
+        if (own_col) {                               // column k := -a_ik / p, 1 / p on the diagonal
+#pragma unroll
+            for (int ta = 0; ta < 5; ++ta) {
+                const double v = (ta == b && own_row) ? ip : -cfix[ta];
+                if (odd) c[ta][b][1] = v;
+                else c[ta][b][0] = v;
+            }
+        }
+    }
+}
+
+template <int b>
+__device__ __forceinline__ void k4_inv_all(double (&c)[5][5][2], const int m, K4InvBuf* ib, int& step, const int g4, const int t4) {
+    if constexpr (b < 5) {
+        k4_gj_steps<b>(c, m, ib, step, g4, t4);
+        k4_inv_all<b + 1>(c, m, ib, step, g4, t4);
+    }
+}
+
+// panel (row stride kK4Ld2) <- inverse of the padded scratch matrix src; returns false if the result is not finite
+__device__ __forceinline__ bool k4_spd_inverse(const double* __restrict__ src, double* __restrict__ panel, const int m, const int lane,
+                                               const int g4, const int t4) {
+    double c[5][5][2];
+#pragma unroll
+    for (int ta = 0; ta < 5; ++ta)
+#pragma unroll
+        for (int tb = 0; tb < 5; ++tb) {
+            const int i = 8 * ta + g4, j = 8 * tb + 2 * t4;
+            const double2 v = *reinterpret_cast<const double2*>(src + i * kPadMax + j);
+            c[ta][tb][0] = (i >= m && i == j) ? 1.0 : v.x;          // identity on the padding diagonal
+            c[ta][tb][1] = (i >= m && i == j + 1) ? 1.0 : v.y;
+        }
+    int step = 0;
+    k4_inv_all<0>(c, m, reinterpret_cast<K4InvBuf*>(panel), step, g4, t4);
+    __syncwarp();                                  // the scratch is dead: the result may overwrite it
+    bool finite = true;
+#pragma unroll
+    for (int ta = 0; ta < 5; ++ta)
+#pragma unroll
+        for (int tb = 0; tb < 5; ++tb) {
+            const int i = 8 * ta + g4, j = 8 * tb + 2 * t4;
+            const double x0 = (i < m && j < m) ? c[ta][tb][0] : 0.0, x1 = (i < m && j + 1 < m) ? c[ta][tb][1] : 0.0;
+            finite = finite && (fabs(x0) <= 1.79e308) && (fabs(x1) <= 1.79e308);
+            *reinterpret_cast<double2*>(panel + i * kK4Ld2 + j) = make_double2(x0, x1);
+        }
+    return finite;
+}
+
 // one warp's share of the recursion of the windows w = blockIdx.x, + gridDim.x, ...
-template <int T, int W>
-__device__ __forceinline__ void lwr2_body(const K4Params& P, double* P0, double* P1, double* P2, GJScratch* sh, const Group& g) {
-    const int lane = threadIdx.x & 31, g4 = lane >> 2, t4 = lane & 3;
+template <int W>
+__device__ __forceinline__ void lwr2_body(const K4Params& P, double* P0, double* P1, double* P2) {
+    const int lane = threadIdx.x & 31, g4 = lane >> 2, t4 = lane & 3, l64 = threadIdx.x & 63;
     const int m = P.m, p = P.p;
     const size_t mm = (size_t)m * m;
     const int ksteps = (m + 3) >> 2;
@@ -1492,7 +1603,6 @@ __device__ __forceinline__ void lwr2_body(const K4Params& P, double* P0, double*
     for (int w = blockIdx.x; w < P.n_win; w += gridDim.x) {
         const double* Rw = P.R + (size_t)w * (p + 1) * mm;
         double* Aw = P.A + (size_t)w * mm * p;
-        double dummy[T][T];
         double acc[13][2];
         k4_load<W, true>(acc, Rw, m, m, g4, t4);                                       // Gamma(0) = R(0)^T
         k4_store_pad<W, kPadMax>(gVf, acc, g4, t4);
@@ -1505,83 +1615,42 @@ __device__ __forceinline__ void lwr2_body(const K4Params& P, double* P0, double*
             k4_load<W, true>(acc, Rw + (size_t)(kk + 1) * mm, m, m, g4, t4);
             for (int j = 0; j < kk; ++j) {
                 __syncthreads();                                                        // the previous product is done with P0 / P1
-                k4_async_rows<2>(P0, stA(cur, j), kPadMax, m, g.l64);                  // A_{j+1}[i][q]
-                if (r16) k4_async_rows<2>(P1, Rw + (size_t)(kk - j) * mm, m, m, g.l64);      // R(l)[c][q] = Gamma(l)[q][c]
-                else k4_async_rows<1>(P1, Rw + (size_t)(kk - j) * mm, m, m, g.l64);
+                k4_async_rows<2>(P0, stA(cur, j), kPadMax, m, l64);                    // A_{j+1}[i][q]
+                if (r16) k4_async_rows<2>(P1, Rw + (size_t)(kk - j) * mm, m, m, l64);        // R(l)[c][q] = Gamma(l)[q][c]
+                else k4_async_rows<1>(P1, Rw + (size_t)(kk - j) * mm, m, m, l64);
                 k4_async_wait();
                 __syncthreads();
                 k4_mma<W, true, true, true>(acc, P0, P1, ksteps, g4, t4);
             }
             __syncthreads();
             k4_store_pad<W, kK4Ld2>(P2, acc, g4, t4);                                   // Delta, row-major
-            // ---- phases 2+3: Kf = Delta Vb^-1, Kb = Delta^T Vf^-1, residual covariances
+            // ---- phases 2+3: Vb^-1 -> P1 (warp 0) next to Vf^-1 -> P0 (warp 1);  Kf = Delta Vb^-1, Kb = Delta^T Vf^-1;  residual covariances
             {
-                double iv[T][T];
                 bool finite = true;
-                load_tile<T>(iv, gVb, kPadMax, m, g);
-#pragma unroll
-                for (int a = 0; a < T; ++a)
-#pragma unroll
-                    for (int b = 0; b < T; ++b) {
-                        const int i = g.tr + 8 * a, j = g.tc + 8 * b;
-                        if (!(i < m && j < m)) iv[a][b] = (i == j) ? 1.0 : 0.0;
-                    }
-                // residual covariances are symmetric positive definite: unpivoted elimination is stable
-                gj_inverse_static<T, false>(iv, dummy, m, g, sh);
-#pragma unroll
-                for (int a = 0; a < T; ++a)
-#pragma unroll
-                    for (int b = 0; b < T; ++b) {
-                        const int i = g.tr + 8 * a, j = g.tc + 8 * b;
-                        if (i < m && j < m) {
-                            P1[i * kK4Ld2 + j] = iv[a][b];
-                            finite = finite && (fabs(iv[a][b]) <= 1.79e308);
-                        }
-                    }
+                if (W == 0) finite = k4_spd_inverse(gVb, P1, m, lane, g4, t4);
+                else if (!last) finite = k4_spd_inverse(gVf, P0, m, lane, g4, t4);
                 __syncthreads();
+                double acc2[13][2];
 #pragma unroll
-                for (int n = 0; n < 13; ++n) acc[n][0] = acc[n][1] = 0.0;
+                for (int n = 0; n < 13; ++n) acc[n][0] = acc[n][1] = acc2[n][0] = acc2[n][1] = 0.0;
                 k4_mma<W, false, true, false>(acc, P2, P1, ksteps, g4, t4);             // Kf = sum_q Delta[i][q] Vbinv[q][j]
-                k4_store_pad<W, kK4Ld2>(P0, acc, g4, t4);                               // (phase 1 is done with P0)
+                if (!last) k4_mma<W, false, false, false>(acc2, P2, P0, ksteps, g4, t4);      // Kb = sum_q Delta[q][i] Vfinv[q][j]
+                __syncthreads();                                                         // every thread is done reading the inverses
+                k4_store_pad<W, kK4Ld2>(P0, acc, g4, t4);
                 if (last) k4_store_lag<W>(Aw, p, kk, acc, m, g4, t4);                   // A_p = Kf
                 else k4_store_pad<W, kPadMax>(stA(nxt, kk), acc, g4, t4);
                 if (!last) {
-                    load_tile<T>(iv, gVf, kPadMax, m, g);
-#pragma unroll
-                    for (int a = 0; a < T; ++a)
-#pragma unroll
-                        for (int b = 0; b < T; ++b) {
-                            const int i = g.tr + 8 * a, j = g.tc + 8 * b;
-                            if (!(i < m && j < m)) iv[a][b] = (i == j) ? 1.0 : 0.0;
-                        }
-                    gj_inverse_static<T, false>(iv, dummy, m, g, sh);
-                    __syncthreads();                                                     // every thread is done reading Vb^-1
-#pragma unroll
-                    for (int a = 0; a < T; ++a)
-#pragma unroll
-                        for (int b = 0; b < T; ++b) {
-                            const int i = g.tr + 8 * a, j = g.tc + 8 * b;
-                            if (i < m && j < m) {
-                                P1[i * kK4Ld2 + j] = iv[a][b];
-                                finite = finite && (fabs(iv[a][b]) <= 1.79e308);
-                            }
-                        }
-                    __syncthreads();
-#pragma unroll
-                    for (int n = 0; n < 13; ++n) acc[n][0] = acc[n][1] = 0.0;
-                    k4_mma<W, false, false, false>(acc, P2, P1, ksteps, g4, t4);        // Kb = sum_q Delta[q][i] Vfinv[q][j]
-                    k4_store_pad<W, kPadMax>(stB(nxt, kk), acc, g4, t4);
-                    __syncthreads();                                                     // every thread is done reading Vf^-1
-                    k4_store_pad<W, kK4Ld2>(P1, acc, g4, t4);
-                    k4_load_pad<W, kPadMax>(acc, gVb, g4, t4);
-                    __syncthreads();
-                    k4_mma<W, true, true, false>(acc, P1, P2, ksteps, g4, t4);          // Vb -= Kb Delta
-                    k4_store_pad<W, kPadMax>(gVb, acc, g4, t4);
-                } else {
-                    __syncthreads();
+                    k4_store_pad<W, kK4Ld2>(P1, acc2, g4, t4);
+                    k4_store_pad<W, kPadMax>(stB(nxt, kk), acc2, g4, t4);
+                    k4_load_pad<W, kPadMax>(acc2, gVb, g4, t4);
                 }
                 k4_load_pad<W, kPadMax>(acc, gVf, g4, t4);
-                k4_mma<W, true, true, true>(acc, P0, P2, ksteps, g4, t4);               // Vf -= Kf Delta^T   (P0 written before the barriers above)
+                __syncthreads();
+                if (!last) {
+                    k4_mma<W, true, true, false>(acc2, P1, P2, ksteps, g4, t4);         // Vb -= Kb Delta
+                    k4_store_pad<W, kPadMax>(gVb, acc2, g4, t4);
+                }
+                k4_mma<W, true, true, true>(acc, P0, P2, ksteps, g4, t4);               // Vf -= Kf Delta^T
                 k4_store_pad<W, kPadMax>(gVf, acc, g4, t4);
                 if (!finite) atomicOr(&P.status[w], 2);      // singular (or not positive definite) residual covariance
                 if (P.Vall) k4_store<W>(P.Vall + ((size_t)w * p + kk) * mm, m, acc, m, g4, t4);
@@ -1594,7 +1663,7 @@ __device__ __forceinline__ void lwr2_body(const K4Params& P, double* P0, double*
                 const double* own = isA ? stA(cur, j) : stB(cur, j);
                 const double* other = isA ? stB(cur, kk - 1 - j) : stA(cur, kk - 1 - j);
                 __syncthreads();                                                         // P2 (Delta / previous operand) is free
-                k4_async_rows<2>(P2, other, kPadMax, m, g.l64);
+                k4_async_rows<2>(P2, other, kPadMax, m, l64);
                 k4_load_pad<W, kPadMax>(acc, own, g4, t4);
                 k4_async_wait();
                 __syncthreads();
@@ -1614,16 +1683,11 @@ __global__ void __launch_bounds__(64, kK4PerSM) lwr2_kernel(const K4Params P) {
     double* P0 = reinterpret_cast<double*>(smem_raw);
     double* P1 = P0 + kK4Panel2;
     double* P2 = P1 + kK4Panel2;
-    GJScratch* sh = reinterpret_cast<GJScratch*>(P2 + kK4Panel2);
-    Group g = make_group();
-    g.gid = 0;
-    g.bar = 1;
     for (int e = threadIdx.x; e < 3 * kK4Panel2; e += 64) P0[e] = 0.0;      // padding rows / columns stay zero for good
     __syncthreads();
-    if ((threadIdx.x >> 5) == 0) lwr2_body<T, 0>(P, P0, P1, P2, sh, g);
-    else lwr2_body<T, 1>(P, P0, P1, P2, sh, g);
+    if ((threadIdx.x >> 5) == 0) lwr2_body<0>(P, P0, P1, P2);
+    else lwr2_body<1>(P, P0, P1, P2);
 }
-
 
 size_t lwr_ws_doubles(int grid, int m, int p) {       // lwr2_kernel keeps its scratch matrices padded to 40 x 40 (m <= 40 on this path)
     const size_t mm = (size_t)(m > kPadMax ? m : kPadMax) * (m > kPadMax ? m : kPadMax);
@@ -1652,7 +1716,7 @@ int launch_lwr(const K4Params& P, int grid, cudaStream_t stream) {
         return check_launch("lwr1_kernel");
     }
 #endif
-    const size_t smem = (size_t)3 * kK4Panel2 * sizeof(double) + sizeof(GJScratch);
+    const size_t smem = (size_t)3 * kK4Panel2 * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(lwr2_kernel<kTileMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "lwr: %s", cudaGetErrorString(e));
     // five 43 KB CTAs per SM need the large shared-memory carve-out (the default split may leave room for two only)

@@ -232,7 +232,7 @@ size_t hs_transfer_ws_bytes(int n_win, int m, int p, int F) {
     k5_segments(F, k5_groups(), &ns, &sl);
     if (m > kPadMaxHost)      // generic path: one partial row sum per bin + per-CTA scratch matrices
         return align_up((size_t)p * F * 16) + align_up((size_t)n_win * F * m * sizeof(double)) + align_up(transfer_generic_scratch_bytes(m)) + 256;
-    // z table, row sums of the optimistic pass, per-matrix flags, list of flagged matrices, counter, |H|^2 staging (n_win, F, m, m)
+    // z table, row sums of the optimistic pass, per-matrix flags, list of flagged matrices, counter, |H|^2 staging (n_win, m, F, m)
     return align_up((size_t)p * F * 16) + k5_rowpart_bytes(n_win, ns, m) + 2 * align_up((size_t)n_win * F * sizeof(int)) + 512 +
            align_up((size_t)n_win * F * m * m * sizeof(double));
 }
@@ -278,7 +278,7 @@ int hs_transfer_dtf_f64(const double* d_A, const double* d_freqs, int F, double 
     P.A = d_A;
     P.z = z;
     const bool want_dtf = d_dtf || d_ffdtf;
-    const bool staged = want_dtf && stage;       // m <= 40: |H|^2 goes through the (w, f, i, j) staging buffer
+    const bool staged = want_dtf && stage;       // m <= 40: |H|^2 goes through the (w, i, f, j) staging buffer
     P.dtf = staged ? stage : (d_dtf ? d_dtf : d_ffdtf);
     P.dtf_fij = staged ? 1 : 0;
     P.rowpart = d_ffdtf ? rowpart : nullptr;

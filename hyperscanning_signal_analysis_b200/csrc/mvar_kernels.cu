@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_dtf_kernel(const K5Params
                             if (MODE == 1) v *= s2;
                             rsum += v;
                             const size_t o = (wbase + (size_t)ri * m + cj[b]) * F + f;
-                            if (P.dtf) P.dtf[P.dtf_fij ? (((size_t)w * F + f) * m + ri) * m + cj[b] : o] = v;
+                            if (P.dtf) P.dtf[P.dtf_fij ? (((size_t)w * m + ri) * F + f) * m + cj[b] : o] = v;
                             if (P.H) {
                                 double2 h = make_double2(ar[a][b], ai[a][b]);
                                 if (MODE == 1) h = make_double2(fma(sc[a].x, ar[a][b], -sc[a].y * ai[a][b]), fma(sc[a].x, ai[a][b], sc[a].y * ar[a][b]));
@@ -323,10 +323,10 @@ __global__ void ffdtf_normalize_kernel(double* __restrict__ dtf, const double* _
     }
 }
 
-// Transposing finalize:  stage (n_win, F, m, m)  ->  dtf / ffdtf (n_win, m, m, F)  with
+// Transposing finalize:  stage (n_win, m, F, m)  ->  dtf / ffdtf (n_win, m, m, F)  with
 // ffdtf[w][i][j][f] = dtf[w][i][j][f] / sum_{j,f} dtf[w][i][j][f]   (mtmvar.py:281-283).
-// One CTA per (window, row i): the F runs of m contiguous doubles are read coalesced, transposed through shared
-// memory in chunks of kFinChunk bins and written as contiguous runs along f.
+// One CTA per (window, row i): its input is ONE contiguous run of F * m doubles (K5 stores row i of every bin's matrix there), read
+// with 16-byte loads, transposed through shared memory in chunks of kFinChunk bins and written as contiguous runs along f.
 constexpr int kFinChunk = 64;
 __global__ void __launch_bounds__(256, 4) dtf_finalize_kernel(const double* __restrict__ stage, const double* __restrict__ rowpart,
                                                            const int* __restrict__ bad, int m, int F, int n_seg,
@@ -336,22 +336,28 @@ __global__ void __launch_bounds__(256, 4) dtf_finalize_kernel(const double* __re
     __shared__ double denom_s;
     __shared__ int any_bad;
     const size_t obase = ((size_t)w * m + i) * (size_t)m * F;
-    constexpr int kPer = 10;                          // elements per thread and chunk (m * kFinChunk <= 2560)
+    constexpr int kPer = 5;                           // double2 per thread and chunk (m * kFinChunk <= 2560)
     const bool vec_ok = ((F & 1) == 0) && ((reinterpret_cast<uintptr_t>(dtf_out) & 15) == 0) && ((reinterpret_cast<uintptr_t>(ffdtf_out) & 15) == 0);
     const int nchunk = (F + kFinChunk - 1) / kFinChunk;
-    const double* sbase = stage + ((size_t)w * F * m + i) * m;
-    // (f, j) of element e = tid + 256 u of a chunk, advanced incrementally (no division in the loops)
-    const int f_first = threadIdx.x / m, j_first = threadIdx.x - f_first * m;
-    const int df = 256 / m, dj = 256 - df * m;
-    double v[kPer];
+    const double* sbase = stage + obase;              // (f, j) of this (w, i) at sbase[f * m + j]
+    const bool in_vec = ((m & 1) == 0) && ((reinterpret_cast<uintptr_t>(stage) & 15) == 0);      // a chunk is a whole number of aligned double2
+    const int chunk_len = kFinChunk * m;
+    const int total = F * m;
+    // (f, j) of the pair e = 2 (tid + 256 u) of a chunk, advanced incrementally (no division in the loops)
+    const int f_first = (2 * threadIdx.x) / m, j_first = 2 * threadIdx.x - f_first * m;
+    const int df = 512 / m, dj = 512 - df * m;
+    double2 v[kPer];
     auto fetch = [&](const int f0) {
-        int f = f_first, j = j_first;
+        const int base = f0 * m;
 #pragma unroll
         for (int u = 0; u < kPer; ++u) {
-            v[u] = (f < kFinChunk && f0 + f < F) ? __ldcs(sbase + (size_t)(f0 + f) * m * m + j) : 0.0;
-            f += df;
-            j += dj;
-            if (j >= m) { j -= m; ++f; }
+            const int e = 2 * (threadIdx.x + 256 * u);
+            if (in_vec) {
+                v[u] = (e < chunk_len && base + e < total) ? __ldcs(reinterpret_cast<const double2*>(sbase + base + e)) : make_double2(0.0, 0.0);
+            } else {
+                v[u].x = (e < chunk_len && base + e < total) ? __ldcs(sbase + base + e) : 0.0;
+                v[u].y = (e + 1 < chunk_len && base + e + 1 < total) ? __ldcs(sbase + base + e + 1) : 0.0;
+            }
         }
     };
     fetch(0);                                         // in flight while the denominator is put together
@@ -372,7 +378,7 @@ __global__ void __launch_bounds__(256, 4) dtf_finalize_kernel(const double* __re
         if (rowpart && any_bad)
             for (int f = 0; f < F; ++f)
                 if (bad[(size_t)w * F + f])
-                    for (int j = 0; j < m; ++j) acc += stage[(((size_t)w * F + f) * m + i) * m + j];
+                    for (int j = 0; j < m; ++j) acc += sbase[(size_t)f * m + j];
         denom_s = acc;
     }
     __syncthreads();
@@ -387,7 +393,11 @@ __global__ void __launch_bounds__(256, 4) dtf_finalize_kernel(const double* __re
             int f = f_first, j = j_first;
 #pragma unroll
             for (int u = 0; u < kPer; ++u) {
-                if (f < kFinChunk) tile[j * (kFinChunk + 1) + f] = v[u];
+                if (f < kFinChunk) {
+                    tile[j * (kFinChunk + 1) + f] = v[u].x;
+                    if (j + 1 < m) tile[(j + 1) * (kFinChunk + 1) + f] = v[u].y;
+                    else if (f + 1 < kFinChunk) tile[f + 1] = v[u].y;                   // (f + 1, j = 0): odd m only
+                }
                 f += df;
                 j += dj;
                 if (j >= m) { j -= m; ++f; }

@@ -43,7 +43,7 @@ struct K5Params {
     int per_cta;            // tensor-pipe kernel: matrices (w * F + f, contiguous range) per CTA; rowpart is then (n_win, n_seg, m)
                             //    with slot = CTA index - first CTA of the window, n_seg = ceil(F / per_cta) + 1
     int pipe_turns;         // tensor-pipe kernel: 1 = one warp at a time per SM sub-partition streams its block step's DMMAs
-    int dtf_fij;            // 1: P.dtf is a staging buffer laid out (n_win, F, m, m) -- one contiguous matrix per bin --
+    int dtf_fij;            // 1: P.dtf is a staging buffer laid out (n_win, m, F, m) -- row i of every bin's matrix contiguous --
                             //    that launch_dtf_finalize transposes to the reference's (n_win, m, m, F)
 };
 

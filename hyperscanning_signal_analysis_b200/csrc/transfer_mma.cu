@@ -559,7 +559,7 @@ __device__ __forceinline__ void mma_store_generic(const double (&c)[T][T][2], co
                 if (FINAL) {
                     const double v = fma(re, re, im * im);
                     rsum += v;
-                    if (P.dtf) P.dtf[P.dtf_fij ? (((size_t)w * sF + f) * m + i) * m + j : o] = v;
+                    if (P.dtf) P.dtf[P.dtf_fij ? (((size_t)w * m + i) * sF + f) * m + j : o] = v;
                     if (P.H) P.H[o] = make_double2(re, im);
                 } else {
                     P.Af[o] = make_double2(re, im);
@@ -972,8 +972,8 @@ __global__ void __launch_bounds__(NG * 64, 1) transfer_mma_kernel(const K5Params
             } else {
                 const double* X = reinterpret_cast<const double*>(gs->u.X) + (x.part ^ 1) * (25 * 32) + x.lane;      // the partner's outbox
                 const int j0 = 2 * x.t4 + x.part;
-                double* dst = P.dtf ? P.dtf + (((size_t)w * F + f) * m + x.g4) * m + j0 : nullptr;
-                const size_t row_step = (size_t)8 * m;
+                double* dst = P.dtf ? P.dtf + (((size_t)w * m + x.g4) * F + f) * m + j0 : nullptr;      // staging (w, i, f, j)
+                const size_t row_step = (size_t)8 * F * m;
 #pragma unroll
                 for (int ta = 0; ta < T; ++ta) {
                     double rsum = 0.0;
@@ -1242,8 +1242,8 @@ __global__ void __launch_bounds__(NG * 64 + 128, 1) transfer_ws_kernel(const K5P
             } else {
                 const double* X = reinterpret_cast<const double*>(gs->u.X) + (x.part ^ 1) * (25 * 32) + x.lane;      // the partner's outbox
                 const int j0 = 2 * x.t4 + x.part;
-                double* dst = P.dtf ? P.dtf + (((size_t)w * F + f) * m + x.g4) * m + j0 : nullptr;
-                const size_t row_step = (size_t)8 * m;
+                double* dst = P.dtf ? P.dtf + (((size_t)w * m + x.g4) * F + f) * m + j0 : nullptr;      // staging (w, i, f, j)
+                const size_t row_step = (size_t)8 * F * m;
 #pragma unroll
                 for (int ta = 0; ta < T; ++ta) {
                     double rsum = 0.0;

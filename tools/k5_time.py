@@ -5,6 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
 from hyperscanning_signal_analysis_b200 import _lib
+if os.environ.get('HS_LIB'): _lib.LIB_PATH = os.path.abspath(os.environ['HS_LIB'])      # a library variant built next to the product one
 n_win_req = int(sys.argv[1]) if len(sys.argv) > 1 else 599
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 M, WIN, P, F, FS = bench.M, bench.WIN, bench.P, bench.F, bench.FS

@@ -249,15 +249,15 @@ class EEG_IBI_FFDTF_Pipeline:
         return hits[0], True
 
     def _load_eeg_and_ibi(self, eeg_file, ibi_file, role):
-        import xarray as xr          # the reference's on-disk format (NetCDF via xarray); not installed on the build box
-        with xr.open_dataarray(eeg_file) as da:
+        from .export import open_dataarray      # xarray where it exists, the classic-NetCDF reader of export.py otherwise
+        with open_dataarray(eeg_file) as da:
             eeg = da.values.T.copy()
             time_s = da.coords["time"].values.copy()
-            names = da.coords["channel"].values.tolist()
+            names = [str(c) for c in da.coords["channel"].values.tolist()]
             duration = float(da.attrs["event_duration_s"])
             raw_fs = da.attrs.get("sampling_freq") or da.attrs.get("sfreq")
             fs_eeg = float(raw_fs) if raw_fs is not None else 128.0
-        with xr.open_dataarray(ibi_file) as da:
+        with open_dataarray(ibi_file) as da:
             ibi = da.values.T.copy()
             raw_fs = da.attrs.get("sampling_freq") or da.attrs.get("sfreq")
             fs_ibi = float(raw_fs) if raw_fs is not None else fs_eeg

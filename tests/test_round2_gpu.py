@@ -150,6 +150,28 @@ def test_process_dyad_builds_the_reference_result(tmp_path):
     assert z["ff_dtf_windowed"].shape == (3, 4, 4, 30)
 
 
+def test_run_pipeline_from_netcdf_files(tmp_path):
+    """run_pipeline (src/eeg_alpha_ibi_ffdtf.py:661-790) end to end: files in the on-disk container (export.write_netcdf3) ->
+    discovery -> _load_eeg_and_ibi -> pre-window stage -> windows -> ffDTF -> the reference's .npz; same numbers as process_dyad."""
+    from hyperscanning_signal_analysis_b200 import export
+    from hyperscanning_signal_analysis_b200.eeg_alpha_ibi_ffdtf import EEG_IBI_FFDTF_Pipeline
+    g = golden("round2.npz")
+    pw, x = _prewindow_inputs()
+    names = [str(s) for s in pw["names"]]
+    fs = float(pw["fs"])
+    t = np.arange(x.shape[1]) / fs
+    for role, eeg, ibi in (("ch", x[:19], pw["ibi"][0]), ("cg", x[19:], pw["ibi"][1])):
+        for kind, arr, chans in (("EEG", eeg.T, names), ("IBI", ibi[:, None], ["IBI"])):
+            folder = tmp_path / "in" / kind / "W_001"
+            folder.mkdir(parents=True, exist_ok=True)
+            export.write_netcdf3(folder / f"W_001_{kind}_{role}_M1.nc", arr, t, chans, {"sampling_freq": fs, "event_duration_s": float(t[-1]), "who": role})
+    pipe = EEG_IBI_FFDTF_Pipeline(tmp_path / "in", tmp_path / "out", ["M1"], n_windows=3, ar_p=5)
+    quiet(pipe.run_pipeline)
+    z = np.load(tmp_path / "out" / "W_001" / "W_001_M1_ffDTF.npz")
+    assert z["ff_dtf_windowed"].shape == (3, 4, 4, 30)
+    assert relerr(z["ff_dtf_windowed"], g["w3_p5_ffdtf"]) < 1e-5
+
+
 def test_ffdtf_elementwise_above_floor(mv):
     """Norm-wise 1e-7 leaves small entries unchecked (ffDTF spans many decades): element-wise check above 1e-6 max."""
     g = golden("mvar_cfg2_windows.npz")

@@ -150,6 +150,7 @@ def cpu_baseline(y, starts, freqs, budget_s=20.0):
     return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n} of {len(starts)} windows of the same task, oracle/mvar_oracle.full_freq_dtf (NumPy port of src/mtmvar.py), "
                       f"{cores} processes x 1 BLAS thread; single-process {1.0 / t_one:.2f} windows/s",
+            "serial_value": 1.0 / t_one,       # one process, one window at a time: how the reference's run_pipeline loop runs
             "seconds": dt}
 
 
@@ -170,7 +171,8 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_config(args.gpus), "windows_per_step": n,
                        "sample": "each step = a bounded sample of these windows on the host CPU (rank 0 only)"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": vals[-1]["cores"], "kind": "port", "sample": vals[-1]["sample"]},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": vals[-1]["cores"], "kind": "port", "sample": vals[-1]["sample"],
+                             "serial_value": vals[-1]["serial_value"]},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 

@@ -172,6 +172,48 @@ def test_run_pipeline_from_netcdf_files(tmp_path):
     assert relerr(z["ff_dtf_windowed"], g["w3_p5_ffdtf"]) < 1e-5
 
 
+def _transfer_with_flag_count(A, freqs, fs):
+    """hs_transfer_dtf_f64 through the C ABI on one window: (|H|^2 (m, m, F), number of matrices the optimistic pass flagged)."""
+    import torch
+    from hyperscanning_signal_analysis_b200 import _lib
+    lib = _lib.load()
+    m, _, p = A.shape
+    F = len(freqs)
+    Ad = torch.from_numpy(np.ascontiguousarray(A[None])).cuda()
+    fr = torch.from_numpy(np.ascontiguousarray(freqs, dtype=np.float64)).cuda()
+    out = torch.empty((1, m, m, F), dtype=torch.float64, device="cuda")
+    st = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ws = torch.zeros(lib.hs_transfer_ws_bytes(1, m, p, F), dtype=torch.uint8, device="cuda")
+    sp = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.hs_transfer_dtf_f64(Ad.data_ptr(), fr.data_ptr(), F, float(fs), 1, m, p, None, None, out.data_ptr(), None, st.data_ptr(),
+                                       ws.data_ptr(), sp), "transfer")
+    torch.cuda.synchronize()
+    off = lib.hs_transfer_ws_flag_offset(1, m, p, F)
+    return out[0].cpu().numpy(), int(ws[off:off + 4].view(torch.int32).item())
+
+
+@pytest.mark.parametrize("m", [7, 8, 28, 29, 31, 32, 33, 35, 36, 37, 39, 40])
+def test_a_posteriori_check_at_every_padding_geometry(m):
+    """The optimistic elimination verifies every matrix through the padding column when there is one (m < 8 T: the column carries
+    A(f) u; it lies inside the last eliminated block for 8 T - 4 < m and outside it otherwise) and through an explicit H v product
+    when m = 8 T.  Benign matrices must not be flagged, a matrix that needs pivoting must be -- and be repaired -- in each case."""
+    from oracle import mvar_oracle as mo
+    rng = np.random.default_rng(400 + m)
+    p, fs = 3, 256.0
+    freqs = np.array([0.0, 5.0, 31.0, 64.0, 100.0, 127.0])
+    A = 0.1 * rng.standard_normal((m, m, p)) / np.sqrt(m)                       # A(f) close to I: no pivoting needed
+    Hr, _ = mo.mvar_transfer_function(A, freqs, fs)
+    dtf, flagged = _transfer_with_flag_count(A, freqs, fs)
+    assert flagged == 0
+    assert relerr(dtf, np.abs(Hr) ** 2) < TOL_MODEL
+    B = np.zeros((m, m, p))                          # A(0) = a cyclic shift exactly: the first pivot block is singular, the unpivoted pass must fail
+    B[:, :, 0] = np.eye(m) - np.roll(np.eye(m), 1, axis=1)
+    Hb, _ = mo.mvar_transfer_function(B, freqs, fs)
+    dtf_b, flagged_b = _transfer_with_flag_count(B, freqs, fs)
+    assert 1 <= flagged_b <= len(freqs)
+    assert relerr(dtf_b, np.abs(Hb) ** 2) < TOL_MODEL
+
+
 def test_ffdtf_elementwise_above_floor(mv):
     """Norm-wise 1e-7 leaves small entries unchecked (ffDTF spans many decades): element-wise check above 1e-6 max."""
     g = golden("mvar_cfg2_windows.npz")

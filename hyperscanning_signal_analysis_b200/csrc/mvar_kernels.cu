@@ -1604,10 +1604,10 @@ __device__ __forceinline__ void lwr2_body(const K4Params& P, double* P0, double*
     const size_t mm = (size_t)m * m;
     const int ksteps = (m + 3) >> 2;
     const bool r16 = ((m & 1) == 0) && ((reinterpret_cast<size_t>(P.R) & 15) == 0);       // rows of R(l) are whole 16-byte chunks
-    double* ws = P.ws + (size_t)blockIdx.x * (4 * p + 2) * kK4Sd;       // [par][A|B][p] padded matrices, Vf, Vb
-    auto stA = [&](int par, int j) { return ws + ((size_t)(par * 2 + 0) * p + j) * kK4Sd; };   // j = 0-based index of A_{j+1}
-    auto stB = [&](int par, int j) { return ws + ((size_t)(par * 2 + 1) * p + j) * kK4Sd; };
-    double* gVf = ws + (size_t)4 * p * kK4Sd;
+    double* ws = P.ws + (size_t)blockIdx.x * (2 * p + 2) * kK4Sd;       // [A|B][p] padded matrices (updated in place), Vf, Vb
+    auto stA = [&](int j) { return ws + (size_t)j * kK4Sd; };            // j = 0-based index of A_{j+1}
+    auto stB = [&](int j) { return ws + ((size_t)p + j) * kK4Sd; };
+    double* gVf = ws + (size_t)2 * p * kK4Sd;
     double* gVb = gVf + kK4Sd;
 
     for (int w = blockIdx.x; w < P.n_win; w += gridDim.x) {
@@ -1619,13 +1619,12 @@ __device__ __forceinline__ void lwr2_body(const K4Params& P, double* P0, double*
         k4_store_pad<W, kPadMax>(gVb, acc, g4, t4);
         __syncthreads();
         for (int kk = 0; kk < p; ++kk) {
-            const int cur = kk & 1, nxt = cur ^ 1;
             const bool last = (kk == p - 1);
             // ---- phase 1: Delta = Gamma(kk+1) - sum_j A_{j+1} Gamma(kk-j)
             k4_load<W, true>(acc, Rw + (size_t)(kk + 1) * mm, m, m, g4, t4);
             for (int j = 0; j < kk; ++j) {
                 __syncthreads();                                                        // the previous product is done with P0 / P1
-                k4_async_rows<2>(P0, stA(cur, j), kPadMax, m, l64);                    // A_{j+1}[i][q]
+                k4_async_rows<2>(P0, stA(j), kPadMax, m, l64);                    // A_{j+1}[i][q]
                 if (r16) k4_async_rows<2>(P1, Rw + (size_t)(kk - j) * mm, m, m, l64);        // R(l)[c][q] = Gamma(l)[q][c]
                 else k4_async_rows<1>(P1, Rw + (size_t)(kk - j) * mm, m, m, l64);
                 k4_async_wait();
@@ -1648,10 +1647,10 @@ __device__ __forceinline__ void lwr2_body(const K4Params& P, double* P0, double*
                 __syncthreads();                                                         // every thread is done reading the inverses
                 k4_store_pad<W, kK4Ld2>(P0, acc, g4, t4);
                 if (last) k4_store_lag<W>(Aw, p, kk, acc, m, g4, t4);                   // A_p = Kf
-                else k4_store_pad<W, kPadMax>(stA(nxt, kk), acc, g4, t4);
+                else k4_store_pad<W, kPadMax>(stA(kk), acc, g4, t4);
                 if (!last) {
                     k4_store_pad<W, kK4Ld2>(P1, acc2, g4, t4);
-                    k4_store_pad<W, kPadMax>(stB(nxt, kk), acc2, g4, t4);
+                    k4_store_pad<W, kPadMax>(stB(kk), acc2, g4, t4);
                     k4_load_pad<W, kPadMax>(acc2, gVb, g4, t4);
                 }
                 k4_load_pad<W, kPadMax>(acc, gVf, g4, t4);
@@ -1666,21 +1665,38 @@ __device__ __forceinline__ void lwr2_body(const K4Params& P, double* P0, double*
                 if (P.Vall) k4_store<W>(P.Vall + ((size_t)w * p + kk) * mm, m, acc, m, g4, t4);
                 if (last) k4_store<W>(P.V + (size_t)w * mm, m, acc, m, g4, t4);
             }
-            // ---- phase 4: order update  A_j -= Kf B_{kk-1-j}  (and  B_j -= Kb A_{kk-1-j}  unless this is the last order)
-            for (int it = 0; it < (last ? kk : 2 * kk); ++it) {
-                const bool isA = it < kk;
-                const int j = isA ? it : it - kk;
-                const double* own = isA ? stA(cur, j) : stB(cur, j);
-                const double* other = isA ? stB(cur, kk - 1 - j) : stA(cur, kk - 1 - j);
-                __syncthreads();                                                         // P2 (Delta / previous operand) is free
-                k4_async_rows<2>(P2, other, kPadMax, m, l64);
-                k4_load_pad<W, kPadMax>(acc, own, g4, t4);
-                k4_async_wait();
-                __syncthreads();
-                if (isA) k4_mma<W, true, true, false>(acc, P0, P2, ksteps, g4, t4);
-                else k4_mma<W, true, true, false>(acc, P1, P2, ksteps, g4, t4);
-                if (last) k4_store_lag<W>(Aw, p, j, acc, m, g4, t4);                    // final A_{j+1}
-                else k4_store_pad<W, kPadMax>(isA ? stA(nxt, j) : stB(nxt, j), acc, g4, t4);
+            // ---- phase 4: order update  A_j -= Kf B_{kk-1-j},  B_j -= Kb A_{kk-1-j}, IN PLACE: the updates of A_ja and B_jb (ja + jb = kk - 1)
+            //      read only each other's old values, so both results are formed before either is stored (no second copy of the A / B
+            //      sets: the scratch of all 599 windows is 138 MB instead of 261 MB and mostly stays in L2)
+            if (last) {
+                for (int j = 0; j < kk; ++j) {
+                    __syncthreads();                                                     // P2 (Delta / previous operand) is free
+                    k4_async_rows<2>(P2, stB(kk - 1 - j), kPadMax, m, l64);
+                    k4_load_pad<W, kPadMax>(acc, stA(j), g4, t4);
+                    k4_async_wait();
+                    __syncthreads();
+                    k4_mma<W, true, true, false>(acc, P0, P2, ksteps, g4, t4);
+                    k4_store_lag<W>(Aw, p, j, acc, m, g4, t4);                          // final A_{j+1}
+                }
+            } else {
+                for (int it = 0; it < kk; ++it) {
+                    const int ja = it, jb = kk - 1 - it;
+                    double acc2[13][2];
+                    __syncthreads();                                                     // P2 is free
+                    k4_async_rows<2>(P2, stB(jb), kPadMax, m, l64);
+                    k4_load_pad<W, kPadMax>(acc, stA(ja), g4, t4);
+                    k4_async_wait();
+                    __syncthreads();
+                    k4_mma<W, true, true, false>(acc, P0, P2, ksteps, g4, t4);          // A_ja - Kf B_jb   (kept in registers)
+                    __syncthreads();                                                     // every thread is done with B_jb in P2
+                    k4_async_rows<2>(P2, stA(ja), kPadMax, m, l64);                     // the OLD A_ja
+                    k4_load_pad<W, kPadMax>(acc2, stB(jb), g4, t4);
+                    k4_async_wait();
+                    __syncthreads();
+                    k4_mma<W, true, true, false>(acc2, P1, P2, ksteps, g4, t4);         // B_jb - Kb A_ja
+                    k4_store_pad<W, kPadMax>(stA(ja), acc, g4, t4);
+                    k4_store_pad<W, kPadMax>(stB(jb), acc2, g4, t4);
+                }
             }
             __syncthreads();
         }
@@ -1701,7 +1717,11 @@ __global__ void __launch_bounds__(64, kK4PerSM) lwr2_kernel(const K4Params P) {
 
 size_t lwr_ws_doubles(int grid, int m, int p) {       // lwr2_kernel keeps its scratch matrices padded to 40 x 40 (m <= 40 on this path)
     const size_t mm = (size_t)(m > kPadMax ? m : kPadMax) * (m > kPadMax ? m : kPadMax);
-    return (size_t)grid * (4 * p + 2) * mm;
+#ifdef HS_EXPERIMENT
+    return (size_t)grid * (4 * p + 2) * mm;       // lwr1_kernel keeps two copies of the A / B sets
+#else
+    return (size_t)grid * (2 * p + 2) * mm;
+#endif
 }
 int lwr_grid(int n_win) { const int slots = device_sm_count() * kK4PerSM; return n_win < slots ? n_win : slots; }
 

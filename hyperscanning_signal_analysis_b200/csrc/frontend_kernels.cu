@@ -925,6 +925,135 @@ static size_t lookback_bytes(int n_sig, long long tiles) {
 }
 
 
+// ------------------------------------------------------------------ K2 on the FP64 tensor pipe
+// FIR filtering / decimation as a Toeplitz product in the natural sample index: for 8 consecutive outputs o0 .. o0 + 7 of 8 SIGNALS,
+//     C[s][n] = sum_e S_s[q o0 + e] B[e][n],      B[e][n] = taps[e - q n]  (0 outside the filter),   e = 0 .. 7 q + ntaps - 1,
+// i.e. ceil((7 q + ntaps) / 4) k-steps of mma.sync.m8n8k4.f64 per 8 x 8 outputs (q = 8, 161 taps: 55 DMMAs, 74 % of their FMAs on
+// non-zero band entries; q = 1, 201 taps: 97 %).  B is a fixed banded Toeplitz matrix: its fragments are constants per lane, held in
+// registers for the whole kernel (the two halves of the k range go to two warps, whose partial sums are added through shared
+// memory); an A fragment is one shared load of CONSECUTIVE samples (lane (g4, t4): signal g4, sample q o0 + 4 kk + t4), so the input
+// spans are staged exactly as they lie in memory -- 16-byte cp.async copies straight from global to shared memory, double buffered
+// (the next tile's copies run under this tile's products) -- with a signal stride = 4 (mod 16) doubles for conflict-free fragment loads.  A DMMA (256 FMAs) costs one
+// LDS instead of the 64 LDS + address computations the register-window kernel spends on as many FMAs: that kernel is bound by
+// instruction issue (ncu: LSU 69 %, issue 57 %, FP64 pipe at a third of its peak), not by memory.
+// One CTA = 8 signals x kMmaTilesPerCta tiles of kMmaOut outputs, 8 warps.  Used when 7 q + ntaps <= 224 and there are >= 5 signals.
+constexpr int kMmaOut = 64;                                 // outputs per tile
+constexpr int kMmaTilesPerCta = 16;                         // consecutive output tiles per CTA: the B fragments are built once per CTA
+__host__ __device__ inline int mma_dec_ksteps(int q, int ntaps) { return (7 * q + ntaps + 3) / 4; }
+__host__ __device__ inline int mma_dec_kh(int q, int ntaps) { const int ks = mma_dec_ksteps(q, ntaps); return ks <= 14 ? 7 : (ks <= 28 ? 14 : 28); }
+__host__ __device__ inline int mma_dec_sig_stride(int q, int ntaps) {
+    const int span = q * kMmaOut + ntaps - 1, reach = q * (kMmaOut - 8) + 8 * mma_dec_kh(q, ntaps);      // the k range is padded to 2 KH steps
+    int st = span > reach ? span : reach;
+    st += (4 - (st & 15) + 16) & 15;                        // = 4 (mod 16)
+    return st;
+}
+
+__device__ __forceinline__ void dmma884_fe(double& c0, double& c1, const double a, const double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// Stage the input spans of the 8 signals of one tile exactly as they lie in memory, S[s][i] = x_s[lo + i] (zero outside the signal),
+// with cp.async straight from global to shared memory: 16 bytes per copy on interior tiles with aligned spans (all of a thread's ~11
+// copies in flight at once, committed as one group), 8-byte copies with bounds checks and zero fill on edge tiles.
+// (Measured: one cp.async.bulk per signal and tile with a transaction mbarrier -- no copy instructions in the warps at all -- is slower
+//  here, 0.58 against 0.31 ms for cfg4: with two buffers the copy of the next tile can only start one product phase (~0.9 us) ahead,
+//  which a 5 KB bulk copy does not cover, and a third buffer costs the second CTA per SM.)
+__device__ __forceinline__ void mma_dec_stage(double* __restrict__ buf, const double* __restrict__ x, const long long n,
+                                              const long long sig_stride, const int n_sig, const int s0, const long long lo, const int span,
+                                              const int ss, const bool aligned) {
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(buf);
+    const bool whole = aligned && lo >= 0 && lo + span <= n;          // the span lies inside the signal and starts on a 16-byte boundary
+    const int n_live = min(8, n_sig - s0);                             // a missing signal keeps the zeros the buffers start with
+    if (whole) {
+        const int chunks = span >> 1;
+        const unsigned ss8 = 8u * (unsigned)ss;
+        for (int c = threadIdx.x; c < chunks; c += 256) {              // two rounds for q = 8, 161 taps
+            const double* src = x + (long long)s0 * sig_stride + lo + 2 * c;
+            unsigned dst = sbase + 16u * c;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                if (s < n_live) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                src += sig_stride;
+                dst += ss8;
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int s = 0; s < n_live; ++s) {
+            const double* xs = x + (long long)(s0 + s) * sig_stride + lo;
+            const unsigned ds = sbase + 8u * (unsigned)(s * ss);
+            for (int i = threadIdx.x; i < span; i += 256) {
+                if (lo + i >= 0 && lo + i < n) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ds + 8u * i), "l"(xs + i) : "memory");
+                else buf[s * ss + i] = 0.0;
+            }
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int KH>      // k-steps per warp half: 2 KH >= ceil((7 q + ntaps) / 4)
+__global__ void __launch_bounds__(256, 2) fir_mma_kernel(const double* __restrict__ x, long long n, long long sig_stride, int n_sig, int q,
+                                                         long long off, const double* __restrict__ b, int ntaps,
+                                                         double* __restrict__ y, long long n_out, long long y_stride) {
+    extern __shared__ __align__(16) double dec_smem[];
+    const int ss = mma_dec_sig_stride(q, ntaps);
+    double2* red = reinterpret_cast<double2*>(dec_smem + 2 * 8 * ss);  // [4 warps][2 tiles][32 lanes] partial sums of the upper k half
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g4 = lane >> 2, t4 = lane & 3;
+    // warp (pw, nw): the k-steps [pw KH, (pw + 1) KH) of the 8-output tiles 2 nw, 2 nw + 1
+    const int pw = warp >> 2, nw = warp & 3;
+    const int s0 = blockIdx.y * 8;
+    const int span = q * kMmaOut + ntaps - 1;
+    const long long lo0 = off - (ntaps - 1);
+    // bulk copies need 16-byte aligned sources and sizes: even span, even first index (q k0 + lo0 for every tile), even signal stride
+    const bool aligned = ((span & 1) == 0) && ((lo0 & 1) == 0) && (((q * kMmaOut) & 1) == 0) && ((sig_stride & 1) == 0) &&
+                         ((reinterpret_cast<size_t>(x) & 15) == 0);
+    // the samples behind a span that the padded k range reaches meet zero taps, but must be finite: zero both buffers once
+    for (int i = threadIdx.x; i < 2 * 8 * ss; i += 256) dec_smem[i] = 0.0;
+    // ---- B fragments: lane (n = g4, e = 4 kk + t4) <- taps[e - q n] = b[ntaps - 1 - (e - q n)]
+    double bf[KH];
+#pragma unroll
+    for (int k = 0; k < KH; ++k) {
+        const int d = 4 * (pw * KH + k) + t4 - q * g4;
+        bf[k] = (d >= 0 && d < ntaps) ? b[ntaps - 1 - d] : 0.0;
+    }
+    __syncthreads();
+    const long long tile0 = (long long)blockIdx.x * kMmaTilesPerCta;
+    if (tile0 * kMmaOut < n_out) mma_dec_stage(dec_smem, x, n, sig_stride, n_sig, s0, (long long)q * tile0 * kMmaOut + lo0, span, ss, aligned);
+    for (int tile = 0; tile < kMmaTilesPerCta; ++tile) {
+        const long long k0 = (tile0 + tile) * kMmaOut;
+        if (k0 >= n_out) break;
+        // the next tile's copy runs while this tile is multiplied (double buffer; the barrier after the products of tile - 1 freed it)
+        const bool more = tile + 1 < kMmaTilesPerCta && k0 + kMmaOut < n_out;
+        if (more) mma_dec_stage(dec_smem + ((tile + 1) & 1) * 8 * ss, x, n, sig_stride, n_sig, s0, (long long)q * (k0 + kMmaOut) + lo0, span, ss, aligned);
+        if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const double* Sa = dec_smem + (tile & 1) * 8 * ss + g4 * ss + q * (nw * 16) + 4 * pw * KH + t4;
+        double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int k = 0; k < KH; ++k) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) dmma884_fe(c[h][0], c[h][1], Sa[8 * q * h + 4 * k], bf[k]);
+        }
+        if (pw == 1) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) red[(nw * 2 + h) * 32 + lane] = make_double2(c[h][0], c[h][1]);
+        }
+        __syncthreads();
+        if (pw == 0 && s0 + g4 < n_sig) {
+            double* ys = y + (long long)(s0 + g4) * y_stride;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double2 o = red[(nw * 2 + h) * 32 + lane];
+                const long long k = k0 + (2 * nw + h) * 8 + 2 * t4;
+                if (k < n_out) ys[k] = c[h][0] + o.x;
+                if (k + 1 < n_out) ys[k + 1] = c[h][1] + o.y;
+            }
+        }
+        // (no barrier here: the next tile's copies go to the OTHER buffer, and the barrier that follows them comes before the next
+        //  write of red and before anything overwrites this tile's buffer)
+    }
+}
+
 extern "C" {
 
 size_t hs_filtfilt_ws_bytes(int n_sig, int64_t n) {
@@ -1119,6 +1248,20 @@ int hs_fir_filter_f64(const double* d_x, int n_sig, int64_t n, int64_t sig_strid
     if (n_sig <= 0 || n <= 0 || n_out <= 0) return HS_OK;
     const size_t smem = ((size_t)q * dec_phase_stride(q, ntaps) + ntaps) * sizeof(double);
     if (smem > 200 * 1024) return set_error(HS_ERR_UNSUPPORTED, "hs_fir_filter_f64: q=%d, ntaps=%d need %zu B shared memory", q, ntaps, smem);
+    if (n_sig >= 5 && mma_dec_ksteps(q, ntaps) <= 56) {      // Toeplitz products on the FP64 tensor pipe
+        const size_t smem_m = (size_t)2 * 8 * mma_dec_sig_stride(q, ntaps) * sizeof(double) + (size_t)4 * 2 * 32 * sizeof(double2);
+        dim3 grid_m((unsigned)((n_out + (long long)kMmaOut * kMmaTilesPerCta - 1) / ((long long)kMmaOut * kMmaTilesPerCta)), (unsigned)((n_sig + 7) / 8));
+        auto launch_m = [&](auto kern) -> int {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
+            if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "hs_fir_filter_f64: %s", cudaGetErrorString(e));
+            kern<<<grid_m, 256, smem_m, (cudaStream_t)stream>>>(d_x, n, sig_stride, n_sig, q, off, d_b, ntaps, d_y, n_out, y_stride);
+            return check_launch("fir_mma_kernel");
+        };
+        const int kh = mma_dec_kh(q, ntaps);
+        if (kh == 7) return launch_m(fir_mma_kernel<7>);
+        if (kh == 14) return launch_m(fir_mma_kernel<14>);
+        return launch_m(fir_mma_kernel<28>);
+    }
     dim3 grid((unsigned)((n_out + kDecOut - 1) / kDecOut), n_sig);
     auto launch = [&](auto kern) -> int {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -366,13 +366,15 @@ __device__ __forceinline__ void mma_tile_steps(double (&c)[T][T][2], const int m
         mma_extract<T, t>(c, h, x);
         mma_group_sync(x);
         double2 det = make_double2(1.0, 0.0);      // ADJ == 2: P holds adj(D), L comes out multiplied by det and U is divided by it below
+        double2 pv, pk;       // P[t4][g4 >> 1] (B fragments of -P) and P[g4 & 3][t4] (rows K of the panel)
 #ifdef HS_EXPERIMENT
         if (x.dbg & 1) {      // experiment: no 4 x 4 inverse (timing only, results are wrong)
             if (x.lane < 16) gs->u.p.P[x.part][x.lane] = make_double2((x.lane % 5 == 0) ? 1.0 : 0.0, 0.0);
             __syncwarp();
+            pv = gs->u.p.P[x.part][x.t4 * 4 + (x.g4 >> 1)];
+            pk = gs->u.p.P[x.part][(x.g4 & 3) * 4 + x.t4];
         } else
 #endif
-        double2 pv, pk;       // P[t4][g4 >> 1] (B fragments of -P) and P[g4 & 3][t4] (rows K of the panel)
         if (ADJ == 4) {
             mma_inverse4_newton(x, K0, h, pv, pk);
         } else {

@@ -21,7 +21,7 @@ for k in "$@"; do
     k5w)  cap k5_ws         'transfer_ws_kernel'    python tools/prof_mvar.py 599 1 ;;
     fin)  cap fin           'dtf_finalize_kernel'   python tools/prof_mvar.py 599 1 ;;
     k1)   cap k1_fused      'iir_tile_fused_kernel' python tools/bench_frontend.py 600 ;;
-    k2)   cap k2_decimate   'fir_decimate'   python tools/bench_frontend.py 600 ;;
+    k2)   cap k2_fir_mma    'fir_mma_kernel'   python tools/bench_frontend.py 1800 ;;
     k6)   cap k6_r16        'mt_psd_r16_kernel'     python tools/bench_frontend.py 600 ;;
     list) python bench.py --steps 2 --warmup 3 --no-cpu --no-extra > $TXT/r02_list_plain.log 2>&1 &&
           ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $TXT/r02_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-extra > $TXT/r02_list_ncu.log 2>&1

@@ -1361,18 +1361,20 @@ __global__ void __launch_bounds__(64, kK4PerSM) lwr1_kernel(const K4Params P) {
 
 
 // -------------------------------------------------------------------------------------
-// K4 on the FP64 tensor pipe (the one that runs): same recursion, same panels and barriers as lwr1_kernel, but every
-// product is mma.sync.m8n8k4.f64.  lwr1_kernel issues 1000 DFMAs + 400 LDS per thread and product and is bound by instruction
-// issue / fixed latencies with 2.5 warps per scheduler (0.19 of the FP64 peak on LWR's own flops); a DMMA does the work of 8
-// DFMAs per lane from two fragment loads, so a product is 130 DMMAs + 80 LDS per lane.
-//   * the 25 accumulator tiles of a 40 x 40 product are split 13 / 12 between the two warps of the window (tile order row-major:
-//     warp 0 rows 0, 1 and three tiles of row 2; warp 1 the rest): per k-step 3 A fragments + 5 B fragments for 13 DMMAs;
-//   * panels keep their roles (P0 / P1 / P2 rotate through A_j, Gamma, Delta, V^-1, Kf, Kb) with a row stride of 44 doubles
-//     (= 12 mod 16): a fragment is read along a row or along a column of the panel -- (ld g4 + t4) or (ld t4 + g4) mod 16 distinct over
-//     a half-warp -- so no transposed copies exist, as before;
-//   * accumulators live in the m8n8k4 layout (lane (g4, t4): row 8a + g4, columns 8b + 2 t4, +1) and go to / come from the
-//     global scratch row-major; the SPD inverses stay on the register-tile Gauss-Jordan (gj_inverse_static) and exchange
-//     V_f / V_b with the products through that scratch (different thread -> element maps, hence the barriers around them).
+// K4 on the FP64 tensor pipe (the one that runs): the recursion and the panel roles of lwr1_kernel, with
+//   * every product as mma.sync.m8n8k4.f64: lwr1_kernel issues 1000 DFMAs + 400 LDS per thread and product; a DMMA does the work of 8
+//     DFMAs per lane from two fragment loads, so a product is 130 DMMAs + 80 LDS per lane.  The 25 accumulator tiles of a 40 x 40
+//     product are split 13 / 12 between the two warps of the window (tile order row-major: warp 0 rows 0, 1 and three tiles of row 2;
+//     warp 1 the rest): per k-step 3 A fragments + 5 B fragments for 13 DMMAs;
+//   * panels (P0 / P1 / P2 rotate through A_j, Gamma, Delta, V^-1, Kf, Kb) with a row stride of 44 doubles (= 12 mod 16): a fragment is
+//     read along a row or along a column of the panel -- (ld g4 + t4) or (ld t4 + g4) mod 16 distinct over a half-warp -- so no
+//     transposed copies exist, as before;
+//   * the data movement the profiler showed to dominate lwr1_kernel taken out of the warps: scratch matrices (A_j, B_j, V_f, V_b) are
+//     zero-padded 40 x 40, go global -> panel by cp.async and global <-> accumulator as unconditional 16-byte accesses; the order update
+//     is done in place (A_ja and B_jb, ja + jb = kk - 1, read only each other's old values); the final A_k go straight to the output;
+//   * accumulators in the m8n8k4 layout (lane (g4, t4): row 8a + g4, columns 8b + 2 t4, +1); the two SPD inverses of an order run side
+//     by side, one warp each, on the whole matrix in that warp's registers (k4_spd_inverse below).
+// 599 cfg2 windows: 0.68 ms (lwr1_kernel: 1.08 ms); dram 1.2 GB per launch.
 // -------------------------------------------------------------------------------------
 constexpr int kK4Ld2 = kPadMax + 4;             // 44
 constexpr int kK4Panel2 = kPadMax * kK4Ld2;

@@ -137,3 +137,37 @@ def test_psd_stays_inside_its_buffers(env, n, K):
     if n % 2 == 0:
         ref[:, -1] *= 0.5
     assert float(np.max(np.abs(got - ref[:, k_lo:k_hi])) / np.max(np.abs(ref))) < 1e-9
+
+
+@pytest.mark.parametrize("n_sig,n,q,ntaps,off,shift", [
+    (5, 5000, 8, 161, 80, 0), (13, 4099, 8, 161, 80, 0), (38, 3000, 4, 81, 40, 0), (8, 2048, 2, 41, 20, 0),
+    (6, 1500, 1, 201, 0, 0), (7, 1500, 1, 201, 100, 0), (9, 3001, 8, 160, 79, 0), (5, 700, 8, 161, 80, 0),
+    (16, 100, 8, 161, 80, 0), (5, 20000, 8, 161, 80, 1), (11, 70000, 8, 161, 80, 0), (8, 9000, 1, 217, 3, 0)])
+def test_fir_on_the_tensor_pipe_matches_direct_evaluation(env, n_sig, n, q, ntaps, off, shift):
+    """hs_fir_filter_f64 with >= 5 signals and 7 q + ntaps <= 224 runs fir_mma_kernel (Toeplitz products, cp.async staging): every
+    staging path (16-byte interior copies, 8-byte copies for odd strides / unaligned bases / even tap counts, zero-filled edges,
+    missing signals of the last group of 8, signals shorter than the filter) against y[k] = sum_j b[j] x[q k + off - j], inside
+    sentinel-guarded buffers."""
+    torch, _lib, lib = env
+    rng = np.random.default_rng(n_sig * 1000 + n + ntaps)
+    xbuf = Guarded(torch, (n_sig * n + shift) * 8)
+    xall = xbuf.view(torch.float64, (n_sig * n + shift,))
+    xall.copy_(torch.from_numpy(rng.standard_normal(n_sig * n + shift) * 10 + 1))
+    xh = xall[shift:].cpu().numpy().reshape(n_sig, n)
+    b = rng.standard_normal(ntaps)
+    b_d = torch.from_numpy(b).cuda()
+    n_out = (n + q - 1) // q if off < n else 1
+    n_out = max(1, min(n_out, (n - 1 + ntaps - 1 - off) // q + 1)) if off <= n - 1 + ntaps - 1 else 1
+    ybuf = Guarded(torch, n_sig * n_out * 8)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.hs_fir_filter_f64(xbuf.ptr + 8 * shift, n_sig, n, n, q, off, b_d.data_ptr(), ntaps, ybuf.ptr, n_out, n_out, st), "fir")
+    torch.cuda.synchronize()
+    assert ybuf.intact() and xbuf.intact()
+    got = ybuf.view(torch.float64, (n_sig, n_out)).cpu().numpy()
+    ref = np.zeros((n_sig, n_out))
+    for s in range(n_sig):
+        full = np.convolve(xh[s], b)                     # full[i] = sum_j b[j] x[i - j]
+        idx = q * np.arange(n_out) + off
+        ok = idx < full.size
+        ref[s, ok] = full[idx[ok]]
+    assert float(np.max(np.abs(got - ref)) / np.max(np.abs(ref))) < 1e-12

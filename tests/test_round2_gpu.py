@@ -214,6 +214,29 @@ def test_a_posteriori_check_at_every_padding_geometry(m):
     assert relerr(dtf_b, np.abs(Hb) ** 2) < TOL_MODEL
 
 
+@pytest.mark.parametrize("m,p", [(6, 2), (38, 8)])
+def test_more_windows_than_resident_slots(mv, m, p):
+    """More windows than the Yule-Walker kernel has resident CTAs (5 per SM: 740 on a B200): CTAs then walk several windows through
+    the same scratch and panels.  Sampled windows against the oracle, all of them through the row sums."""
+    from oracle import mvar_oracle as mo
+    rng = np.random.default_rng(900 + m)
+    n, hop, n_win = 64 if m == 6 else 512, 16 if m == 6 else 64, 1700 if m == 6 else 1000
+    T = n + hop * (n_win - 1)
+    x = rng.standard_normal((m, T))
+    x[:, 1:] += 0.6 * x[:, :-1]
+    x += 0.1 * rng.standard_normal((m, m)) @ x
+    starts = np.arange(n_win) * hop
+    freqs = np.linspace(0.0, 64.0, 12, endpoint=False)
+    ff, A, V = mv.windowed_ffdtf(x, starts, n, freqs, 128.0, p, return_model=True)
+    ff = ff.cpu().numpy()
+    np.testing.assert_allclose(ff.sum(axis=(2, 3)), 1.0, rtol=1e-11)
+    for w in (0, 739, 740, 741, n_win - 1):
+        Ar, Vr = mo.ar_coeff(x[:, starts[w]:starts[w] + n], p)
+        assert relerr(A[w].cpu().numpy(), Ar) < TOL_MODEL and relerr(V[w].cpu().numpy(), Vr) < TOL_MODEL, w
+        ref = mo.full_freq_dtf(x[:, starts[w]:starts[w] + n], freqs, 128.0, optimal_model_order=p)
+        assert relerr(ff[w], ref) < TOL_MODEL, w
+
+
 def test_ffdtf_elementwise_above_floor(mv):
     """Norm-wise 1e-7 leaves small entries unchecked (ffDTF spans many decades): element-wise check above 1e-6 max."""
     g = golden("mvar_cfg2_windows.npz")

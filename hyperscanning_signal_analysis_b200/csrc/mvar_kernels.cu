@@ -1954,6 +1954,165 @@ __global__ void __launch_bounds__(256) pcoh_kernel(const double2* __restrict__ S
         }
 }
 
+// Partial coherence for m > 40: the same identity (minor_cr = (-1)^(r+c) det S (S^-1)_rc), one CTA per (window, bin), IN PLACE in the
+// kappa output -- the (m, m) slice of bin f (element stride F) is the work matrix, so no scratch is needed:
+//   1. slice <- D S D (diagonal pre-scaling by powers of two, as above);
+//   2. Gauss-Jordan with partial pivoting and PHYSICAL row swaps; only the PHASE of the determinant is tracked (product of the pivots'
+//      unit phases times the swap parity): kappa is invariant under det -> rho det (rho > 0), and |det| of a 128 x 128 matrix leaves
+//      the double range;
+//   3. the swaps applied to the columns in reverse order: slice = (D S D)^-1 =: X;
+//   4. kappa[c][r] = (-1)^(r+c) e^(i phi) X_rc / csqrt(e^(2 i phi) X_cc X_rr), pairwise in place (the diagonal of X is kept in shared
+//      memory), 1 on the diagonal.
+// Strided and unblocked: a completeness path (the reference's m^2 minor determinants per bin are O(m^5)), not a tuned one.
+__global__ void __launch_bounds__(256) pcoh_generic_kernel(const double2* __restrict__ S, const int m, const int F, double2* __restrict__ kappa,
+                                                           const double* __restrict__ ffdtf, double* __restrict__ ddtf, int* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char pg_smem[];
+    double2* col = reinterpret_cast<double2*>(pg_smem);      // m: pivot column / diagonal of X
+    double2* row = col + m;                                  // m: scaled pivot row
+    int* ex = reinterpret_cast<int*>(row + m);               // m: scaling exponents
+    int* perm = ex + m;                                      // m: row swapped with k at step k
+    __shared__ double s_red[256];
+    __shared__ int s_idx[256];
+    __shared__ double2 s_phase;
+    __shared__ int s_sing;
+    const int f = blockIdx.x, w = blockIdx.y;
+    const size_t sF = (size_t)F;
+    const double2* Sw = S + (size_t)w * m * m * sF + f;
+    double2* a = kappa + (size_t)w * m * m * sF + f;         // a[e * sF], e = i * m + j
+    for (int i = threadIdx.x; i < m; i += 256) {
+        const double2 d = Sw[((size_t)i * m + i) * sF];
+        const double mag = hypot(d.x, d.y);
+        ex[i] = (mag > 0.0 && mag < 1e300) ? -(ilogb(mag) / 2) : 0;
+    }
+    if (threadIdx.x == 0) { s_phase = make_double2(1.0, 0.0); s_sing = 0; }
+    __syncthreads();
+    for (int e = threadIdx.x; e < m * m; e += 256) {
+        const int i = e / m, j = e - i * m;
+        double2 v = Sw[(size_t)e * sF];
+        v.x = scalbn(v.x, ex[i] + ex[j]);
+        v.y = scalbn(v.y, ex[i] + ex[j]);
+        a[(size_t)e * sF] = v;
+    }
+    __syncthreads();
+    for (int k = 0; k < m; ++k) {
+        // pivot: largest |a_ik|, i >= k (ties: smallest i)
+        double best = -1.0;
+        int bi = 1 << 20;
+        for (int i = k + threadIdx.x; i < m; i += 256) {
+            const double2 v = a[((size_t)i * m + k) * sF];
+            const double mag = fma(v.x, v.x, v.y * v.y);
+            if (mag > best) { best = mag; bi = i; }
+        }
+        s_red[threadIdx.x] = best;
+        s_idx[threadIdx.x] = bi;
+        __syncthreads();
+        for (int off = 128; off > 0; off >>= 1) {
+            if (threadIdx.x < off) {
+                const double ob = s_red[threadIdx.x + off];
+                const int oi = s_idx[threadIdx.x + off];
+                if (ob > s_red[threadIdx.x] || (ob == s_red[threadIdx.x] && oi < s_idx[threadIdx.x])) { s_red[threadIdx.x] = ob; s_idx[threadIdx.x] = oi; }
+            }
+            __syncthreads();
+        }
+        const int r = s_idx[0];
+        const bool ok = s_red[0] > 0.0 && s_red[0] < 1.79e308;
+        if (!ok) {                                            // singular (or non-finite) S(f): flag the window, leave the bin
+            if (threadIdx.x == 0) { s_sing = 1; atomicOr(&status[w], 4); }
+            __syncthreads();
+            break;
+        }
+        if (threadIdx.x == 0) perm[k] = r;
+        if (r != k)                                           // physical row swap
+            for (int j = threadIdx.x; j < m; j += 256) {
+                const double2 t0 = a[((size_t)k * m + j) * sF];
+                a[((size_t)k * m + j) * sF] = a[((size_t)r * m + j) * sF];
+                a[((size_t)r * m + j) * sF] = t0;
+            }
+        __syncthreads();
+        const double2 pv = a[((size_t)k * m + k) * sF];
+        const double d = 1.0 / fma(pv.x, pv.x, pv.y * pv.y);
+        const double2 iv = make_double2(pv.x * d, -pv.y * d);
+        if (threadIdx.x == 0) {                               // phase of det: times pv / |pv|, times -1 for a swap
+            const double inv_abs = rsqrt(fma(pv.x, pv.x, pv.y * pv.y));
+            double2 ph = cmul2(s_phase, make_double2(pv.x * inv_abs, pv.y * inv_abs));
+            const double nrm = rsqrt(fma(ph.x, ph.x, ph.y * ph.y));
+            const double sg = (r != k) ? -nrm : nrm;
+            s_phase = make_double2(ph.x * sg, ph.y * sg);
+        }
+        for (int i = threadIdx.x; i < m; i += 256) col[i] = (i == k) ? make_double2(0.0, 0.0) : a[((size_t)i * m + k) * sF];
+        for (int j = threadIdx.x; j < m; j += 256) {
+            const double2 xv = (j == k) ? make_double2(1.0, 0.0) : a[((size_t)k * m + j) * sF];
+            row[j] = cmul2(xv, iv);
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < m * m; e += 256) {
+            const int i = e / m, j = e - i * m;
+            double2 xv;
+            if (i == k) {
+                xv = row[j];
+            } else {
+                xv = (j == k) ? make_double2(0.0, 0.0) : a[(size_t)e * sF];
+                const double2 c = col[i], rv = row[j];
+                xv.x = fma(-c.x, rv.x, fma(c.y, rv.y, xv.x));
+                xv.y = fma(-c.x, rv.y, fma(-c.y, rv.x, xv.y));
+            }
+            a[(size_t)e * sF] = xv;
+        }
+        __syncthreads();
+    }
+    if (s_sing) {                                             // defined output for a flagged bin: identity
+        for (int e = threadIdx.x; e < m * m; e += 256) {
+            const int i = e / m, j = e - i * m;
+            a[(size_t)e * sF] = make_double2((i == j) ? 1.0 : 0.0, 0.0);
+            if (ddtf) ddtf[(size_t)w * m * m * sF + (size_t)e * sF + f] = (i == j) ? ffdtf[(size_t)w * m * m * sF + (size_t)e * sF + f] : 0.0;
+        }
+        return;
+    }
+    // (P S')^-1 -> S'^-1: the row swaps as column swaps, last one first
+    for (int k = m - 1; k >= 0; --k) {
+        const int r = perm[k];
+        if (r != k)
+            for (int i = threadIdx.x; i < m; i += 256) {
+                const double2 t0 = a[((size_t)i * m + k) * sF];
+                a[((size_t)i * m + k) * sF] = a[((size_t)i * m + r) * sF];
+                a[((size_t)i * m + r) * sF] = t0;
+            }
+        __syncthreads();
+    }
+    const double2 ph = s_phase;
+    const double2 ph2 = cmul2(ph, ph);
+    for (int i = threadIdx.x; i < m; i += 256) col[i] = a[((size_t)i * m + i) * sF];       // X_ii
+    __syncthreads();
+    const double* ffw = ffdtf ? ffdtf + (size_t)w * m * m * sF + f : nullptr;
+    double* ddw = ddtf ? ddtf + (size_t)w * m * m * sF + f : nullptr;
+    for (int e = threadIdx.x; e < m * m; e += 256) {
+        const int r = e / m, c = e - r * m;
+        if (r > c) continue;
+        if (r == c) {
+            a[(size_t)e * sF] = make_double2(1.0, 0.0);
+            if (ddw) ddw[(size_t)e * sF] = ffw[(size_t)e * sF];
+            continue;
+        }
+        // kappa[c][r] from X_rc, kappa[r][c] from X_cr: the pair is read before either is written
+        const size_t e_rc = (size_t)r * m + c, e_cr = (size_t)c * m + r;
+        const double2 x_rc = a[e_rc * sF], x_cr = a[e_cr * sF];
+        const double2 den = csqrt2(cmul2(ph2, cmul2(col[c], col[r])));
+        const bool live = den.x != 0.0 || den.y != 0.0;
+        const double sg = ((r + c) & 1) ? -1.0 : 1.0;
+        double2 n_rc = cmul2(ph, x_rc), n_cr = cmul2(ph, x_cr);
+        n_rc = make_double2(sg * n_rc.x, sg * n_rc.y);
+        n_cr = make_double2(sg * n_cr.x, sg * n_cr.y);
+        const double2 k_cr = live ? cdiv2(n_rc, den) : make_double2(0.0, 0.0);      // kappa[c][r] <- minor_cr ~ X_rc
+        const double2 k_rc = live ? cdiv2(n_cr, den) : make_double2(0.0, 0.0);      // kappa[r][c] <- minor_rc ~ X_cr
+        a[e_cr * sF] = k_cr;
+        a[e_rc * sF] = k_rc;
+        if (ddw) {
+            ddw[e_cr * sF] = ffw[e_cr * sF] * hypot(k_cr.x, k_cr.y);
+            ddw[e_rc * sF] = ffw[e_rc * sF] * hypot(k_rc.x, k_rc.y);
+        }
+    }
+}
+
 int launch_pcoh(const void* S, int n_win, int m, int F, void* kappa, const double* ffdtf, double* ddtf, int* status, cudaStream_t stream) {
     const long long n_mat = (long long)n_win * F;
     const int grid = (int)((n_mat + 3) / 4);
@@ -1965,7 +2124,14 @@ int launch_pcoh(const void* S, int n_win, int m, int F, void* kappa, const doubl
         case 3: pcoh_kernel<3><<<grid, 256, 0, stream>>>(Sp, (int)n_mat, m, F, kp, ffdtf, ddtf, status); break;
         case 4: pcoh_kernel<4><<<grid, 256, 0, stream>>>(Sp, (int)n_mat, m, F, kp, ffdtf, ddtf, status); break;
         case 5: pcoh_kernel<5><<<grid, 256, 0, stream>>>(Sp, (int)n_mat, m, F, kp, ffdtf, ddtf, status); break;
-        default: return set_error(HS_ERR_UNSUPPORTED, "partial coherence: m = %d > %d not built", m, kPadMax);
+        default: {
+            // m > 40: in place in the kappa output (no workspace in this entry point's signature)
+            if (!kappa) return set_error(HS_ERR_INVALID, "partial coherence: m = %d > %d needs the kappa output as its work matrix", m, kPadMax);
+            const size_t smem = (size_t)2 * m * sizeof(double2) + (size_t)2 * m * sizeof(int);
+            if (smem > 48 * 1024) return set_error(HS_ERR_UNSUPPORTED, "partial coherence: m = %d too large", m);
+            pcoh_generic_kernel<<<dim3(F, n_win), 256, smem, stream>>>(Sp, m, F, kp, ffdtf, ddtf, status);
+            return check_launch("pcoh_generic_kernel");
+        }
     }
     return check_launch("pcoh_kernel");
 }

@@ -124,7 +124,7 @@ int hs_gpdc_f64(const void* d_Af, const double* d_V, int n_win, int m, int F, do
  * inverse per bin (minor_ij = (-1)^(i+j) det S (S^-1)_ji), and the product of direct_dtf (:379-383).
  *   d_S (n_win, m, m, F) complex128 in;  d_kappa (n_win, m, m, F) complex128 out or NULL;
  *   d_ffdtf in / d_ddtf out (n_win, m, m, F) float64, both or neither:  ddtf = ffdtf * |kappa|.
- * d_status[w] |= 4 when S(f) of window w is singular for some bin.  m <= 40.                     */
+ * d_status[w] |= 4 when S(f) of window w is singular for some bin.  m > 40: in place in d_kappa, which must then be given.  */
 int hs_partial_coherence_f64(const void* d_S, int n_win, int m, int F, void* d_kappa, const double* d_ffdtf,
                              double* d_ddtf, int32_t* d_status, void* stream);
 

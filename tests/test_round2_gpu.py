@@ -237,6 +237,36 @@ def test_more_windows_than_resident_slots(mv, m, p):
         assert relerr(ff[w], ref) < TOL_MODEL, w
 
 
+@pytest.mark.parametrize("m,F", [(41, 3), (48, 4), (64, 2)])
+def test_partial_coherence_more_than_40_channels(mv, m, F):
+    """partial_coherence / dDTF beyond the register-tile limit (pcoh_generic_kernel: pivoted Gauss-Jordan in place in the output, the
+    phase of the determinant instead of its value) against the reference's minor determinants (oracle, mtmvar.py:300-321)."""
+    import torch
+    from oracle import mvar_oracle as mo
+    rng = np.random.default_rng(70 + m)
+    H = rng.standard_normal((m, m, F)) + 1j * rng.standard_normal((m, m, F))
+    V = rng.standard_normal((m, m))
+    V = V @ V.T + m * np.eye(m)
+    S = np.stack([H[:, :, f] @ (V @ H[:, :, f].T) for f in range(F)], axis=2) * 1e-9       # the reference's S = H V H^T, in "volts"
+    # kappa is invariant under S -> c S.  The reference's minors are ~1e-225 at this scale and the PRODUCT of two underflows to 0 (it then
+    # returns kappa = 0 everywhere off the diagonal: INTEGRATION.md, known differences); the oracle is therefore run on a copy of S scaled
+    # to unit geometric-mean singular value per bin, the GPU path on the data as they are.
+    gm = np.array([np.exp(np.mean(np.log(np.linalg.svd(S[:, :, f], compute_uv=False)))) for f in range(F)])
+    ref = mo.partial_coherence(S / gm)
+    got = mv.partial_coherence(S)
+    assert got.shape == ref.shape and np.all(got[np.arange(m), np.arange(m), :] == 1.0)
+    scale = max(1.0, np.max(np.abs(ref)))                       # S = H V H^T (plain transpose) is not Hermitian: |kappa| may exceed 1
+    assert np.max(np.abs(got - ref)) < 1e-8 * scale              # det of (m-1) x (m-1) minors on the CPU side
+    ff = rng.uniform(0.0, 1.0, (1, m, m, F))
+    kap, dd, status = mv.batched_partial_coherence(torch.from_numpy(S[None]).cuda(), torch.from_numpy(ff).cuda())
+    assert int(status.max()) == 0
+    assert np.max(np.abs(dd[0].cpu().numpy() - ff[0] * np.abs(ref))) < 1e-8 * scale
+    Ssing = S.copy()
+    Ssing[:, 5, :] = 0.0                                          # a zero column stays exactly zero through the elimination: zero pivot
+    with pytest.raises(np.linalg.LinAlgError):
+        mv.partial_coherence(Ssing)
+
+
 def test_ffdtf_elementwise_above_floor(mv):
     """Norm-wise 1e-7 leaves small entries unchecked (ffDTF spans many decades): element-wise check above 1e-6 max."""
     g = golden("mvar_cfg2_windows.npz")

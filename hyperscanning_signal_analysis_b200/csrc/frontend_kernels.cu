@@ -358,23 +358,41 @@ __global__ void __launch_bounds__(kTileThreads) iir_tile_apply_kernel(const IirP
 //      s_in(t) = e(t-1) + Q e(t-2) + Q^2 e(t-3) + ... ,   Q = M^8192,
 // stopping at the first predecessor that already published its inclusive state, at the beginning of the signal
 // (s_0 = zi * x_0), or when Q^k has decayed below 1e-30 (stable filters: |Q| ~ 1e-15 for the loader's 1 Hz high-pass at
-// 1024 Hz, so one or two records are read).  Tickets make the wait deadlock free: every predecessor holds an earlier
-// ticket, i.e. it is already running.  Records are tagged with the sweep number, so they are cleared once per call, not
-// per sweep.  Per sweep: 1 coalesced read + 1 coalesced write of the signal.
+// 1024 Hz, so one or two records are read).  The wait is deadlock free: CTAs are dispatched in index order, so every
+// predecessor is already running.  Per sweep: 1 coalesced read + 1 coalesced write of the signal.
+// A record is ONE 16-byte word {state 0, state 1} that carries its own validity: every sweep of a call has its own records,
+// preset to all-ones (a NaN no arithmetic produces; a published value that happens to be that pattern is replaced by the
+// canonical NaN), written by one 16-byte store and polled by one 16-byte load.  No flag word, no release / acquire pair:
+// a look-back costs one L2 round trip instead of two dependent ones.
 struct IirLookback {
-    double* agg;         // (n_sig, n_tiles, 2) zero-state end state of every tile
-    double* incl;        // (n_sig, n_tiles, 2) true end state
-    int* flags;          // (n_sig, n_tiles) 2 sw + 1: aggregate published, 2 sw + 2: inclusive published
-    unsigned* ticket;    // one counter per sweep of the call
+    double2* rec;        // (n_sig, n_tiles, 2) of this sweep: [0] zero-state end state of the tile (aggregate), [1] true end state
     int sweep;           // sweep number within the call
 };
 
-__device__ __forceinline__ int ld_flag(const int* p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+constexpr unsigned long long kRecEmpty = ~0ull;
+__device__ __forceinline__ double2 ld_rec(const double2* p) {
+    double2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_flag(int* p, const int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_rec(double2* p, double a, double b) {
+    if ((unsigned long long)__double_as_longlong(a) == kRecEmpty) a = __longlong_as_double(0x7ff8000000000000LL);
+    if ((unsigned long long)__double_as_longlong(b) == kRecEmpty) b = __longlong_as_double(0x7ff8000000000000LL);
+    asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ bool rec_valid(const double2 v) {
+    return (unsigned long long)__double_as_longlong(v.x) != kRecEmpty && (unsigned long long)__double_as_longlong(v.y) != kRecEmpty;
+}
+// state of record j for the look-back: 2 = true end state, 1 = aggregate, 0 = nothing published yet
+template <int D>
+__device__ __forceinline__ int rec_fetch(const double2* rec, const long long j, double (&a)[D]) {
+    const double2 ri = ld_rec(rec + j * 2 + 1), ra = ld_rec(rec + j * 2);
+    const bool vi = rec_valid(ri), va = rec_valid(ra);
+    const double2 r = vi ? ri : ra;
+    a[0] = r.x;
+    if (D > 1) a[D - 1] = r.y;
+    return vi ? 2 : (va ? 1 : 0);
+}
 
 constexpr int kFusedThreads = kTileThreads + 32;      // 8 compute warps + the look-back warp
 
@@ -393,7 +411,7 @@ __global__ void __launch_bounds__(kFusedThreads, 3) iir_tile_fused_kernel(const 
     const int s = (int)(tk / n_tiles);
     const long long tile = tk - (long long)s * n_tiles;
     const long long rec0 = (long long)s * n_tiles;
-    const int f_agg = 2 * S.sweep + 1, f_incl = 2 * S.sweep + 2;
+    constexpr int f_agg = 1, f_incl = 2;
     if (warp == kTileThreads / 32) {
         // ---- look-back warp: the start state of this tile from the predecessors' records.  It needs nothing of this tile, so it
         //      runs WHILE the compute warps stage and scan their samples: its two or three L2 round trips are off the critical path.
@@ -418,23 +436,13 @@ __global__ void __launch_bounds__(kFusedThreads, 3) iir_tile_fused_kernel(const 
             double a[D];
 #pragma unroll
             for (int q = 0; q < D; ++q) a[q] = 0.0;
-            if (j >= 0 && lane < kWidth) {
-                f = ld_flag(S.flags + rec0 + j);
-                if (f >= f_agg) {
-                    const double* src = (f == f_incl) ? S.incl : S.agg;
-#pragma unroll
-                    for (int q = 0; q < D; ++q) a[q] = __ldcg(src + (rec0 + j) * 2 + q);
-                }
-            }
+            if (j >= 0 && lane < kWidth) f = rec_fetch<D>(S.rec, rec0 + j, a);
             for (int l = 0; l < kWidth && !done; ++l) {
                 int fl = __shfl_sync(0xffffffffu, f, l);
                 const bool exists = (j0 - l >= 0);
                 if (exists && fl < f_agg) {          // not published yet: lane l waits for exactly this record
                     if (lane == l) {
-                        do { f = ld_flag(S.flags + rec0 + j); } while (f < f_agg);
-                        const double* src = (f == f_incl) ? S.incl : S.agg;
-#pragma unroll
-                        for (int q = 0; q < D; ++q) a[q] = __ldcg(src + (rec0 + j) * 2 + q);
+                        do { f = rec_fetch<D>(S.rec, rec0 + j, a); } while (f < f_agg);
                     }
                     fl = __shfl_sync(0xffffffffu, f, l);
                 }
@@ -484,14 +492,15 @@ __global__ void __launch_bounds__(kFusedThreads, 3) iir_tile_fused_kernel(const 
         }
         asm volatile("bar.sync 2, %0;" ::"n"(kFusedThreads) : "memory");      // rendezvous: e_sh (compute warps) and sin_sh are both in place
         if (lane == 0) {
+            double o[2] = {0.0, 0.0};
 #pragma unroll
             for (int i = 0; i < D; ++i) {
                 double v = e_sh[i];
 #pragma unroll
                 for (int q = 0; q < D; ++q) v = fma(ct.pw[0][i * D + q], acc[q], v);
-                S.incl[(rec0 + tile) * 2 + i] = v;
+                o[i] = v;
             }
-            st_flag(S.flags + rec0 + tile, f_incl);
+            st_rec(S.rec + (rec0 + tile) * 2 + 1, o[0], o[1]);
         }
         return;
     }
@@ -510,16 +519,15 @@ __global__ void __launch_bounds__(kFusedThreads, 3) iir_tile_fused_kernel(const 
     }
     tile_sync<true>();
     if (threadIdx.x == 0) {
-        double e[D];
+        double e[2] = {0.0, 0.0};
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             double acc = 0.0;
             for (int q = 0; q < kTileThreads / 32; ++q) acc += red[q][k];
             e[k] = acc;
             e_sh[k] = acc;
-            S.agg[(rec0 + tile) * 2 + k] = acc;
         }
-        st_flag(S.flags + rec0 + tile, f_agg);
+        st_rec(S.rec + (rec0 + tile) * 2, e[0], e[1]);
     }
     // ---- inclusive scan of the zero-state pieces inside the warp:  v_l = sum_{l' <= l} P^(l-l') z_l'
     double v[D];
@@ -919,9 +927,10 @@ struct PreparedFilter {
 static std::mutex g_prep_mutex;
 static std::deque<PreparedFilter> g_prep_cache;
 
+// look-back records: one set per sweep of a call (2 sweeps per tiled filter), 2 x 16 bytes per (signal, tile)
 static size_t lookback_bytes(int n_sig, long long tiles) {
     const size_t recs = (size_t)n_sig * (size_t)tiles;
-    return recs * 4 * sizeof(double) + ((recs + 63) / 64) * 64 * sizeof(int) + 64 * sizeof(unsigned) + 256;
+    return (size_t)2 * kMaxTiledFilters * recs * 2 * sizeof(double2) + 256;
 }
 
 
@@ -1099,11 +1108,9 @@ static int iir_run(double* d_x, int n_sig, int64_t n, int64_t sig_stride, int64_
     const long long tiles_max = (Lmax + kTile - 1) / kTile;
     double* lb_base = ppow_dev + (size_t)kMaxTiledFilters * kPpowEntries * 4;
     IirLookback LB;
-    LB.agg = lb_base;
-    LB.incl = lb_base + (size_t)n_sig * tiles_max * 2;
-    LB.flags = reinterpret_cast<int*>(lb_base + (size_t)n_sig * tiles_max * 4);
-    LB.ticket = reinterpret_cast<unsigned*>(LB.flags + (((size_t)n_sig * tiles_max + 63) / 64) * 64);
+    LB.rec = reinterpret_cast<double2*>(lb_base);
     LB.sweep = 0;
+    const size_t lb_set = (size_t)n_sig * tiles_max * 2;      // double2 per sweep
     bool lb_cleared = false;
     std::vector<double> ppow_host;
 
@@ -1200,13 +1207,15 @@ static int iir_run(double* d_x, int n_sig, int64_t n, int64_t sig_stride, int64_
         auto sweep = [&](const IirPass& Pp) -> int {
             if (!tiled) return run_sweep_d(c.d, Pp, c, st);
             if (!fused_mode) return c.d == 1 ? run_sweep_tiled<1>(Pp, c, ct, d_ppow, st) : run_sweep_tiled<2>(Pp, c, ct, d_ppow, st);
-            if (!lb_cleared) {      // flags and the per-sweep ticket counters: cleared once per call (records carry the sweep number)
-                const size_t bytes = (((size_t)n_sig * tiles_max + 63) / 64) * 64 * sizeof(int) + 64 * sizeof(unsigned);
-                if (cudaMemsetAsync(LB.flags, 0, bytes, st) != cudaSuccess) return set_error(HS_ERR_CUDA, "filtfilt: memset failed");
+            if (!lb_cleared) {      // every sweep of the call has its own records: all of them preset to "empty" (all-ones) once
+                int n_tiled = 0;
+                for (int q = 0; q < n_filt; ++q) n_tiled += use_tiled[q] ? 1 : 0;
+                const size_t bytes = (size_t)(causal ? 1 : 2) * n_tiled * lb_set * sizeof(double2);
+                if (cudaMemsetAsync(LB.rec, 0xff, bytes, st) != cudaSuccess) return set_error(HS_ERR_CUDA, "filtfilt: memset failed");
                 lb_cleared = true;
             }
             IirLookback S = LB;
-            S.ticket = exp_env_int("HS_IIR_TICKET", 0) ? LB.ticket + LB.sweep : nullptr;
+            S.rec = LB.rec + (size_t)LB.sweep * lb_set;
             const int r = c.d == 1 ? run_sweep_fused<1>(Pp, c, ct, d_ppow, S, st) : run_sweep_fused<2>(Pp, c, ct, d_ppow, S, st);
             ++LB.sweep;
             return r;

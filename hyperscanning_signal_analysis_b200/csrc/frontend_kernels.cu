@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(128) iir_apply_kernel(const IirPass P, const I
 //                  the tile back coalesced.
 // Per sweep: 2 coalesced reads + 1 coalesced write of the signal (the thread-per-chunk path does the same amount of
 // traffic, uncoalesced).
-constexpr int kTileThreads = 256;      // (512 threads x 16 samples, two CTAs per SM, measured slower: 5.6 vs 4.4 ms for the cfg4 cascade)
+constexpr int kTileThreads = 128;      // (512 threads x 16 samples, two CTAs per SM, measured slower: 5.6 vs 4.4 ms for the cfg4 cascade)
 constexpr int kTilePer = 32;
 constexpr int kTilePerLog2 = 5;
 constexpr int kTile = kTileThreads * kTilePer;      // 8192 sweep positions per CTA
@@ -219,7 +219,7 @@ __device__ __forceinline__ void mv2(const double* __restrict__ Pm, const double 
 // ninth warp that only does the look-back)
 template <bool NAMED>
 __device__ __forceinline__ void tile_sync() {
-    if (NAMED) asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (NAMED) asm volatile("bar.sync 1, %0;" ::"n"(kTileThreads) : "memory");
     else __syncthreads();
 }
 
@@ -352,20 +352,22 @@ __global__ void __launch_bounds__(kTileThreads) iir_tile_apply_kernel(const IirP
 }
 
 // ------------------------------------------------------------------ K1, single-pass tiled sweep (decoupled look-back)
-// tile_local + carry + tile_apply read the signal twice per sweep.  Here ONE kernel does the sweep: a CTA takes a ticket
-// (tiles of a signal in sweep order), stages its tile once, computes the tile's zero-state end state e (its "aggregate"),
-// publishes it, and then obtains its true start state by LOOKING BACK over the predecessors' records:
-//      s_in(t) = e(t-1) + Q e(t-2) + Q^2 e(t-3) + ... ,   Q = M^8192,
-// stopping at the first predecessor that already published its inclusive state, at the beginning of the signal
-// (s_0 = zi * x_0), or when Q^k has decayed below 1e-30 (stable filters: |Q| ~ 1e-15 for the loader's 1 Hz high-pass at
-// 1024 Hz, so one or two records are read).  The wait is deadlock free: CTAs are dispatched in index order, so every
-// predecessor is already running.  Per sweep: 1 coalesced read + 1 coalesced write of the signal.
+// tile_local + carry + tile_apply read the signal twice per sweep.  Here ONE kernel does the sweep: a CTA (tiles of a signal
+// in sweep order) stages its tile once, computes the tile's zero-state end state e (its "aggregate"), publishes it, and then
+// obtains its true start state by LOOKING BACK over the predecessors' aggregates:
+//      s_in(t) = e(t-1) + Q e(t-2) + Q^2 e(t-3) + ... ,   Q = M^kTile,
+// stopping at the beginning of the signal (s_0 = zi * x_0) or when Q^k has decayed below 1e-30 (|Q| ~ 2e-8 for the loader's
+// 1 Hz high-pass at 1024 Hz: four records, fetched by four lanes at once).  Only aggregates are read -- never a predecessor's
+// finished state, which would shorten the walk but make the summation order depend on timing: the result is bit-reproducible.
+// Aggregates depend on nothing but their own tile, so the wait is deadlock free (CTAs are dispatched in index order: every
+// predecessor is running or done).  Filters that decay too slowly for this (|Q^8| >= 1e-3) take the three-kernel path.
+// Per sweep: 1 coalesced read + 1 coalesced write of the signal.
 // A record is ONE 16-byte word {state 0, state 1} that carries its own validity: every sweep of a call has its own records,
 // preset to all-ones (a NaN no arithmetic produces; a published value that happens to be that pattern is replaced by the
 // canonical NaN), written by one 16-byte store and polled by one 16-byte load.  No flag word, no release / acquire pair:
 // a look-back costs one L2 round trip instead of two dependent ones.
 struct IirLookback {
-    double2* rec;        // (n_sig, n_tiles, 2) of this sweep: [0] zero-state end state of the tile (aggregate), [1] true end state
+    double2* rec;        // (n_sig, n_tiles) of this sweep: zero-state end state of every tile (its aggregate)
     int sweep;           // sweep number within the call
 };
 
@@ -383,26 +385,24 @@ __device__ __forceinline__ void st_rec(double2* p, double a, double b) {
 __device__ __forceinline__ bool rec_valid(const double2 v) {
     return (unsigned long long)__double_as_longlong(v.x) != kRecEmpty && (unsigned long long)__double_as_longlong(v.y) != kRecEmpty;
 }
-// state of record j for the look-back: 2 = true end state, 1 = aggregate, 0 = nothing published yet
+// record j for the look-back: 1 = published, 0 = not yet
 template <int D>
 __device__ __forceinline__ int rec_fetch(const double2* rec, const long long j, double (&a)[D]) {
-    const double2 ri = ld_rec(rec + j * 2 + 1), ra = ld_rec(rec + j * 2);
-    const bool vi = rec_valid(ri), va = rec_valid(ra);
-    const double2 r = vi ? ri : ra;
+    const double2 r = ld_rec(rec + j);
     a[0] = r.x;
     if (D > 1) a[D - 1] = r.y;
-    return vi ? 2 : (va ? 1 : 0);
+    return rec_valid(r) ? 1 : 0;
 }
 
 constexpr int kFusedThreads = kTileThreads + 32;      // 8 compute warps + the look-back warp
 
 template <int D>
-__global__ void __launch_bounds__(kFusedThreads, 3) iir_tile_fused_kernel(const IirPass P, const IirCoef c, const IirCoef ct, const double* __restrict__ ppow,
+__global__ void __launch_bounds__(kFusedThreads, 768 / kTileThreads) iir_tile_fused_kernel(const IirPass P, const IirCoef c, const IirCoef ct, const double* __restrict__ ppow,
                                                                         const IirLookback S) {
     extern __shared__ double tile_sm[];
     __shared__ double red[kTileThreads / 32][2];
     __shared__ double wtot[kTileThreads / 32][2];
-    __shared__ double e_sh[2], sin_sh[2];
+    __shared__ double sin_sh[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // Tile id = linear CTA index: CTAs are dispatched in index order, so every predecessor of a running CTA is running or done
     // (the assumption cub::DeviceScan's decoupled look-back makes).
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(kFusedThreads, 3) iir_tile_fused_kernel(const 
     const int s = (int)(tk / n_tiles);
     const long long tile = tk - (long long)s * n_tiles;
     const long long rec0 = (long long)s * n_tiles;
-    constexpr int f_agg = 1, f_incl = 2;
+    constexpr int f_agg = 1;
     if (warp == kTileThreads / 32) {
         // ---- look-back warp: the start state of this tile from the predecessors' records.  It needs nothing of this tile, so it
         //      runs WHILE the compute warps stage and scan their samples: its two or three L2 round trips are off the critical path.
@@ -427,10 +427,10 @@ __global__ void __launch_bounds__(kFusedThreads, 3) iir_tile_fused_kernel(const 
         bool done = false;
         long long j0 = tile - 1;
         while (!done) {
-            // the nearest 4 records are fetched at once WITHOUT blocking (a stable filter needs one or two: |Q| ~ 1e-15); the
-            // walk below then waits only for a record it really needs -- waiting for all of them would tie every CTA to the
-            // slowest of its predecessors' loads
-            constexpr int kWidth = 4;
+            // the nearest 8 records are fetched at once WITHOUT blocking (the loader's filters need one to four); the walk below
+            // then waits only for a record it really needs -- waiting for all of them would tie every CTA to the slowest of
+            // its predecessors' loads
+            constexpr int kWidth = 8;
             const long long j = j0 - lane;
             int f = 0;
             double a[D];
@@ -453,8 +453,6 @@ __global__ void __launch_bounds__(kFusedThreads, 3) iir_tile_fused_kernel(const 
                     const double x0 = sweep_read(P, base, dc, 0);
 #pragma unroll
                     for (int q = 0; q < D; ++q) al[q] = c.zi[q] * x0;
-                    done = true;
-                } else if (fl == f_incl) {
                     done = true;
                 }
 #pragma unroll
@@ -490,18 +488,7 @@ __global__ void __launch_bounds__(kFusedThreads, 3) iir_tile_fused_kernel(const 
 #pragma unroll
             for (int i = 0; i < D; ++i) sin_sh[i] = acc[i];
         }
-        asm volatile("bar.sync 2, %0;" ::"n"(kFusedThreads) : "memory");      // rendezvous: e_sh (compute warps) and sin_sh are both in place
-        if (lane == 0) {
-            double o[2] = {0.0, 0.0};
-#pragma unroll
-            for (int i = 0; i < D; ++i) {
-                double v = e_sh[i];
-#pragma unroll
-                for (int q = 0; q < D; ++q) v = fma(ct.pw[0][i * D + q], acc[q], v);
-                o[i] = v;
-            }
-            st_rec(S.rec + (rec0 + tile) * 2 + 1, o[0], o[1]);
-        }
+        asm volatile("bar.sync 2, %0;" ::"n"(kFusedThreads) : "memory");      // rendezvous: sin_sh is in place
         return;
     }
     double z[D];
@@ -525,9 +512,8 @@ __global__ void __launch_bounds__(kFusedThreads, 3) iir_tile_fused_kernel(const 
             double acc = 0.0;
             for (int q = 0; q < kTileThreads / 32; ++q) acc += red[q][k];
             e[k] = acc;
-            e_sh[k] = acc;
         }
-        st_rec(S.rec + (rec0 + tile) * 2, e[0], e[1]);
+        st_rec(S.rec + rec0 + tile, e[0], e[1]);
     }
     // ---- inclusive scan of the zero-state pieces inside the warp:  v_l = sum_{l' <= l} P^(l-l') z_l'
     double v[D];
@@ -927,10 +913,10 @@ struct PreparedFilter {
 static std::mutex g_prep_mutex;
 static std::deque<PreparedFilter> g_prep_cache;
 
-// look-back records: one set per sweep of a call (2 sweeps per tiled filter), 2 x 16 bytes per (signal, tile)
+// look-back records: one set per sweep of a call (2 sweeps per tiled filter), 16 bytes per (signal, tile)
 static size_t lookback_bytes(int n_sig, long long tiles) {
     const size_t recs = (size_t)n_sig * (size_t)tiles;
-    return (size_t)2 * kMaxTiledFilters * recs * 2 * sizeof(double2) + 256;
+    return (size_t)2 * kMaxTiledFilters * recs * sizeof(double2) + 256;
 }
 
 
@@ -1110,7 +1096,7 @@ static int iir_run(double* d_x, int n_sig, int64_t n, int64_t sig_stride, int64_
     IirLookback LB;
     LB.rec = reinterpret_cast<double2*>(lb_base);
     LB.sweep = 0;
-    const size_t lb_set = (size_t)n_sig * tiles_max * 2;      // double2 per sweep
+    const size_t lb_set = (size_t)n_sig * tiles_max;          // double2 per sweep
     bool lb_cleared = false;
     std::vector<double> ppow_host;
 
@@ -1131,7 +1117,7 @@ static int iir_run(double* d_x, int n_sig, int64_t n, int64_t sig_stride, int64_
     // host-side preparation of every filter first (coefficients, zi, power tables), ONE upload, then only launches:
     // the device never waits for the host between sweeps
     std::vector<IirCoef> coefs(n_filt), coefs_tile(n_filt);
-    std::vector<char> use_tiled(n_filt, 0);
+    std::vector<char> use_tiled(n_filt, 0), fused_ok(n_filt, 0);
     std::vector<double> all_tables;
     for (int k = 0; k < n_filt; ++k) {
         // trailing zero taps do not change the filter but would change padlen: the caller passes ntaps = max(len(a), len(b))
@@ -1173,6 +1159,12 @@ static int iir_run(double* d_x, int n_sig, int64_t n, int64_t sig_stride, int64_
         }
         const long long L = n + 2LL * coefs[k].e;
         use_tiled[k] = tiled_mode && coefs[k].d <= 2 && t_stride == 1 && k < kMaxTiledFilters && L >= kTile;
+        {       // the look-back sums Q^k e(t-1-k) until |Q^k| < 1e-30: worth it only when that is a handful of records
+            double q8 = 0.0;
+            if (coefs[k].d <= 2)
+                for (int i = 0; i < coefs[k].d * coefs[k].d; ++i) q8 = std::max(q8, std::fabs(coefs_tile[k].pw[3][i]));
+            fused_ok[k] = q8 < 1e-3;
+        }
         if (use_tiled[k]) {
             all_tables.resize((size_t)(k + 1) * kPpowEntries * 4, 0.0);
             memcpy(all_tables.data() + (size_t)k * kPpowEntries * 4, ppow_host.data(), ppow_host.size() * sizeof(double));
@@ -1206,7 +1198,7 @@ static int iir_run(double* d_x, int n_sig, int64_t n, int64_t sig_stride, int64_
         double* d_ppow = ppow_dev + (size_t)k * kPpowEntries * 4;
         auto sweep = [&](const IirPass& Pp) -> int {
             if (!tiled) return run_sweep_d(c.d, Pp, c, st);
-            if (!fused_mode) return c.d == 1 ? run_sweep_tiled<1>(Pp, c, ct, d_ppow, st) : run_sweep_tiled<2>(Pp, c, ct, d_ppow, st);
+            if (!fused_mode || !fused_ok[k]) return c.d == 1 ? run_sweep_tiled<1>(Pp, c, ct, d_ppow, st) : run_sweep_tiled<2>(Pp, c, ct, d_ppow, st);
             if (!lb_cleared) {      // every sweep of the call has its own records: all of them preset to "empty" (all-ones) once
                 int n_tiled = 0;
                 for (int q = 0; q < n_filt; ++q) n_tiled += use_tiled[q] ? 1 : 0;

@@ -178,7 +178,7 @@ def test_decimate_signals_object_semantics():
 
 @pytest.mark.parametrize("n,fs", [(8192 * 3 + 517, 1024.0), (8192, 256.0), (50000, 256.0)])
 def test_long_signals_take_the_tiled_path(n, fs):
-    """Signals longer than one 8192-sample tile run through the coalesced tiled kernels (biquads, unit time stride);
+    """Signals longer than one tile run through the coalesced tiled kernels (biquads, unit time stride);
     compare with SciPy's filtfilt cascade as dataloader.py:788-792 applies it, and with the thread-per-chunk kernels."""
     import os
     import torch
@@ -194,6 +194,28 @@ def test_long_signals_take_the_tiled_path(n, fs):
     for q in (2, 8, 5):
         d_ref = signal.decimate(ref, q, ftype="fir", zero_phase=True, axis=1)
         assert relerr(frontend.decimate(got, q), d_ref) < TOL_SIGNAL
+
+
+@pytest.mark.parametrize("fc", [0.3, 0.02])
+def test_slowly_decaying_filter_over_many_tiles(fc):
+    """A high-pass far below the loader's 1 Hz: the state forgets slowly, so the tile start states reach back over many tiles
+    (fc = 0.3 Hz: a look-back of ~20 aggregates in rounds of 8; fc = 0.02 Hz: |Q^8| >= 1e-3, the three-kernel path with its carry
+    kernel).  Against scipy.signal.filtfilt, and bit-reproducible."""
+    import torch
+    from hyperscanning_signal_analysis_b200 import frontend
+    fs, n = 1024.0, 4096 * 40 + 333
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((4, n)).cumsum(axis=1) * 0.05 + 10.0 * rng.standard_normal((4, n))
+    b, a = signal.butter(2, fc, "high", fs=fs)
+    ref = signal.filtfilt(b, a, x, axis=1)
+    xd = torch.from_numpy(x).cuda()
+    y1, y2 = xd.clone(), xd.clone()
+    frontend.filtfilt_cascade_(y1, [(b, a)], remove_dc=False)
+    frontend.filtfilt_cascade_(y2, [(b, a)], remove_dc=False)
+    assert torch.equal(y1, y2)
+    # filtfilt through a pole at 1 - 1e-4 amplifies rounding differently in any two implementations: SciPy's own result moves by
+    # ~1e-8 relative when the same recurrence is evaluated in a different order
+    assert relerr(y1.cpu().numpy(), ref) < (TOL_SIGNAL if fc > 0.1 else 1e-6)
 
 
 def test_cfg4_full_size_properties():

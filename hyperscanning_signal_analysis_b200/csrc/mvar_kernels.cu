@@ -611,13 +611,22 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, const unsig
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <int KC>      // column tiles per warp: 3 (up to 48 column tiles with 16 warps), 6 (up to 96)
-__global__ void __launch_bounds__(512, 1) lagcov_mma_kernel(const K3Params P, const int ld) {
+__global__ void __launch_bounds__(512, 1) lagcov_mma_kernel(const K3Params P, const int ld, const int n_full, const int n_parts, const int wpp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long stage_bar;
     double* xs = reinterpret_cast<double*>(smem_raw);                 // [40][ld], channel-major, zero padded
     const int m = P.m, n = P.n, p = P.p;
-    const int w = blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    // CTAs 0 .. n_full - 1 take a whole window each (full waves of the grid).  The windows of the last, partial wave are split over
+    // n_parts CTAs each: part q runs the column tiles of warps q wpp .. (q + 1) wpp - 1 of a whole-window CTA -- the same tiles by
+    // the same instructions (bit-identical results), but with the SM's tensor pipe to itself the tail takes 1 / (warps per
+    // sub-partition) of a full wave instead of a full wave for a handful of windows.
+    const bool split = (int)blockIdx.x >= n_full;
+    const int w = split ? n_full + ((int)blockIdx.x - n_full) / n_parts : (int)blockIdx.x;
+    const int part = split ? ((int)blockIdx.x - n_full) % n_parts : 0;
+    const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int warp_cta = threadIdx.x >> 5;
+    const int warp = split ? part * wpp + warp_cta : warp_cta;        // the whole-window warp whose tiles this warp computes
+    const bool warp_on = !split || (warp_cta < wpp && warp < nwarps);
     const int g4 = lane >> 2, t4 = lane & 3;
     const int TA = (m + 7) >> 3;                                        // row / column tiles actually populated
     const int n_cols = TA * (p + 1);
@@ -633,7 +642,7 @@ __global__ void __launch_bounds__(512, 1) lagcov_mma_kernel(const K3Params P, co
 #pragma unroll
     for (int u = 0; u < KC; ++u) {
         const int c = warp * KC + u;
-        okc[u] = c < n_cols;
+        okc[u] = warp_on && c < n_cols;
         lag[u] = okc[u] ? c / TA : 0;
         tb[u] = okc[u] ? c - lag[u] * TA : 0;
     }
@@ -652,7 +661,7 @@ __global__ void __launch_bounds__(512, 1) lagcov_mma_kernel(const K3Params P, co
         __syncthreads();                                               // previous trial's products are done with xs (and the barrier is initialised)
         if (rows_aligned && (off & 1) == 0) {
             // TMA path: warp 0 issues one bulk copy per channel row (n * 8 bytes each), all threads wait on the transaction barrier
-            if (warp == 0) {
+            if (warp_cta == 0) {
                 fence_proxy_async();                                   // the generic-proxy reads of the previous trial precede these async writes
                 if (lane == 0) mbar_expect_tx(&stage_bar, (unsigned)(m * n * sizeof(double)));
                 __syncwarp();
@@ -661,7 +670,7 @@ __global__ void __launch_bounds__(512, 1) lagcov_mma_kernel(const K3Params P, co
             mbar_wait(&stage_bar, stage_phase);
             stage_phase ^= 1;
         } else
-        for (int r = warp; r < m; r += nwarps) {                       // one warp per channel row: coalesced
+        for (int r = warp_cta; r < m; r += nwarps) {                   // one warp per channel row: coalesced
             const double* src = xu + (size_t)r * P.ch_stride;
             double* dst = xs + (size_t)r * ld;
             for (int t0 = lane; t0 < n; t0 += 8 * 32) {
@@ -889,7 +898,18 @@ int launch_lagcov(const K3Params& P, cudaStream_t stream) {
             auto kern = kc == 3 ? lagcov_mma_kernel<3> : lagcov_mma_kernel<6>;
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
             if (e != cudaSuccess) return set_error(HS_ERR_CUDA, "lagcov: %s", cudaGetErrorString(e));
-            kern<<<P.n_win, nwarps * 32, smem_mma, stream>>>(P, ld);
+            // last, partial wave: its windows are split over several CTAs (see the kernel)
+            int per_sm = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nwarps * 32, smem_mma) != cudaSuccess || per_sm < 1) per_sm = 1;
+            const int slots = device_sm_count() * per_sm;
+            const int rem = P.n_win % slots;
+            int n_parts = rem ? slots / rem : 1;
+            if (n_parts > nwarps) n_parts = nwarps;
+            const int wpp = (nwarps + n_parts - 1) / n_parts;
+            n_parts = (nwarps + wpp - 1) / wpp;
+            const int n_full = n_parts > 1 ? P.n_win - rem : P.n_win;
+            const int grid = n_full + (P.n_win - n_full) * n_parts;
+            kern<<<grid, nwarps * 32, smem_mma, stream>>>(P, ld, n_full, n_parts, wpp);
             return check_launch("lagcov_mma_kernel");
         }
     }

@@ -290,7 +290,8 @@ def measure_cfg2(args, lib, mtmvar, _lib, torch, dist, world, rank, local, with_
         res["roofline"] = {
             "kernel": "transfer_mma_kernel: A(f) assembly + complex 38x38 block Gauss-Jordan on the FP64 tensor pipe (DMMA m8n8k4) + |H|^2, "
                       "599*256 matrices per launch",
-            "bound": "fp64", "achieved": k5_tflops, "peak": dfma_peak, "unit": "TFLOP/s", "frac": k5_tflops / dfma_peak if dfma_peak else None,
+            "bound": "tensor", "pipe": "fp64 (DMMA m8n8k4: the only tensor-pipe type for float64; tcgen05 has no f64 kind)",
+            "achieved": k5_tflops, "peak": dfma_peak, "unit": "TFLOP/s", "frac": k5_tflops / dfma_peak if dfma_peak else None,
             "peak_source": "hs_measure_dfma_tflops: register-only DFMA loop on all SMs, measured in this run; DMMA m8n8k4 peaks at the same "
                            "rate (tools/fp64_peak.cu). MEASURED_PEAKS.json has no FP64 figure (its hbm_gbs is %s)" % peaks.get("hbm_gbs"),
             "flops_per_launch": fl["transfer"] * n_win, "ms_per_launch": k5_ms,
@@ -479,7 +480,7 @@ def measure_cfg5(args, lib, _lib, torch):
     tot_ms = t_k3 + t_k4 + t_k5
     out = {"workload": f"cfg5: {n_windows} windows x (128 ch x 512 samples x 100 epochs), p=15, F=512",
            "windows_per_s": n_windows / tot_ms * 1e3, "ms": {"lagcov": t_k3, "yule_walker": t_k4, "transfer+normalise": t_k5},
-           "lagcov_roofline": {"bound": "fp64", "achieved": f_k3 * n_windows / t_k3 * 1e-9, "peak": peak, "unit": "TFLOP/s",
+           "lagcov_roofline": {"bound": "tensor", "pipe": "fp64 (DMMA m8n8k4)", "achieved": f_k3 * n_windows / t_k3 * 1e-9, "peak": peak, "unit": "TFLOP/s",
                                "frac": f_k3 * n_windows / t_k3 * 1e-9 / peak, "flops_per_window": f_k3},
            "yule_walker_tflops": f_k4 * n_windows / t_k4 * 1e-9, "transfer_tflops": f_k5 * n_windows / t_k5 * 1e-9,
            "transfer_frac_of_fp64_peak": f_k5 * n_windows / t_k5 * 1e-9 / peak}

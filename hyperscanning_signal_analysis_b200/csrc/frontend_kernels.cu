@@ -414,47 +414,70 @@ __global__ void __launch_bounds__(kFusedThreads, 768 / kTileThreads) iir_tile_fu
     constexpr int f_agg = 1;
     if (warp == kTileThreads / 32) {
         // ---- look-back warp: the start state of this tile from the predecessors' records.  It needs nothing of this tile, so it
-        //      runs WHILE the compute warps stage and scan their samples: its two or three L2 round trips are off the critical path.
+        //      runs WHILE the compute warps stage and scan their samples.
         const double* base = P.in + (long long)s * P.in_sig_stride;
         const double dc = P.mean ? P.mean[s] : 0.0;
+        auto times_Q = [&](double (&Pw)[D][D]) -> double {      // Pw <- Pw Q; returns max |entry|
+            double nx[D][D], mx = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int q = 0; q < D; ++q) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int r = 0; r < D; ++r) v = fma(Pw[i][r], ct.pw[0][r * D + q], v);
+                    nx[i][q] = v;
+                    mx = fmax(mx, fabs(v));
+                }
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int q = 0; q < D; ++q) Pw[i][q] = nx[i][q];
+            return mx;
+        };
         double acc[D], Pw[D][D];
+        // 1. how many terms the sum has: until |Q^k| < 1e-30 (what lies further back changes the state by less than 1e-14 of an
+        //    ulp) or the beginning of the signal, whose term is the start state s_0 = zi * x_0 itself.  Depends on Q only.
+        long long n_terms = 0;
+        {
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = 0; j < D; ++j) Pw[i][j] = (i == j) ? 1.0 : 0.0;
+            double mx;
+            do {
+                ++n_terms;
+                mx = times_Q(Pw);
+            } while (mx >= 1e-30 && n_terms < tile + 1);
+        }
+        // 2. the terms, 32 at a time: every lane waits for ITS record (all of them are needed, and the waits overlap: one L2 round
+        //    trip after the last of them is published), then they are summed in order, nearest first
 #pragma unroll
         for (int i = 0; i < D; ++i) {
             acc[i] = 0.0;
 #pragma unroll
             for (int j = 0; j < D; ++j) Pw[i][j] = (i == j) ? 1.0 : 0.0;
         }
-        bool done = false;
-        long long j0 = tile - 1;
-        while (!done) {
-            // the nearest 8 records are fetched at once WITHOUT blocking (the loader's filters need one to four); the walk below
-            // then waits only for a record it really needs -- waiting for all of them would tie every CTA to the slowest of
-            // its predecessors' loads
-            constexpr int kWidth = 8;
-            const long long j = j0 - lane;
-            int f = 0;
+        for (long long k0 = 0; k0 < n_terms; k0 += 32) {
+            const long long k = k0 + lane, j = tile - 1 - k;
             double a[D];
 #pragma unroll
             for (int q = 0; q < D; ++q) a[q] = 0.0;
-            if (j >= 0 && lane < kWidth) f = rec_fetch<D>(S.rec, rec0 + j, a);
-            for (int l = 0; l < kWidth && !done; ++l) {
-                int fl = __shfl_sync(0xffffffffu, f, l);
-                const bool exists = (j0 - l >= 0);
-                if (exists && fl < f_agg) {          // not published yet: lane l waits for exactly this record
-                    if (lane == l) {
-                        do { f = rec_fetch<D>(S.rec, rec0 + j, a); } while (f < f_agg);
-                    }
-                    fl = __shfl_sync(0xffffffffu, f, l);
+            if (k < n_terms) {
+                if (j >= 0) {
+                    while (rec_fetch<D>(S.rec, rec0 + j, a) < f_agg) {}
+                } else {            // beginning of the signal: s_0 = zi * x_0 (the first sample of the extended sweep)
+                    const double x0 = sweep_read(P, base, dc, 0);
+#pragma unroll
+                    for (int q = 0; q < D; ++q) a[q] = c.zi[q] * x0;
                 }
+            }
+            __syncwarp();
+            const int cnt = (int)((n_terms - k0 < 32) ? (n_terms - k0) : 32);
+            for (int l = 0; l < cnt; ++l) {
                 double al[D];
 #pragma unroll
                 for (int q = 0; q < D; ++q) al[q] = __shfl_sync(0xffffffffu, a[q], l);
-                if (!exists) {      // beginning of the signal: s_0 = zi * x_0 (the first sample of the extended sweep)
-                    const double x0 = sweep_read(P, base, dc, 0);
-#pragma unroll
-                    for (int q = 0; q < D; ++q) al[q] = c.zi[q] * x0;
-                    done = true;
-                }
 #pragma unroll
                 for (int i = 0; i < D; ++i) {
                     double v = acc[i];
@@ -462,27 +485,8 @@ __global__ void __launch_bounds__(kFusedThreads, 768 / kTileThreads) iir_tile_fu
                     for (int q = 0; q < D; ++q) v = fma(Pw[i][q], al[q], v);
                     acc[i] = v;
                 }
-                if (!done) {           // Pw <- Pw Q
-                    double nx[D][D], mx = 0.0;
-#pragma unroll
-                    for (int i = 0; i < D; ++i)
-#pragma unroll
-                        for (int q = 0; q < D; ++q) {
-                            double v = 0.0;
-#pragma unroll
-                            for (int r = 0; r < D; ++r) v = fma(Pw[i][r], ct.pw[0][r * D + q], v);
-                            nx[i][q] = v;
-                            mx = fmax(mx, fabs(v));
-                        }
-#pragma unroll
-                    for (int i = 0; i < D; ++i)
-#pragma unroll
-                        for (int q = 0; q < D; ++q) Pw[i][q] = nx[i][q];
-                    // |Q^k| < 1e-30: what lies further back changes the state by less than 1e-14 of an ulp
-                    if (mx < 1e-30) done = true;
-                }
+                times_Q(Pw);
             }
-            j0 -= kWidth;
         }
         if (lane == 0) {
 #pragma unroll

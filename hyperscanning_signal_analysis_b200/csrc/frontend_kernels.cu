@@ -404,12 +404,14 @@ __global__ void __launch_bounds__(kFusedThreads, 768 / kTileThreads) iir_tile_fu
     __shared__ double wtot[kTileThreads / 32][2];
     __shared__ double sin_sh[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // Tile id = linear CTA index: CTAs are dispatched in index order, so every predecessor of a running CTA is running or done
-    // (the assumption cub::DeviceScan's decoupled look-back makes).
+    // CTAs are dispatched in index order, so every predecessor of a running CTA (a lower index) is running or done (the assumption
+    // cub::DeviceScan's decoupled look-back makes).  Signal-minor order: CTA b = tile (b / n_sig) of signal (b % n_sig), so the
+    // tiles a look-back reads belong to CTAs n_sig, 2 n_sig, ... positions earlier in the dispatch order -- they have a head start
+    // instead of having been launched in the same instant, and their aggregates are usually there when the look-back asks.
     const unsigned tk = blockIdx.x;
     const long long n_tiles = P.n_chunks;
-    const int s = (int)(tk / n_tiles);
-    const long long tile = tk - (long long)s * n_tiles;
+    const int s = (int)(tk % (unsigned)P.n_sig);
+    const long long tile = tk / (unsigned)P.n_sig;
     const long long rec0 = (long long)s * n_tiles;
     constexpr int f_agg = 1;
     if (warp == kTileThreads / 32) {

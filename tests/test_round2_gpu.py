@@ -237,6 +237,28 @@ def test_more_windows_than_resident_slots(mv, m, p):
         assert relerr(ff[w], ref) < TOL_MODEL, w
 
 
+@pytest.mark.parametrize("n_win", [1, 7, 75, 149, 160, 222, 296, 303])
+def test_lagcov_last_wave_split_is_bit_identical(mv, n_win):
+    """K3 splits the windows of the last, partial wave of its grid over several CTAs (1 ... 15 parts, depending on how many windows
+    are left over after the full waves of one CTA per SM).  Every part computes the same tiles with the same instruction sequence
+    as a whole-window CTA: R of a window must not depend on how many other windows the launch holds -- bit for bit -- and must be
+    the reference's biased lag covariance (mtmvar.py:57-59, 72-73)."""
+    import torch
+    m, n, p, hop = 38, 512, 8, 64
+    rng = np.random.default_rng(123)
+    x = rng.standard_normal((m, hop * 303 + n))
+    xd = torch.from_numpy(x).cuda()
+    offs = torch.arange(n_win, dtype=torch.int64, device="cuda") * hop
+    R = mv.batched_lagcov(xd, offs, x.shape[1], n_win, 1, m, n, p)
+    for w in sorted({0, n_win // 2, max(n_win - 8, 0), n_win - 1}):
+        alone = mv.batched_lagcov(xd, offs[w:w + 1].clone(), x.shape[1], 1, 1, m, n, p)
+        assert torch.equal(R[w], alone[0]), w
+    w = n_win - 1
+    xw = x[:, w * hop:w * hop + n]
+    ref = np.stack([xw[:, :n - L] @ xw[:, L:].T / n for L in range(p + 1)])
+    assert relerr(R[w].cpu().numpy(), ref) < 1e-12
+
+
 @pytest.mark.parametrize("m,F", [(41, 3), (48, 4), (64, 2)])
 def test_partial_coherence_more_than_40_channels(mv, m, F):
     """partial_coherence / dDTF beyond the register-tile limit (pcoh_generic_kernel: pivoted Gauss-Jordan in place in the output, the

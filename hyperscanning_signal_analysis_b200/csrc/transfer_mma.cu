@@ -226,11 +226,9 @@ __device__ __forceinline__ void mma_inverse4_adj(const MmaCtx& x, const int K0, 
 //      loaded in that form straight from the Re / Im planes; computed operands take their other component from lane ^ 16.
 //      det = (D adj)[j][j] = sum_i D[j][i] adj[i][j]: one term per lane, summed over i by two butterfly rounds.
 //      31 FP64 instructions + 14 shuffles per block step against 84 + 16 for mma_inverse4_adj.
-__device__ __forceinline__ void mma_inverse4_split(const MmaCtx& x, const int K0, const int buf) {
+__device__ __forceinline__ void mma_inverse4_split(const MmaCtx& x, const double* __restrict__ Dr, const double* __restrict__ Di) {
     MmaGroupSmem* gs = x.gs;
     const int s = x.lane >> 4, i = (x.lane >> 2) & 3, j = x.lane & 3;
-    const double* Dr = gs->u.p.Craw[buf][0] + K0 * 4;
-    const double* Di = gs->u.p.Craw[buf][1] + K0 * 4;
     const double* D1 = s ? Di : Dr;                    // plane of the component this lane produces
     const double* D2 = s ? Dr : Di;
     const int neg = s ? 0 : (int)0x80000000;           // the Re lanes take -Im of a second operand
@@ -378,7 +376,7 @@ __device__ __forceinline__ void mma_tile_steps(double (&c)[T][T][2], const int m
         if (ADJ == 4) {
             mma_inverse4_newton(x, K0, h, pv, pk);
         } else {
-            if (ADJ == 3) mma_inverse4_split(x, K0, h);
+            if (ADJ == 3) mma_inverse4_split(x, gs->u.p.Craw[h][0] + K0 * 4, gs->u.p.Craw[h][1] + K0 * 4);
             else if (ADJ == 2) mma_inverse4_adj<false>(x, K0, h, det);
             else if (ADJ == 1) mma_inverse4_adj<true>(x, K0, h, det);
             else mma_inverse4(x, K0, h);
@@ -446,10 +444,97 @@ __device__ __forceinline__ void mma_tile_steps(double (&c)[T][T][2], const int m
     }
 }
 
+// ---- ADJ == 5: the same two block steps with the pivot-block inverse taken ONE STEP AHEAD inside the warp.  The diagonal tile that
+//      holds the next pivot block is updated first; its 4 x 4 block (own component) goes to gs->Dblk, one group barrier later both
+//      warps hold both components and run the cofactor inverse for the NEXT step -- 31 FP64 instructions + 14 shuffles that depend on
+//      nothing else in flight -- while the other 48 update DMMAs of THIS step are issued around them.  The chain's turns at the FP64 pipe
+//      (50 - 100 cycles each behind the other warps' DMMAs) no longer sit between a step's hand-over and its first DMMA.  Same
+//      operations on the same values as ADJ == 3: bit-identical results.
+template <int T, int tn>
+__device__ __forceinline__ void mma_publish_next(const double (&c)[T][T][2], const int hn, const MmaCtx& x) {
+    if ((x.g4 >> 2) == hn && (x.t4 >> 1) == hn)
+        *reinterpret_cast<double2*>(&x.gs->Dblk[x.part][(x.g4 & 3) * 4 + 2 * (x.t4 & 1)]) = make_double2(c[tn][tn][0], c[tn][tn][1]);
+}
+
+template <int T, int t>
+__device__ __forceinline__ void mma_tile_steps_la(double (&c)[T][T][2], const int m, const MmaCtx& x) {
+    MmaGroupSmem* gs = x.gs;
+    const int fo = x.g4 * 4 + x.t4;
+    const int sgn = x.part ? 0 : (int)0x80000000;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int K0 = 8 * t + 4 * h;
+        if (K0 >= m) break;
+        mma_extract<T, t>(c, h, x);
+        mma_group_sync(x);
+        if (t == 0 && h == 0) mma_inverse4_split(x, gs->u.p.Craw[0][0], gs->u.p.Craw[0][1]);      // nothing to look ahead from
+        const double2 pv = gs->u.p.P[x.part][x.t4 * 4 + (x.g4 >> 1)];
+        const double2 pk = gs->u.p.P[x.part][(x.g4 & 3) * 4 + x.t4];
+        double a0[T], a1[T];
+        {
+            const bool odd = x.g4 & 1;
+            const double bB1 = odd ? -pv.y : -pv.x;
+            const double bB2 = odd ? -pv.x : pv.y;
+            const double* Cr = gs->u.p.Craw[h][0] + fo;
+            const double* Ci = gs->u.p.Craw[h][1] + fo;
+#pragma unroll
+            for (int ta = 0; ta < T; ++ta) {
+                double l0 = 0.0, l1 = 0.0;
+                dmma884(l0, l1, Cr[32 * ta], bB1);
+                dmma884(l0, l1, Ci[32 * ta], bB2);
+                a0[ta] = l0;
+                a1[ta] = l1;
+            }
+            if ((x.g4 >> 2) == h) {
+                const bool dg = (x.g4 & 3) == x.t4;
+                a0[t] = pk.x - (dg ? 1.0 : 0.0);
+                a1[t] = pk.y;
+            }
+#pragma unroll
+            for (int ta = 0; ta < T; ++ta) a1[ta] = flip_sign(a1[ta], sgn);
+        }
+        const double* Ua = gs->u.p.Rraw[h][x.part] + x.t4 * kUS + x.g4;
+        const double* Ub = gs->u.p.Rraw[h][x.part ^ 1] + x.t4 * kUS + x.g4;
+        double b0[T], b1[T];
+#pragma unroll
+        for (int tb = 0; tb < T; ++tb) {
+            b0[tb] = Ua[8 * tb];
+            b1[tb] = Ub[8 * tb];
+        }
+        // the diagonal tile that holds the NEXT pivot block first, then that block's inverse next to the rest of the update
+        constexpr bool kLastTile = (t + 1 >= T);
+        const int tn = (h == 0 || kLastTile) ? t : t + 1;
+        const bool has_next = (K0 + 4 < m) && !(h == 1 && kLastTile);
+        if (has_next) {
+            if (h == 0) {
+                dmma884(c[t][t][0], c[t][t][1], a0[t], b0[t]);
+                dmma884(c[t][t][0], c[t][t][1], a1[t], b1[t]);
+                mma_publish_next<T, t>(c, 1, x);
+            } else if constexpr (!kLastTile) {
+                dmma884(c[t + 1][t + 1][0], c[t + 1][t + 1][1], a0[t + 1], b0[t + 1]);
+                dmma884(c[t + 1][t + 1][0], c[t + 1][t + 1][1], a1[t + 1], b1[t + 1]);
+                mma_publish_next<T, t + 1>(c, 0, x);
+            }
+            mma_group_sync(x);                     // both components of the next block are in Dblk (and this warp is past its pv / pk loads)
+            mma_inverse4_split(x, gs->Dblk[0], gs->Dblk[1]);
+        }
+#pragma unroll
+        for (int ta = 0; ta < T; ++ta) {
+#pragma unroll
+            for (int tb = 0; tb < T; ++tb) {
+                if (has_next && ta == tb && ta == tn) continue;      // done above
+                dmma884(c[ta][tb][0], c[ta][tb][1], a0[ta], b0[tb]);
+                dmma884(c[ta][tb][0], c[ta][tb][1], a1[ta], b1[tb]);
+            }
+        }
+    }
+}
+
 template <int T, int t, int ADJ>
 __device__ __forceinline__ void mma_all_tiles(double (&c)[T][T][2], const int m, const MmaCtx& x) {
     if constexpr (t < T) {
-        mma_tile_steps<T, t, ADJ>(c, m, x);
+        if constexpr (ADJ == 5) mma_tile_steps_la<T, t>(c, m, x);
+        else mma_tile_steps<T, t, ADJ>(c, m, x);
         mma_all_tiles<T, t + 1, ADJ>(c, m, x);
     }
 }
@@ -1292,6 +1377,8 @@ int launch_mma_t(const K5Params& P, int sm_count, cudaStream_t stream) {
     constexpr bool kMain = (T == 5 && NG == 6);
     auto kern = (adj == 4) ? transfer_mma_kernel<T, NG, 4> : (adj == 3) ? transfer_mma_kernel<T, NG, 3> : (adj == 2 && kMain) ? transfer_mma_kernel<T, NG, kMain ? 2 : 0>
               : (adj == 1 && kMain) ? transfer_mma_kernel<T, NG, kMain ? 1 : 0> : transfer_mma_kernel<T, NG, 0>;
+#elif defined(HS_K5_LOOKAHEAD)
+    auto kern = transfer_mma_kernel<T, NG, 5>;       // the same with the inverse taken one step ahead (mma_tile_steps_la)
 #else
     auto kern = transfer_mma_kernel<T, NG, 3>;       // cofactor pivot-block inverse, Re / Im split over the half-warps, for every tile count
 #endif

@@ -1375,7 +1375,8 @@ int launch_mma_t(const K5Params& P, int sm_count, cudaStream_t stream) {
 #ifdef HS_EXPERIMENT
     static const int adj = exp_env_int("HS_K5_ADJ", 3);
     constexpr bool kMain = (T == 5 && NG == 6);
-    auto kern = (adj == 4) ? transfer_mma_kernel<T, NG, 4> : (adj == 3) ? transfer_mma_kernel<T, NG, 3> : (adj == 2 && kMain) ? transfer_mma_kernel<T, NG, kMain ? 2 : 0>
+    constexpr bool kMain5 = (T == 5);       // the look-ahead variant: measured at 4 and 6 groups
+    auto kern = (adj == 5 && kMain5) ? transfer_mma_kernel<T, NG, kMain5 ? 5 : 3> : (adj == 4) ? transfer_mma_kernel<T, NG, 4> : (adj == 3) ? transfer_mma_kernel<T, NG, 3> : (adj == 2 && kMain) ? transfer_mma_kernel<T, NG, kMain ? 2 : 0>
               : (adj == 1 && kMain) ? transfer_mma_kernel<T, NG, kMain ? 1 : 0> : transfer_mma_kernel<T, NG, 0>;
 #elif defined(HS_K5_LOOKAHEAD)
     auto kern = transfer_mma_kernel<T, NG, 5>;       // the same with the inverse taken one step ahead (mma_tile_steps_la)

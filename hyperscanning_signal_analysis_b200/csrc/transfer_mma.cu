@@ -450,13 +450,31 @@ __device__ __forceinline__ void mma_tile_steps(double (&c)[T][T][2], const int m
 //      nothing else in flight -- while the other 48 update DMMAs of THIS step are issued around them.  The chain's turns at the FP64 pipe
 //      (50 - 100 cycles each behind the other warps' DMMAs) no longer sit between a step's hand-over and its first DMMA.  Same
 //      operations on the same values as ADJ == 3: bit-identical results.
+//      Written plainly (ADJ == 5, TIED = false) this does not happen: ptxas believes a DFMA to be short, keeps the whole chain in front
+//      of the 48 independent DMMAs (~200 chain instructions, then 46 DMMAs in a row in the SASS) and the variant is slower (6.11 vs
+//      4.91 ms with 6 groups and the spills of the longer live ranges, 5.16 vs 5.09 ms with 4 groups and none).  ADJ == 6 (TIED = true)
+//      therefore cuts the chain into five pieces and gives each piece a lane / address offset computed from the last accumulator of
+//      the DMMA batch (one column of the update, its two B fragments loaded in front of it: 16 registers less than keeping all ten)
+//      that precedes it in the source: a value that is always 0 but that the compiler cannot fold (tie_zero), i.e. a true data
+//      dependency.  The SASS then alternates chain instructions and DMMAs.  Measured: in the HS_EXPERIMENT build 4.98 -> 4.82 ms with
+//      6 groups and 5.09 -> 4.79 ms with 4; compiled as the product kernel 4.91 -> 4.91 / 4.94 ms (two block steps per tile unrolled:
+//      9000 instead of 7100 instructions, 240 instead of 76 bytes of spill stores).  With the chain hidden the kernel is no faster
+//      than with the chain exposed: the FP64 pipe's turns, not the chain's latency, are what a block step costs.  Both variants stay
+//      in HS_EXPERIMENT builds (HS_K5_ADJ = 5 / 6); the product kernel is ADJ == 3.
 template <int T, int tn>
 __device__ __forceinline__ void mma_publish_next(const double (&c)[T][T][2], const int hn, const MmaCtx& x) {
     if ((x.g4 >> 2) == hn && (x.t4 >> 1) == hn)
         *reinterpret_cast<double2*>(&x.gs->Dblk[x.part][(x.g4 & 3) * 4 + 2 * (x.t4 & 1)]) = make_double2(c[tn][tn][0], c[tn][tn][1]);
 }
 
-template <int T, int t>
+// An integer that is always 0 but that the compiler cannot prove to be (squares are 0 or 1 mod 4): a data dependency on `v` without a
+// change of value.  Used by the TIED look-ahead to pin pieces of the inverse chain BEHIND batches of update DMMAs in the SASS.
+__device__ __forceinline__ int tie_zero(const double v) {
+    const int hi = __double2hiint(v);
+    return (hi * hi) & 2;
+}
+
+template <int T, int t, bool TIED>
 __device__ __forceinline__ void mma_tile_steps_la(double (&c)[T][T][2], const int m, const MmaCtx& x) {
     MmaGroupSmem* gs = x.gs;
     const int fo = x.g4 * 4 + x.t4;
@@ -495,37 +513,113 @@ __device__ __forceinline__ void mma_tile_steps_la(double (&c)[T][T][2], const in
         }
         const double* Ua = gs->u.p.Rraw[h][x.part] + x.t4 * kUS + x.g4;
         const double* Ub = gs->u.p.Rraw[h][x.part ^ 1] + x.t4 * kUS + x.g4;
-        double b0[T], b1[T];
-#pragma unroll
-        for (int tb = 0; tb < T; ++tb) {
-            b0[tb] = Ua[8 * tb];
-            b1[tb] = Ub[8 * tb];
-        }
         // the diagonal tile that holds the NEXT pivot block first, then that block's inverse next to the rest of the update
         constexpr bool kLastTile = (t + 1 >= T);
         const int tn = (h == 0 || kLastTile) ? t : t + 1;
-        const bool has_next = (K0 + 4 < m) && !(h == 1 && kLastTile);
+        // T = ceil(m / 8): every block of the tiles before the last one has a successor (known at compile time: one code path)
+        const bool has_next = !kLastTile || ((K0 + 4 < m) && h == 0);
+        double b0[T], b1[T];
+        if (!TIED || !has_next) {       // the tied path loads a column's two fragments in front of that column's batch: 16 registers less
+#pragma unroll
+            for (int tb = 0; tb < T; ++tb) {
+                b0[tb] = Ua[8 * tb];
+                b1[tb] = Ub[8 * tb];
+            }
+        }
         if (has_next) {
             if (h == 0) {
-                dmma884(c[t][t][0], c[t][t][1], a0[t], b0[t]);
-                dmma884(c[t][t][0], c[t][t][1], a1[t], b1[t]);
+                const double u0 = TIED ? Ua[8 * t] : b0[t], u1 = TIED ? Ub[8 * t] : b1[t];
+                dmma884(c[t][t][0], c[t][t][1], a0[t], u0);
+                dmma884(c[t][t][0], c[t][t][1], a1[t], u1);
                 mma_publish_next<T, t>(c, 1, x);
             } else if constexpr (!kLastTile) {
-                dmma884(c[t + 1][t + 1][0], c[t + 1][t + 1][1], a0[t + 1], b0[t + 1]);
-                dmma884(c[t + 1][t + 1][0], c[t + 1][t + 1][1], a1[t + 1], b1[t + 1]);
+                const double u0 = TIED ? Ua[8 * (t + 1)] : b0[t + 1], u1 = TIED ? Ub[8 * (t + 1)] : b1[t + 1];
+                dmma884(c[t + 1][t + 1][0], c[t + 1][t + 1][1], a0[t + 1], u0);
+                dmma884(c[t + 1][t + 1][0], c[t + 1][t + 1][1], a1[t + 1], u1);
                 mma_publish_next<T, t + 1>(c, 0, x);
             }
             mma_group_sync(x);                     // both components of the next block are in Dblk (and this warp is past its pv / pk loads)
-            mma_inverse4_split(x, gs->Dblk[0], gs->Dblk[1]);
+            if (!TIED) mma_inverse4_split(x, gs->Dblk[0], gs->Dblk[1]);
         }
+        if (!TIED || !has_next) {
 #pragma unroll
-        for (int ta = 0; ta < T; ++ta) {
+            for (int ta = 0; ta < T; ++ta) {
 #pragma unroll
-            for (int tb = 0; tb < T; ++tb) {
-                if (has_next && ta == tb && ta == tn) continue;      // done above
-                dmma884(c[ta][tb][0], c[ta][tb][1], a0[ta], b0[tb]);
-                dmma884(c[ta][tb][0], c[ta][tb][1], a1[ta], b1[tb]);
+                for (int tb = 0; tb < T; ++tb) {
+                    if (has_next && ta == tb && ta == tn) continue;      // done above
+                    dmma884(c[ta][tb][0], c[ta][tb][1], a0[ta], b0[tb]);
+                    dmma884(c[ta][tb][0], c[ta][tb][1], a1[ta], b1[tb]);
+                }
             }
+        } else {
+            // the inverse chain of mma_inverse4_split in five pieces, a batch of update DMMAs in front of each of the last four; piece k
+            // takes a (zero) lane / address offset from the last accumulator of batch k - 1, so it cannot be scheduled before that batch
+            const int s2 = x.lane >> 4, ii = (x.lane >> 2) & 3, jj = x.lane & 3;
+            const double* Dr = gs->Dblk[0];
+            const double* Di = gs->Dblk[1];
+            const double* D1 = s2 ? Di : Dr;
+            const double* D2 = s2 ? Dr : Di;
+            const int neg = s2 ? 0 : (int)0x80000000;
+            const int r0 = (0 >= jj) ? 1 : 0, r1 = (1 >= jj) ? 2 : 1, r2 = (2 >= jj) ? 3 : 2;
+            const int c0 = (0 >= ii) ? 1 : 0, c1 = (1 >= ii) ? 2 : 1, c2 = (2 >= ii) ? 3 : 2;
+            double last = 0.0;
+            auto batch = [&](const int tb) {              // column tb of the update (without the tile done above)
+                if (tb < T) {
+                    const double u0 = Ua[8 * tb], u1 = Ub[8 * tb];
+#pragma unroll
+                    for (int ta = 0; ta < T; ++ta) {
+                        if (ta == tb && ta == tn) continue;
+                        dmma884(c[ta][tb][0], c[ta][tb][1], a0[ta], u0);
+                        dmma884(c[ta][tb][0], c[ta][tb][1], a1[ta], u1);
+                        last = c[ta][tb][0];
+                    }
+                }
+            };
+#define HS_LD1(R, C, vr, vi) const double vr = Dr[(R) * 4 + (C)], vi = Di[(R) * 4 + (C)]
+#define HS_LD2(R, C, v1, v2) const double v1 = D1[(R) * 4 + (C)], v2 = flip_sign(D2[(R) * 4 + (C)], neg)
+            // piece 0: operands and the 2 x 2 minors
+            HS_LD1(r1, c0, a10r, a10i); HS_LD1(r1, c1, a11r, a11i); HS_LD1(r1, c2, a12r, a12i);
+            HS_LD2(r2, c0, a20p, a20q); HS_LD2(r2, c1, a21p, a21q); HS_LD2(r2, c2, a22p, a22q);
+            const double m0 = fma(-a12i, a21q, fma(-a12r, a21p, fma(a11i, a22q, a11r * a22p)));
+            const double m1 = fma(-a12i, a20q, fma(-a12r, a20p, fma(a10i, a22q, a10r * a22p)));
+            const double m2 = fma(-a11i, a20q, fma(-a11r, a20p, fma(a10i, a21q, a10r * a21p)));
+            batch(0);
+            // piece 1: the other component of the minors, the signed cofactor (its operands are loaded here, behind the tie: short live ranges)
+            int z = tie_zero(last);
+            Dr += z;
+            Di += z;
+            HS_LD1(r0, c0, a00r, a00i); HS_LD1(r0, c1, a01r, a01i); HS_LD1(r0, c2, a02r, a02i);
+            const double m0o = flip_sign(__shfl_xor_sync(0xffffffffu, m0, 16 + z), neg);
+            const double m1o = flip_sign(__shfl_xor_sync(0xffffffffu, m1, 16 + z), neg);
+            const double m2o = flip_sign(__shfl_xor_sync(0xffffffffu, m2, 16 + z), neg);
+            double cf = fma(a02i, m2o, fma(a02r, m2, fma(-a01i, m1o, fma(-a01r, m1, fma(a00i, m0o, a00r * m0)))));
+            cf = flip_sign(cf, ((ii + jj) & 1) ? (int)0x80000000 : 0);
+            batch(1);
+            // piece 2: determinant
+            z = tie_zero(last);
+            Dr += z;
+            Di += z;
+            HS_LD1(jj, ii, djr, dji);
+#undef HS_LD1
+#undef HS_LD2
+            const double cfo = __shfl_xor_sync(0xffffffffu, cf, 16 + z);
+            double dt = fma(dji, flip_sign(cfo, neg), djr * cf);
+            dt += __shfl_xor_sync(0xffffffffu, dt, 4);
+            dt += __shfl_xor_sync(0xffffffffu, dt, 8);
+            batch(2);
+            // piece 3: 1 / |det|^2
+            z = tie_zero(last);
+            const double dto = __shfl_xor_sync(0xffffffffu, dt, 16 + z);
+            const double y = rcp_newton2(fma(dt, dt, dto * dto));
+            batch(3);
+            // piece 4: P = adj conj(det) / |det|^2
+            z = tie_zero(last);
+            const double u1 = s2 ? dto : dt, u2 = s2 ? -dt : dto;
+            const double pvn = fma(cfo, u2, cf * u1) * y;
+            reinterpret_cast<double*>(gs->u.p.P[x.part])[2 * (x.lane & 15) + s2 + z] = pvn;
+            __syncwarp();
+#pragma unroll
+            for (int tb = 4; tb < T; ++tb) batch(tb);
         }
     }
 }
@@ -533,7 +627,8 @@ __device__ __forceinline__ void mma_tile_steps_la(double (&c)[T][T][2], const in
 template <int T, int t, int ADJ>
 __device__ __forceinline__ void mma_all_tiles(double (&c)[T][T][2], const int m, const MmaCtx& x) {
     if constexpr (t < T) {
-        if constexpr (ADJ == 5) mma_tile_steps_la<T, t>(c, m, x);
+        if constexpr (ADJ == 5) mma_tile_steps_la<T, t, false>(c, m, x);
+        else if constexpr (ADJ == 6) mma_tile_steps_la<T, t, true>(c, m, x);
         else mma_tile_steps<T, t, ADJ>(c, m, x);
         mma_all_tiles<T, t + 1, ADJ>(c, m, x);
     }
@@ -1376,10 +1471,8 @@ int launch_mma_t(const K5Params& P, int sm_count, cudaStream_t stream) {
     static const int adj = exp_env_int("HS_K5_ADJ", 3);
     constexpr bool kMain = (T == 5 && NG == 6);
     constexpr bool kMain5 = (T == 5);       // the look-ahead variant: measured at 4 and 6 groups
-    auto kern = (adj == 5 && kMain5) ? transfer_mma_kernel<T, NG, kMain5 ? 5 : 3> : (adj == 4) ? transfer_mma_kernel<T, NG, 4> : (adj == 3) ? transfer_mma_kernel<T, NG, 3> : (adj == 2 && kMain) ? transfer_mma_kernel<T, NG, kMain ? 2 : 0>
+    auto kern = (adj == 6 && kMain5) ? transfer_mma_kernel<T, NG, kMain5 ? 6 : 3> : (adj == 5 && kMain5) ? transfer_mma_kernel<T, NG, kMain5 ? 5 : 3> : (adj == 4) ? transfer_mma_kernel<T, NG, 4> : (adj == 3) ? transfer_mma_kernel<T, NG, 3> : (adj == 2 && kMain) ? transfer_mma_kernel<T, NG, kMain ? 2 : 0>
               : (adj == 1 && kMain) ? transfer_mma_kernel<T, NG, kMain ? 1 : 0> : transfer_mma_kernel<T, NG, 0>;
-#elif defined(HS_K5_LOOKAHEAD)
-    auto kern = transfer_mma_kernel<T, NG, 5>;       // the same with the inverse taken one step ahead (mma_tile_steps_la)
 #else
     auto kern = transfer_mma_kernel<T, NG, 3>;       // cofactor pivot-block inverse, Re / Im split over the half-warps, for every tile count
 #endif

@@ -396,6 +396,87 @@ __device__ __forceinline__ int rec_fetch(const double2* rec, const long long j, 
 
 constexpr int kFusedThreads = kTileThreads + 32;      // 8 compute warps + the look-back warp
 
+// Start state of (signal s, tile) from the predecessors' aggregates (one warp; see the header comment).  acc = s_in.
+template <int D>
+__device__ __forceinline__ void lookback_start_state(const IirPass& P, const IirCoef& c, const IirCoef& ct, const IirLookback& S, const int s,
+                                                     const long long tile, const long long rec0, const int lane, double (&acc)[D]) {
+    constexpr int f_agg = 1;
+    // ---- look-back warp: the start state of this tile from the predecessors' records.  It needs nothing of this tile, so it
+    //      runs WHILE the compute warps stage and scan their samples.
+    const double* base = P.in + (long long)s * P.in_sig_stride;
+    const double dc = P.mean ? P.mean[s] : 0.0;
+    auto times_Q = [&](double (&Pw)[D][D]) -> double {      // Pw <- Pw Q; returns max |entry|
+        double nx[D][D], mx = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int q = 0; q < D; ++q) {
+                double v = 0.0;
+#pragma unroll
+                for (int r = 0; r < D; ++r) v = fma(Pw[i][r], ct.pw[0][r * D + q], v);
+                nx[i][q] = v;
+                mx = fmax(mx, fabs(v));
+            }
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int q = 0; q < D; ++q) Pw[i][q] = nx[i][q];
+        return mx;
+    };
+    double Pw[D][D];
+    // 1. how many terms the sum has: until |Q^k| < 1e-30 (what lies further back changes the state by less than 1e-14 of an
+    //    ulp) or the beginning of the signal, whose term is the start state s_0 = zi * x_0 itself.  Depends on Q only.
+    long long n_terms = 0;
+    {
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j < D; ++j) Pw[i][j] = (i == j) ? 1.0 : 0.0;
+        double mx;
+        do {
+            ++n_terms;
+            mx = times_Q(Pw);
+        } while (mx >= 1e-30 && n_terms < tile + 1);
+    }
+    // 2. the terms, 32 at a time: every lane waits for ITS record (all of them are needed, and the waits overlap: one L2 round
+    //    trip after the last of them is published), then they are summed in order, nearest first
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        acc[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) Pw[i][j] = (i == j) ? 1.0 : 0.0;
+    }
+    for (long long k0 = 0; k0 < n_terms; k0 += 32) {
+        const long long k = k0 + lane, j = tile - 1 - k;
+        double a[D];
+#pragma unroll
+        for (int q = 0; q < D; ++q) a[q] = 0.0;
+        if (k < n_terms) {
+            if (j >= 0) {
+                while (rec_fetch<D>(S.rec, rec0 + j, a) < f_agg) {}
+            } else {            // beginning of the signal: s_0 = zi * x_0 (the first sample of the extended sweep)
+                const double x0 = sweep_read(P, base, dc, 0);
+#pragma unroll
+                for (int q = 0; q < D; ++q) a[q] = c.zi[q] * x0;
+            }
+        }
+        __syncwarp();
+        const int cnt = (int)((n_terms - k0 < 32) ? (n_terms - k0) : 32);
+        for (int l = 0; l < cnt; ++l) {
+            double al[D];
+#pragma unroll
+            for (int q = 0; q < D; ++q) al[q] = __shfl_sync(0xffffffffu, a[q], l);
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                double v = acc[i];
+#pragma unroll
+                for (int q = 0; q < D; ++q) v = fma(Pw[i][q], al[q], v);
+                acc[i] = v;
+            }
+            times_Q(Pw);
+        }
+    }}
+
 template <int D>
 __global__ void __launch_bounds__(kFusedThreads, 768 / kTileThreads) iir_tile_fused_kernel(const IirPass P, const IirCoef c, const IirCoef ct, const double* __restrict__ ppow,
                                                                         const IirLookback S) {
@@ -413,83 +494,9 @@ __global__ void __launch_bounds__(kFusedThreads, 768 / kTileThreads) iir_tile_fu
     const int s = (int)(tk % (unsigned)P.n_sig);
     const long long tile = tk / (unsigned)P.n_sig;
     const long long rec0 = (long long)s * n_tiles;
-    constexpr int f_agg = 1;
     if (warp == kTileThreads / 32) {
-        // ---- look-back warp: the start state of this tile from the predecessors' records.  It needs nothing of this tile, so it
-        //      runs WHILE the compute warps stage and scan their samples.
-        const double* base = P.in + (long long)s * P.in_sig_stride;
-        const double dc = P.mean ? P.mean[s] : 0.0;
-        auto times_Q = [&](double (&Pw)[D][D]) -> double {      // Pw <- Pw Q; returns max |entry|
-            double nx[D][D], mx = 0.0;
-#pragma unroll
-            for (int i = 0; i < D; ++i)
-#pragma unroll
-                for (int q = 0; q < D; ++q) {
-                    double v = 0.0;
-#pragma unroll
-                    for (int r = 0; r < D; ++r) v = fma(Pw[i][r], ct.pw[0][r * D + q], v);
-                    nx[i][q] = v;
-                    mx = fmax(mx, fabs(v));
-                }
-#pragma unroll
-            for (int i = 0; i < D; ++i)
-#pragma unroll
-                for (int q = 0; q < D; ++q) Pw[i][q] = nx[i][q];
-            return mx;
-        };
-        double acc[D], Pw[D][D];
-        // 1. how many terms the sum has: until |Q^k| < 1e-30 (what lies further back changes the state by less than 1e-14 of an
-        //    ulp) or the beginning of the signal, whose term is the start state s_0 = zi * x_0 itself.  Depends on Q only.
-        long long n_terms = 0;
-        {
-#pragma unroll
-            for (int i = 0; i < D; ++i)
-#pragma unroll
-                for (int j = 0; j < D; ++j) Pw[i][j] = (i == j) ? 1.0 : 0.0;
-            double mx;
-            do {
-                ++n_terms;
-                mx = times_Q(Pw);
-            } while (mx >= 1e-30 && n_terms < tile + 1);
-        }
-        // 2. the terms, 32 at a time: every lane waits for ITS record (all of them are needed, and the waits overlap: one L2 round
-        //    trip after the last of them is published), then they are summed in order, nearest first
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-            acc[i] = 0.0;
-#pragma unroll
-            for (int j = 0; j < D; ++j) Pw[i][j] = (i == j) ? 1.0 : 0.0;
-        }
-        for (long long k0 = 0; k0 < n_terms; k0 += 32) {
-            const long long k = k0 + lane, j = tile - 1 - k;
-            double a[D];
-#pragma unroll
-            for (int q = 0; q < D; ++q) a[q] = 0.0;
-            if (k < n_terms) {
-                if (j >= 0) {
-                    while (rec_fetch<D>(S.rec, rec0 + j, a) < f_agg) {}
-                } else {            // beginning of the signal: s_0 = zi * x_0 (the first sample of the extended sweep)
-                    const double x0 = sweep_read(P, base, dc, 0);
-#pragma unroll
-                    for (int q = 0; q < D; ++q) a[q] = c.zi[q] * x0;
-                }
-            }
-            __syncwarp();
-            const int cnt = (int)((n_terms - k0 < 32) ? (n_terms - k0) : 32);
-            for (int l = 0; l < cnt; ++l) {
-                double al[D];
-#pragma unroll
-                for (int q = 0; q < D; ++q) al[q] = __shfl_sync(0xffffffffu, a[q], l);
-#pragma unroll
-                for (int i = 0; i < D; ++i) {
-                    double v = acc[i];
-#pragma unroll
-                    for (int q = 0; q < D; ++q) v = fma(Pw[i][q], al[q], v);
-                    acc[i] = v;
-                }
-                times_Q(Pw);
-            }
-        }
+        double acc[D];
+        lookback_start_state<D>(P, c, ct, S, s, tile, rec0, lane, acc);
         if (lane == 0) {
 #pragma unroll
             for (int i = 0; i < D; ++i) sin_sh[i] = acc[i];
@@ -592,6 +599,187 @@ __global__ void __launch_bounds__(kFusedThreads, 768 / kTileThreads) iir_tile_fu
         }
     }
 }
+
+// ------------------------------------------------------------------ K1, single-pass sweep with TWO tiles per CTA in a software pipeline
+// Same arithmetic as iir_tile_fused_kernel (bit-identical results), different schedule: a CTA owns two consecutive tiles A, B of a
+// signal.  Both tiles are brought in by cp.async (8-byte copies straight to their transposed slots: no registers, no waiting thread),
+// then  scan A | publish A | scan B | publish B | apply A | store A | apply B | store B  -- B's loads land under A's scan, A's look-back
+// (and the stores of A) under B's phases.  The DC removal of the first sweep moves from the staging to the two reads of a sample.
+// Measured on the cfg4 cascade (parity tests green, bit-reproducible): 3.77 ms with 2 x 4096 samples per CTA (three CTAs per SM) and
+// 4.08 ms with 2 x 2048 (six CTAs per SM) against 3.50 ms for one 4096-sample tile per CTA, six CTAs per SM: six independent CTAs
+// overlap their phases better than three pipelined ones, and smaller tiles pay for more look-back terms and barriers per byte.
+// HS_EXPERIMENT builds only (HS_IIR_TWO_TILES=1).
+#ifdef HS_EXPERIMENT
+
+__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+
+template <int D>
+__global__ void __launch_bounds__(kFusedThreads, 384 / kTileThreads) iir_tile_fused2_kernel(const IirPass P, const IirCoef c, const IirCoef ct,
+                                                                                            const double* __restrict__ ppow, const IirLookback S) {
+    extern __shared__ double tile_sm2[];                    // [2][kTilePer * kTileLd]
+    __shared__ double red[kTileThreads / 32][2];
+    __shared__ double wtot[2][kTileThreads / 32][2];
+    __shared__ double sin_sh[2][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned tk = blockIdx.x;                          // signal-minor order of the tile PAIRS (see iir_tile_fused_kernel)
+    const long long n_tiles = P.n_chunks;
+    const int s = (int)(tk % (unsigned)P.n_sig);
+    const long long tile0 = 2 * (long long)(tk / (unsigned)P.n_sig);
+    const int n_here = (tile0 + 1 < n_tiles) ? 2 : 1;
+    const long long rec0 = (long long)s * n_tiles;
+    if (warp == kTileThreads / 32) {
+        // look-back warp: the start states of A and B (B's first term is A's aggregate, published by this CTA's compute warps)
+        for (int q = 0; q < n_here; ++q) {
+            double acc[D];
+            lookback_start_state<D>(P, c, ct, S, s, tile0 + q, rec0, lane, acc);
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < D; ++i) sin_sh[q][i] = acc[i];
+            }
+            __syncwarp();
+            if (q == 0) asm volatile("bar.arrive 2, %0;" ::"n"(kFusedThreads) : "memory");
+            else asm volatile("bar.arrive 3, %0;" ::"n"(kFusedThreads) : "memory");
+        }
+        return;
+    }
+    const double* base = P.in + (long long)s * P.in_sig_stride;
+    const double dc = P.mean ? P.mean[s] : 0.0;
+    double dcq[2] = {0.0, 0.0};                              // what the scans still have to subtract from a staged sample
+    // ---- stage both tiles
+    for (int q = 0; q < n_here; ++q) {
+        double* sm = tile_sm2 + (size_t)q * kTilePer * kTileLd;
+        const long long u0 = (tile0 + q) * kTile;
+        const bool interior = P.in_t_stride == 1 && (P.forward ? (u0 >= P.e && u0 + kTile <= P.e + P.n_in) : (u0 + kTile <= P.L));
+        if (interior) {
+            const double* src = P.forward ? base + (u0 - P.e) : base + (P.L - u0 - kTile);
+#pragma unroll 8
+            for (int k = 0; k < kTilePer; ++k) {
+                const int j = k * kTileThreads + threadIdx.x;
+                const int i0 = P.forward ? j : kTile - 1 - j;
+                cp_async8(sm + (i0 & (kTilePer - 1)) * kTileLd + (i0 >> kTilePerLog2), src + j);
+            }
+            dcq[q] = dc;
+        } else {
+            for (int idx = threadIdx.x; idx < kTile; idx += kTileThreads) {
+                const long long u = u0 + idx;
+                sm[(idx & (kTilePer - 1)) * kTileLd + (idx >> kTilePerLog2)] = (u < P.L) ? sweep_read(P, base, dc, u) : 0.0;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // ---- zero-state pieces, aggregates, warp scans
+    double v[2][D];
+    for (int q = 0; q < n_here; ++q) {
+        double* sm = tile_sm2 + (size_t)q * kTilePer * kTileLd;
+        if (q == 0 && n_here == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        tile_sync<true>();
+        double z[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) z[k] = 0.0;
+        const double dq = dcq[q];
+#pragma unroll 8
+        for (int i = 0; i < kTilePer; ++i) df2t_step<D>(c, z, sm[i * kTileLd + threadIdx.x] - dq);
+        {
+            double w[D];
+            mv2<D>(ppow + (size_t)(kTileThreads - 1 - threadIdx.x) * 4, z, w);
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) w[k] += __shfl_xor_sync(0xffffffffu, w[k], off);
+                if (lane == 0) red[warp][k] = w[k];
+            }
+        }
+        tile_sync<true>();
+        if (threadIdx.x == 0) {
+            double e[2] = {0.0, 0.0};
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                double acc = 0.0;
+                for (int r = 0; r < kTileThreads / 32; ++r) acc += red[r][k];
+                e[k] = acc;
+            }
+            st_rec(S.rec + rec0 + tile0 + q, e[0], e[1]);
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) v[q][k] = z[k];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            double o[D], t[D];
+#pragma unroll
+            for (int r = 0; r < D; ++r) o[r] = __shfl_up_sync(0xffffffffu, v[q][r], 1 << k);
+            mv2<D>(ppow + (size_t)(1 << k) * 4, o, t);
+            if (lane >= (1 << k)) {
+#pragma unroll
+                for (int r = 0; r < D; ++r) v[q][r] += t[r];
+            }
+        }
+        if (lane == 31) {
+#pragma unroll
+            for (int r = 0; r < D; ++r) wtot[q][warp][r] = v[q][r];
+        }
+    }
+    // ---- true states, outputs
+    double* ob = P.out + (long long)s * P.out_sig_stride;
+    const long long n = P.L - 2 * (long long)P.e;
+    for (int q = 0; q < n_here; ++q) {
+        double* sm = tile_sm2 + (size_t)q * kTilePer * kTileLd;
+        if (q == 0) asm volatile("bar.sync 2, %0;" ::"n"(kFusedThreads) : "memory");      // sin_sh[q] is known (and wtot[q] complete)
+        else asm volatile("bar.sync 3, %0;" ::"n"(kFusedThreads) : "memory");
+        double W[D];
+#pragma unroll
+        for (int r = 0; r < D; ++r) W[r] = 0.0;
+        for (int j = 0; j < warp; ++j) {
+            double t[D];
+            mv2<D>(ppow + (size_t)32 * 4, W, t);
+#pragma unroll
+            for (int r = 0; r < D; ++r) W[r] = t[r] + wtot[q][j][r];
+        }
+        double sin_[D], st[D], e2[D];
+#pragma unroll
+        for (int r = 0; r < D; ++r) sin_[r] = sin_sh[q][r];
+        mv2<D>(ppow + (size_t)threadIdx.x * 4, sin_, st);
+        mv2<D>(ppow + (size_t)lane * 4, W, e2);
+#pragma unroll
+        for (int r = 0; r < D; ++r) {
+            const double prev = __shfl_up_sync(0xffffffffu, v[q][r], 1);
+            st[r] += e2[r] + (lane ? prev : 0.0);
+        }
+        const double dq = dcq[q];
+#pragma unroll 8
+        for (int i = 0; i < kTilePer; ++i) {
+            double* slot = sm + i * kTileLd + threadIdx.x;
+            *slot = df2t_step<D>(c, st, *slot - dq);
+        }
+        tile_sync<true>();
+        const long long u0 = (tile0 + q) * kTile;
+        if (u0 + kTile <= P.L && (P.forward || (P.L - u0 - kTile - P.e >= 0 && P.L - 1 - u0 - P.e < n))) {
+#pragma unroll 4
+            for (int it = 0; it < kTilePer; ++it) {
+                const int idx = it * kTileThreads + threadIdx.x;
+                const double y = sm[(idx & (kTilePer - 1)) * kTileLd + (idx >> kTilePerLog2)];
+                if (P.forward) ob[u0 + idx] = y;
+                else ob[P.L - 1 - (u0 + idx) - P.e] = y;
+            }
+        } else {
+            for (int idx = threadIdx.x; idx < kTile; idx += kTileThreads) {
+                const long long u = u0 + idx;
+                if (u >= P.L) break;
+                const double y = sm[(idx & (kTilePer - 1)) * kTileLd + (idx >> kTilePerLog2)];
+                if (P.forward) {
+                    ob[u] = y;
+                } else {
+                    const long long t = P.L - 1 - u - P.e;
+                    if (t >= 0 && t < n) ob[t] = y;
+                }
+            }
+        }
+    }
+}
+
+#endif  // HS_EXPERIMENT (two-tile pipelined sweep)
 
 // per-signal mean in two deterministic stages: kMeanParts CTAs per signal reduce contiguous slices (fixed tree order),
 // one more CTA per signal adds the partials in index order.
@@ -765,6 +953,21 @@ static int run_sweep_fused(IirPass P, const IirCoef& c, const IirCoef& ct, const
     }
     const long long ctas = n_tiles * P.n_sig;
     if (ctas > 0x7fffffffLL) return set_error(HS_ERR_UNSUPPORTED, "filtfilt: too many tiles");
+#ifdef HS_EXPERIMENT
+    static const int two_tiles = exp_env_int("HS_IIR_TWO_TILES", 0);
+    if (two_tiles) {
+        static bool attr2_done[3] = {false, false, false};
+        if (!attr2_done[D]) {
+            if (cudaFuncSetAttribute(iir_tile_fused2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem)) != cudaSuccess)
+                return set_error(HS_ERR_CUDA, "filtfilt: cannot reserve %zu B shared memory", 2 * smem);
+            cudaFuncSetAttribute(iir_tile_fused2_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            attr2_done[D] = true;
+        }
+        const long long pairs = (n_tiles + 1) / 2 * P.n_sig;
+        iir_tile_fused2_kernel<D><<<(unsigned)pairs, kFusedThreads, 2 * smem, st>>>(P, c, ct, d_ppow, S);
+        return check_launch("iir_tile_fused2_kernel");
+    }
+#endif
     iir_tile_fused_kernel<D><<<(unsigned)ctas, kFusedThreads, smem, st>>>(P, c, ct, d_ppow, S);
     return check_launch("iir_tile_fused_kernel");
 }
